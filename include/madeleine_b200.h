@@ -1,0 +1,141 @@
+/*
+ * madeleine_b200 — C ABI of the B200-native (sm_100a) MADELEINE hot path.
+ *
+ * The reference (mahmoodlab/MADELEINE) is pure Python/PyTorch and has no FFI of its own; the entry points below
+ * are what a binding for its hot path calls instead of the torch ops cited on each function (file:line under
+ * /root/reference).  Host code (madeleine_b200/ops.py, or the ctypes stub in INTEGRATION.md) loads
+ * libmadeleine_b200.so and passes raw device pointers.
+ *
+ * Conventions
+ *   - every function returns 0 on success; non-zero means failure and mdl_last_error() describes it (thread-local);
+ *   - all pointers are DEVICE pointers unless named host_*; the library never allocates or frees device memory
+ *     and keeps no global mutable state besides cached function attributes;
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, nothing synchronises;
+ *   - "planes": an fp32 matrix held as bf16 hi plane followed (plane_stride elements later) by a bf16 lo plane,
+ *     x ~= hi + lo.  nplanes/nsplit = 2/3 gives fp32-grade products on the bf16 tensor pipe, 1/1 plain bf16;
+ *   - token rows are bag-packed: bag r owns rows [cu_seqlens[r], cu_seqlens[r+1]).
+ */
+#ifndef MADELEINE_B200_H
+#define MADELEINE_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* mdl_last_error(void);
+/* Library/ABI version and the compute capability the kernels were built for (100 = sm_100a). */
+int mdl_version(void);
+int mdl_built_arch(void);
+
+/* ---- operand preparation ---------------------------------------------------------------------------------- */
+/* fp32 [rows, cols] (row stride ld) -> bf16 planes.  Replaces the implicit autocast casts of torch.amp.autocast
+ * (madeleine/utils/trainer.py:108). */
+int mdl_split_planes(const float* x, long long rows, int cols, long long ld, void* planes, long long plane_stride,
+                     int nplanes, void* stream);
+/* planes[i] = split(src[idx[i]]): weight packing (row permutation to head-major = einops rearrange
+ * 'b t (e c) -> b t e c' at Model.py:396, transposes for dgrad, gate interleave for abmil.py:49-52). */
+int mdl_gather_split(const float* src, const int* idx, long long n, void* planes, long long plane_stride, int nplanes,
+                     void* stream);
+int mdl_gather_f32(const float* src, const int* idx, long long n, float* dst, void* stream);
+int mdl_scatter_f32(const float* src, const int* idx, long long n, float* dst, int accumulate, void* stream);
+int mdl_row2bag(const int* cu_seqlens, int n_bags, int* row2bag, long long rows, void* stream);
+
+/* ---- tcgen05 GEMMs ------------------------------------------------------------------------------------------ */
+/* out[M,N] = A[M,K] * B[N,K]^T + bias[n] + rowbias[row2bag[m], n]   (nn.Linear forward, Model.py:351,355,359,
+ * 80-83, and every dgrad with a pre-transposed B).  A's k offset is (n / grp_n_cols) * a_koff when grp_n_cols > 0
+ * (per-head operand slabs).  bias / rowbias / row2bag may be NULL. */
+int mdl_gemm_nt(const void* a_planes, long long a_rows, long long a_cols, long long lda, long long a_plane_stride,
+                const void* b_planes, long long b_rows, long long b_cols, long long ldb, long long b_plane_stride,
+                float* out, long long ldc, int M, int N, int K, int nsplit, int grp_n_cols, int a_koff,
+                const float* bias, const float* rowbias, const int* row2bag, void* stream);
+/* Gated-attention scores of all heads in one launch (BatchedABMIL.forward, abmil.py:49-52; head loop Model.py:406-409):
+ * logits[m,h] = sum_j tanh(x_h Wa_h^T + ba)_j * sigmoid(x_h Wb_h^T + bb)_j * wc_hj + bc_h, x_h = A[:, h*512:(h+1)*512].
+ * b_planes = packed [n_heads*4][128 Wa rows | 128 Wb rows][512].  gate_a/gate_b (fp16 [M, n_heads*512]) may be NULL. */
+int mdl_gemm_gated(const void* a_planes, long long a_rows, long long a_cols, long long lda, long long a_plane_stride,
+                   const void* b_planes, long long b_plane_stride, int M, int n_heads, int nsplit,
+                   const float* ba, const float* bb, const float* wc, const float* bc,
+                   float* logits, void* gate_a, void* gate_b, float drop_p, unsigned long long seed, void* stream);
+/* out[M,N] += sum_t A[t, m]^T B[t, n]  (weight gradients; split over tokens, fp32 red.add).  B's column offset is
+ * (m / grp_m_rows) * b_coff when grp_m_rows > 0.  ksplit <= 0 picks a split automatically. */
+int mdl_gemm_tn_accum(const void* a_planes, long long a_cols, long long lda, long long a_plane_stride,
+                      const void* b_planes, long long b_cols, long long ldb, long long b_plane_stride,
+                      long long tokens, float* out, long long ldc, int M, int N, int nsplit,
+                      int grp_m_rows, int b_coff, int ksplit, void* stream);
+/* CUDA-core cross-checks of the two GEMM shapes above (tests only; never on the product path). */
+int mdl_gemm_nt_simt(const void* a_planes, long long lda, long long a_plane_stride, const void* b_planes, long long ldb,
+                     long long b_plane_stride, float* out, long long ldc, int M, int N, int K, int nsplit, void* stream);
+int mdl_gemm_tn_simt(const void* a_planes, long long lda, long long a_plane_stride, const void* b_planes, long long ldb,
+                     long long b_plane_stride, long long tokens, float* out, long long ldc, int M, int N, int nsplit,
+                     void* stream);
+
+/* ---- LayerNorm + GELU (+dropout) ------------------------------------------------------------------------------ */
+/* nn.LayerNorm -> nn.GELU -> nn.Dropout of ABMILEmbedder.pre_attn (Model.py:352-354, 356-358, 360-362). */
+int mdl_ln_gelu_fwd(const float* z, long long M, int C, const float* gamma, const float* beta, float eps,
+                    float drop_p, unsigned long long seed, unsigned stream_id,
+                    void* planes, long long plane_stride, int nplanes, float* mean, float* rstd, void* stream);
+/* Backward of the above; dh = dh_a + dh_b + sum_v pool_p_v[m, head] * pool_dS_v[pool_seg_v[m], c] (any may be NULL).
+ * Accumulates dgamma, dbeta and the preceding Linear's bias grad dbias (all [C], caller zero-fills). */
+int mdl_ln_gelu_bwd(const float* z, long long M, int C, const float* gamma, const float* beta, const float* mean,
+                    const float* rstd, const float* dh_a, const float* dh_b,
+                    const float* pool_p0, const float* pool_dS0, const int* pool_seg0,
+                    const float* pool_p1, const float* pool_dS1, const int* pool_seg1, int n_heads,
+                    float drop_p, unsigned long long seed, unsigned stream_id,
+                    void* dz_planes, long long plane_stride, int nplanes,
+                    float* dgamma, float* dbeta, float* dbias, void* stream);
+/* Backward of the gate nonlinearities of mdl_gemm_gated; dpre planes [M, n_heads*1024] in packed gate order. */
+int mdl_gate_bwd(const void* gate_a, const void* gate_b, const float* dlogit, const float* wc, long long M, int n_heads,
+                 float drop_p, unsigned long long seed, void* dpre_planes, long long plane_stride, int nplanes,
+                 float* dba, float* dbb, float* dwc, float* dbc, void* stream);
+
+/* ---- attention pooling (the HBM-bound kernel) ---------------------------------------------------------------- */
+/* softmax over tokens + weighted sum (abmil.py:55, Model.py:416-417); activation 0 softmax, 1 leaky_relu, 2 relu,
+ * 3 sigmoid (abmil.py:54-63).  out [n_bags, n_heads*head_dim] head-major; attn_p [tokens, n_heads] optional.
+ * tok_idx (optional) gathers rows: segment r pools rows tok_idx[cu[r] .. cu[r+1]) (n_views=3, Model.py:427-437). */
+int mdl_pool_fwd(const void* x_planes, long long plane_stride, int nplanes, const float* logits, const int* cu_seqlens,
+                 const int* tok_idx, int n_bags, long long total_tokens, int n_heads, int head_dim,
+                 float* out, float* attn_p, int activation, int tsplit, void* stream);
+int mdl_pool_bwd_dlogit(const void* x_planes, long long plane_stride, int nplanes, const float* dS, const float* S,
+                        const float* attn_p, const int* cu_seqlens, const int* tok_idx, int n_bags,
+                        long long total_tokens, int n_heads, int head_dim, float* dlogit, int accumulate,
+                        const float* logits, int activation, int tsplit, void* stream);
+/* head-major planes -> fp32 [M, head_dim, n_heads] (reference channel order), ABMILEmbedder(return_preattn_feats). */
+int mdl_planes_to_ref_order(const void* x_planes, long long plane_stride, int nplanes, long long M, int n_heads,
+                            int head_dim, float* out, void* stream);
+
+/* ---- slide-level projector, stain encodings -------------------------------------------------------------------- */
+/* MADELEINE.projector (Model.py:88-91,145) on [n_bags, 2048]: exact fp32. */
+int mdl_skinny_linear_fwd(const float* X, const float* W, const float* b, int R, int C, int O, float* Y, void* stream);
+int mdl_skinny_linear_bwd(const float* dY, const float* X, const float* W, int R, int C, int O,
+                          float* dX, float* dW, float* db, void* stream);
+/* Stain encodings (Model.py:125-132) folded into a per-bag bias: rowbias[r,:] = W1[:, d_in:] emb[code[r]]. */
+int mdl_stain_rowbias(const float* emb, const int* code, const float* w1, int ldw, int d_in, int se_dim, int n_out,
+                      int R, float* rowbias, void* stream);
+int mdl_bag_colsum_planes(const void* planes, long long plane_stride, int nplanes, int C, const int* cu_seqlens,
+                          int n_bags, float* out, void* stream);
+int mdl_stain_rowbias_bwd(const float* G, const float* emb, const int* code, const float* w1, int ldw, int d_in,
+                          int se_dim, int n_out, int R, float* dw1, float* demb, void* stream);
+int mdl_colsum_f32(const float* x, long long M, int C, float* out, void* stream);
+
+/* ---- losses ------------------------------------------------------------------------------------------------------ */
+/* InfoNCE with in-batch negatives (madeleine/utils/loss.py:111-127). reduction: 0 none, 1 mean, 2 sum. */
+int mdl_infonce_fwd(const float* q, const float* k, int m, int D, float temperature, int symmetric, int reduction,
+                    float* qn, float* kn, float* L, float* lse_r, float* lse_c, float* nll_r, float* nll_c,
+                    float* loss, void* stream);
+int mdl_infonce_bwd(const float* q, const float* k, int m, int D, float temperature,
+                    const float* qn, const float* kn, const float* L, const float* lse_r, const float* lse_c,
+                    const float* w_r, const float* w_c, float* G, float* dq, float* dk, void* stream);
+/* Graph-OT local loss, forward and backward in one call (GOT, madeleine/utils/loss.py:278-301 with
+ * cost_matrix_batch_torch :162-176, IPOT :179-207, cos_batch_torch :210-233, GW :236-275).
+ * v, q [m, n, D] (already token-subsampled); loss = sum_b (wd_b + gwd_b); dv, dq = d loss / d v, q.
+ * extrema (host-visible optional hook for sharded runs): 6 floats {min,max} x {cross, intra_v, intra_q}; when
+ * use_external_extrema != 0 the thresholds use these instead of the local batch extrema (quirk Q5 under sharding). */
+long long mdl_got_workspace_bytes(int m, int n, int D);
+int mdl_got_max_tokens(void);
+int mdl_got_extrema(const float* v, const float* q, int m, int n, int D, void* workspace, float* extrema, void* stream);
+int mdl_got_fwd_bwd(const float* v, const float* q, int m, int n, int D, void* workspace, const float* extrema,
+                    float* loss, float* wd, float* gwd, float* dv, float* dq, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MADELEINE_B200_H */

@@ -1,0 +1,131 @@
+"""ctypes binding of libmadeleine_b200.so (C ABI declared in include/madeleine_b200.h).
+
+There is no CPU or PyTorch fallback: if the shared library cannot be loaded, or a call fails, a RuntimeError is
+raised.  The library is built in-tree by ``madeleine_b200.build`` (nvcc, sm_100a) and shipped next to this file.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmadeleine_b200.so")
+
+_lock = threading.Lock()
+_lib = None
+
+c_p = ctypes.c_void_p
+c_i = ctypes.c_int
+c_ll = ctypes.c_longlong
+c_f = ctypes.c_float
+c_ull = ctypes.c_ulonglong
+c_u = ctypes.c_uint
+
+# name -> argtypes (restype is int unless listed in _RESTYPES)
+SIGNATURES = {
+    "mdl_version": [],
+    "mdl_built_arch": [],
+    "mdl_split_planes": [c_p, c_ll, c_i, c_ll, c_p, c_ll, c_i, c_p],
+    "mdl_gather_split": [c_p, c_p, c_ll, c_p, c_ll, c_i, c_p],
+    "mdl_gather_f32": [c_p, c_p, c_ll, c_p, c_p],
+    "mdl_scatter_f32": [c_p, c_p, c_ll, c_p, c_i, c_p],
+    "mdl_row2bag": [c_p, c_i, c_p, c_ll, c_p],
+    "mdl_gemm_nt": [c_p, c_ll, c_ll, c_ll, c_ll, c_p, c_ll, c_ll, c_ll, c_ll, c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_i,
+                    c_p, c_p, c_p, c_p],
+    "mdl_gemm_gated": [c_p, c_ll, c_ll, c_ll, c_ll, c_p, c_ll, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_f,
+                       c_ull, c_p],
+    "mdl_gemm_tn_accum": [c_p, c_ll, c_ll, c_ll, c_p, c_ll, c_ll, c_ll, c_ll, c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    "mdl_gemm_nt_simt": [c_p, c_ll, c_ll, c_p, c_ll, c_ll, c_p, c_ll, c_i, c_i, c_i, c_i, c_p],
+    "mdl_gemm_tn_simt": [c_p, c_ll, c_ll, c_p, c_ll, c_ll, c_ll, c_p, c_ll, c_i, c_i, c_i, c_p],
+    "mdl_ln_gelu_fwd": [c_p, c_ll, c_i, c_p, c_p, c_f, c_f, c_ull, c_u, c_p, c_ll, c_i, c_p, c_p, c_p],
+    "mdl_ln_gelu_bwd": [c_p, c_ll, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_f, c_ull, c_u,
+                        c_p, c_ll, c_i, c_p, c_p, c_p, c_p],
+    "mdl_gate_bwd": [c_p, c_p, c_p, c_p, c_ll, c_i, c_f, c_ull, c_p, c_ll, c_i, c_p, c_p, c_p, c_p, c_p],
+    "mdl_pool_fwd": [c_p, c_ll, c_i, c_p, c_p, c_p, c_i, c_ll, c_i, c_i, c_p, c_p, c_i, c_i, c_p],
+    "mdl_pool_bwd_dlogit": [c_p, c_ll, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_ll, c_i, c_i, c_p, c_i, c_p, c_i, c_i, c_p],
+    "mdl_planes_to_ref_order": [c_p, c_ll, c_i, c_ll, c_i, c_i, c_p, c_p],
+    "mdl_skinny_linear_fwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p],
+    "mdl_skinny_linear_bwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p],
+    "mdl_stain_rowbias": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p],
+    "mdl_bag_colsum_planes": [c_p, c_ll, c_i, c_i, c_p, c_i, c_p, c_p],
+    "mdl_stain_rowbias_bwd": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p],
+    "mdl_colsum_f32": [c_p, c_ll, c_i, c_p, c_p],
+    "mdl_infonce_fwd": [c_p, c_p, c_i, c_i, c_f, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
+    "mdl_infonce_bwd": [c_p, c_p, c_i, c_i, c_f, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
+    "mdl_got_workspace_bytes": [c_i, c_i, c_i],
+    "mdl_got_max_tokens": [],
+    "mdl_got_extrema": [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p],
+    "mdl_got_fwd_bwd": [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
+}
+_RESTYPES = {"mdl_got_workspace_bytes": c_ll}
+# functions that return a value rather than a status code
+_VALUE_FUNCS = {"mdl_version", "mdl_built_arch", "mdl_got_workspace_bytes", "mdl_got_max_tokens"}
+
+
+def exported_symbols():
+    """Every symbol include/madeleine_b200.h declares (kept in sync by tests/test_abi.py)."""
+    return ["mdl_last_error", *SIGNATURES.keys()]
+
+
+def load():
+    """Load (building first if the .so is absent and nvcc is present). Raises RuntimeError on failure."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            try:
+                from . import build as _build
+                _build.build()
+            except Exception as e:  # noqa: BLE001
+                raise RuntimeError(
+                    f"madeleine_b200: CUDA library {LIB_PATH} is missing and could not be built ({e}). "
+                    "There is no CPU fallback; run `python -m madeleine_b200.build`.") from e
+        try:
+            lib = ctypes.CDLL(LIB_PATH)
+        except OSError as e:
+            raise RuntimeError(f"madeleine_b200: cannot load {LIB_PATH}: {e}. There is no CPU fallback.") from e
+        lib.mdl_last_error.restype = ctypes.c_char_p
+        lib.mdl_last_error.argtypes = []
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPES.get(name, c_i)
+        _lib = lib
+    return _lib
+
+
+def _conv(a):
+    if a is None:
+        return None
+    if isinstance(a, torch.Tensor):
+        return a.data_ptr()
+    return a
+
+
+def call(name, *args):
+    """Call a status-returning entry point with tensors converted to device pointers; raise on failure."""
+    lib = load()
+    rc = getattr(lib, name)(*[_conv(a) for a in args])
+    if name in _VALUE_FUNCS:
+        return rc
+    if rc != 0:
+        msg = lib.mdl_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"madeleine_b200.{name} failed (code {rc}): {msg}")
+    return 0
+
+
+def stream_ptr(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"madeleine_b200: {what} must live on a CUDA device (got {t.device}). The B200 path has no CPU fallback; "
+            "use the reference implementation for CPU execution.")

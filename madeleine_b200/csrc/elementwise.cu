@@ -1,0 +1,548 @@
+// HBM-bound elementwise / row-normalisation kernels around the tcgen05 GEMMs:
+//   split planes (fp32 -> bf16 hi/lo), gather+split weight packing, LayerNorm+GELU(+dropout) forward and backward,
+//   gated-attention backward, per-bag column sums, small index utilities.
+// All are coalesced, 16-byte vectorised, grid-stride over rows with grids sized as a multiple of the SM count.
+#include "common.cuh"
+#include "madeleine_b200.h"
+
+namespace mdl {
+
+static inline int grid_for(long long work_items, int per_block, int max_blocks_per_sm = 8) {
+    long long b = (work_items + per_block - 1) / per_block;
+    long long cap = (long long)kNumSMs * max_blocks_per_sm;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fp32 [rows, cols] (row stride ld) -> bf16 planes [nplanes][rows][cols]
+// ---------------------------------------------------------------------------------------------------
+__global__ void split_planes_kernel(const float* __restrict__ x, long long rows, int cols, long long ld,
+                                    __nv_bfloat16* __restrict__ planes, long long plane_stride, int nplanes) {
+    const int vec_per_row = cols >> 2;
+    const long long total = rows * vec_per_row;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / vec_per_row;
+        const int c = (int)(i - r * vec_per_row) << 2;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ld + c));
+        __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+        split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1); split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
+        const long long o = r * cols + c;
+        *reinterpret_cast<uint2*>(planes + o) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+        if (nplanes > 1)
+            *reinterpret_cast<uint2*>(planes + plane_stride + o) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+    }
+}
+
+// packed[i] = split(src[idx[i]])  (weight packing: permutations / transposes expressed as an index map)
+__global__ void gather_split_kernel(const float* __restrict__ src, const int* __restrict__ idx, long long n,
+                                    __nv_bfloat16* __restrict__ planes, long long plane_stride, int nplanes) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        __nv_bfloat16 h, l;
+        split_bf16(__ldg(src + __ldg(idx + i)), h, l);
+        planes[i] = h;
+        if (nplanes > 1) planes[plane_stride + i] = l;
+    }
+}
+__global__ void gather_f32_kernel(const float* __restrict__ src, const int* __restrict__ idx, long long n, float* __restrict__ dst) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = __ldg(src + __ldg(idx + i));
+}
+// dst[idx[i]] (+)= src[i]; idx is injective so there are no write conflicts.
+__global__ void scatter_f32_kernel(const float* __restrict__ src, const int* __restrict__ idx, long long n, float* __restrict__ dst, int accumulate) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int j = __ldg(idx + i);
+        dst[j] = accumulate ? dst[j] + src[i] : src[i];
+    }
+}
+
+__global__ void row2bag_kernel(const int* __restrict__ cu, int n_bags, int* __restrict__ row2bag, long long rows) {
+    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < rows; m += (long long)gridDim.x * blockDim.x) {
+        int lo = 0, hi = n_bags;  // find bag with cu[bag] <= m < cu[bag+1]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(cu + mid) <= m) lo = mid; else hi = mid;
+        }
+        row2bag[m] = lo;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// LayerNorm + exact GELU (+ dropout) forward.  One warp owns a 512-column segment of a row (16 values per lane,
+// 4 x float4, columns seg*512 + j*128 + lane*4); C/512 warps cooperate on a row.
+// ---------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256)
+ln_gelu_fwd_kernel(const float* __restrict__ z, long long M, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   float eps, float drop_p, unsigned long long seed, unsigned stream_id,
+                   __nv_bfloat16* __restrict__ planes, long long plane_stride, int nplanes,
+                   float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+    constexpr int WPR = C / 512;          // warps per row
+    constexpr int ROWS = 8 / WPR;         // rows per block iteration
+    __shared__ float red[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int seg = warp % WPR, rib = warp / WPR;
+    float g[16], b[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = seg * 512 + j * 128 + lane * 4;
+        const float4 gv = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(beta + c));
+        g[4 * j] = gv.x; g[4 * j + 1] = gv.y; g[4 * j + 2] = gv.z; g[4 * j + 3] = gv.w;
+        b[4 * j] = bv.x; b[4 * j + 1] = bv.y; b[4 * j + 2] = bv.z; b[4 * j + 3] = bv.w;
+    }
+    const long long iters = (M + (long long)gridDim.x * ROWS - 1) / ((long long)gridDim.x * ROWS);
+    for (long long it = 0; it < iters; ++it) {
+        const long long m = (it * gridDim.x + blockIdx.x) * ROWS + rib;
+        const bool ok = m < M;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) t = __ldg(reinterpret_cast<const float4*>(z + m * C + seg * 512 + j * 128 + lane * 4));
+            v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s += v[i];
+        s = warp_sum(s);
+        if constexpr (WPR > 1) {
+            __syncthreads();
+            if (lane == 0) red[warp] = s;
+            __syncthreads();
+            s = 0.f;
+#pragma unroll
+            for (int w = 0; w < WPR; ++w) s += red[rib * WPR + w];
+        }
+        const float mu = s * (1.f / C);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { const float d = v[i] - mu; q = fmaf(d, d, q); }
+        q = warp_sum(q);
+        if constexpr (WPR > 1) {
+            __syncthreads();
+            if (lane == 0) red[warp] = q;
+            __syncthreads();
+            q = 0.f;
+#pragma unroll
+            for (int w = 0; w < WPR; ++w) q += red[rib * WPR + w];
+        }
+        const float rstd = rsqrtf(q * (1.f / C) + eps);
+        if (ok) {
+            if (seg == 0 && lane == 0) { mean_out[m] = mu; rstd_out[m] = rstd; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = seg * 512 + j * 128 + lane * 4;
+                __nv_bfloat16 h[4], l[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float y = gelu_erf((v[4 * j + i] - mu) * rstd * g[4 * j + i] + b[4 * j + i]);
+                    y *= dropout_scale(drop_p, seed, stream_id, (uint64_t)m * C + c + i);
+                    split_bf16(y, h[i], l[i]);
+                }
+                const long long o = m * C + c;
+                *reinterpret_cast<uint2*>(planes + o) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+                if (nplanes > 1)
+                    *reinterpret_cast<uint2*>(planes + plane_stride + o) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// LayerNorm + GELU (+dropout) backward.
+//   dh = dh_a + dh_b + sum_v p_v[m, head(c)] * dS_v[seg_v(m), c]     (the last term fuses the pooling backward)
+//   dy = dh * dropout_scale * gelu'(y),   y = xhat*gamma + beta,  xhat = (z - mean) * rstd
+//   dz = rstd * (dy*gamma - mean_c(dy*gamma) - xhat * mean_c(dy*gamma*xhat))
+// Writes dz as bf16 planes (operand of the following dgrad / wgrad GEMMs) and accumulates the column sums
+// dgamma += dy*xhat, dbeta += dy, dbias += dz with one atomicAdd per column per block.
+// ---------------------------------------------------------------------------------------------------
+struct PoolTerm {
+    const float* p;        // [M, H] attention probabilities of this view (0 outside the view)
+    const float* dS;       // [n_seg, C]
+    const int* row2seg;    // [M]
+};
+
+template <int C>
+__global__ void __launch_bounds__(256)
+ln_gelu_bwd_kernel(const float* __restrict__ z, long long M, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   const float* __restrict__ mean, const float* __restrict__ rstd_in,
+                   const float* __restrict__ dh_a, const float* __restrict__ dh_b, PoolTerm pt0, PoolTerm pt1, int n_heads,
+                   float drop_p, unsigned long long seed, unsigned stream_id,
+                   __nv_bfloat16* __restrict__ dz_planes, long long plane_stride, int nplanes,
+                   float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias) {
+    constexpr int WPR = C / 512;
+    constexpr int ROWS = 8 / WPR;
+    __shared__ float red[2][8];
+    __shared__ float colacc[8][512];  // [warp][lane*16 + i] partial column sums, reused per array
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int seg = warp % WPR, rib = warp / WPR;
+    const int e_per_head = C / n_heads;
+    float g[16], b[16], acc_g[16], acc_b[16], acc_z[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = seg * 512 + j * 128 + lane * 4;
+        const float4 gv = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(beta + c));
+        g[4 * j] = gv.x; g[4 * j + 1] = gv.y; g[4 * j + 2] = gv.z; g[4 * j + 3] = gv.w;
+        b[4 * j] = bv.x; b[4 * j + 1] = bv.y; b[4 * j + 2] = bv.z; b[4 * j + 3] = bv.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { acc_g[i] = 0.f; acc_b[i] = 0.f; acc_z[i] = 0.f; }
+
+    const long long iters = (M + (long long)gridDim.x * ROWS - 1) / ((long long)gridDim.x * ROWS);
+    for (long long it = 0; it < iters; ++it) {
+        const long long m = (it * gridDim.x + blockIdx.x) * ROWS + rib;
+        const bool ok = m < M;
+        float xh[16], dy[16];
+        float mu = 0.f, rs = 0.f;
+        if (ok) { mu = __ldg(mean + m); rs = __ldg(rstd_in + m); }
+        int s0 = 0, s1 = 0;
+        if (ok && pt0.p != nullptr) s0 = __ldg(pt0.row2seg + m);
+        if (ok && pt1.p != nullptr) s1 = __ldg(pt1.row2seg + m);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = seg * 512 + j * 128 + lane * 4;
+            float4 zv = make_float4(0.f, 0.f, 0.f, 0.f), d = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) {
+                zv = __ldg(reinterpret_cast<const float4*>(z + m * C + c));
+                if (dh_a != nullptr) d = __ldg(reinterpret_cast<const float4*>(dh_a + m * C + c));
+                if (dh_b != nullptr) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(dh_b + m * C + c));
+                    d.x += t.x; d.y += t.y; d.z += t.z; d.w += t.w;
+                }
+                const int head = c / e_per_head;
+                if (pt0.p != nullptr) {
+                    const float pw = __ldg(pt0.p + m * n_heads + head);
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(pt0.dS + (long long)s0 * C + c));
+                    d.x = fmaf(pw, t.x, d.x); d.y = fmaf(pw, t.y, d.y); d.z = fmaf(pw, t.z, d.z); d.w = fmaf(pw, t.w, d.w);
+                }
+                if (pt1.p != nullptr) {
+                    const float pw = __ldg(pt1.p + m * n_heads + head);
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(pt1.dS + (long long)s1 * C + c));
+                    d.x = fmaf(pw, t.x, d.x); d.y = fmaf(pw, t.y, d.y); d.z = fmaf(pw, t.z, d.z); d.w = fmaf(pw, t.w, d.w);
+                }
+            }
+            const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
+            const float dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float x = (zz[i] - mu) * rs;
+                const float y = x * g[4 * j + i] + b[4 * j + i];
+                float t = dd[i] * gelu_erf_grad(y);
+                if (ok) t *= dropout_scale(drop_p, seed, stream_id, (uint64_t)m * C + c + i);
+                xh[4 * j + i] = x;
+                dy[4 * j + i] = ok ? t : 0.f;
+            }
+        }
+        float s1sum = 0.f, s2sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float dx = dy[i] * g[i];
+            s1sum += dx;
+            s2sum = fmaf(dx, xh[i], s2sum);
+            acc_g[i] = fmaf(dy[i], xh[i], acc_g[i]);
+            acc_b[i] += dy[i];
+        }
+        s1sum = warp_sum(s1sum);
+        s2sum = warp_sum(s2sum);
+        if constexpr (WPR > 1) {
+            __syncthreads();
+            if (lane == 0) { red[0][warp] = s1sum; red[1][warp] = s2sum; }
+            __syncthreads();
+            s1sum = 0.f; s2sum = 0.f;
+#pragma unroll
+            for (int w = 0; w < WPR; ++w) { s1sum += red[0][rib * WPR + w]; s2sum += red[1][rib * WPR + w]; }
+        }
+        const float m1 = s1sum * (1.f / C), m2 = s2sum * (1.f / C);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = seg * 512 + j * 128 + lane * 4;
+            __nv_bfloat16 h[4], l[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float dzv = ok ? rs * (dy[4 * j + i] * g[4 * j + i] - m1 - xh[4 * j + i] * m2) : 0.f;
+                acc_z[4 * j + i] += dzv;
+                split_bf16(dzv, h[i], l[i]);
+            }
+            if (ok) {
+                const long long o = m * C + c;
+                *reinterpret_cast<uint2*>(dz_planes + o) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+                if (nplanes > 1)
+                    *reinterpret_cast<uint2*>(dz_planes + plane_stride + o) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+            }
+        }
+    }
+    // column sums: combine the ROWS warps that own the same 512-column segment, then one atomic per column per block.
+    // One 16 KB staging buffer is reused for the three arrays.
+#pragma unroll 1
+    for (int a = 0; a < 3; ++a) {
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) colacc[warp][lane * 16 + i] = a == 0 ? acc_g[i] : (a == 1 ? acc_b[i] : acc_z[i]);
+        __syncthreads();
+        float* dst = a == 0 ? dgamma : (a == 1 ? dbeta : dbias);
+        // slot = lane*16 + 4*j + i  <->  column seg*512 + j*128 + lane*4 + i
+        for (int idx = threadIdx.x; idx < WPR * 512; idx += blockDim.x) {
+            const int s = idx / 512, slot = idx % 512;
+            const int ln = slot / 16, r = slot % 16, j = r / 4, i = r % 4;
+            const int c = s * 512 + j * 128 + ln * 4 + i;
+            float t = 0.f;
+#pragma unroll
+            for (int rr = 0; rr < ROWS; ++rr) t += colacc[rr * WPR + s][slot];
+            atomicAdd(dst + c, t);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Gated-attention backward (elementwise part).  gate_a/gate_b hold the (dropout-scaled) tanh / sigmoid outputs
+// as fp16 [M, H*512].  Produces d(pre-activation) as bf16 planes in the packed column order of the gated GEMM
+// (per head: 4 groups of [128 a-cols | 128 b-cols]) and the column sums d(ba), d(bb), d(wc), d(bc).
+// One block = one row per iteration; thread t owns gate columns [8t, 8t+8).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gate_bwd_kernel(const __half* __restrict__ gate_a, const __half* __restrict__ gate_b, const float* __restrict__ dlogit,
+                const float* __restrict__ wc, long long M, int n_heads, float drop_p, unsigned long long seed,
+                __nv_bfloat16* __restrict__ dpre, long long plane_stride, int nplanes,
+                float* __restrict__ dba, float* __restrict__ dbb, float* __restrict__ dwc, float* __restrict__ dbc) {
+    const int HC = n_heads * 512;            // gate columns per row
+    const int j0 = threadIdx.x * 8;          // requires HC == blockDim.x * 8  (n_heads = 4 -> 256 threads)
+    const int head = j0 / 512, jh = j0 % 512;
+    const int packed0 = head * 1024 + (jh / 128) * 256 + (jh % 128);  // a-part; b-part is +128
+    float w[8], s_a[8], s_b[8], s_w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { w[i] = __ldg(wc + j0 + i); s_a[i] = 0.f; s_b[i] = 0.f; s_w[i] = 0.f; }
+    float s_c = 0.f;
+    const float keep_inv = drop_p > 0.f ? (1.f - drop_p) : 1.f;
+    for (long long m = blockIdx.x; m < M; m += gridDim.x) {
+        const float dl = __ldg(dlogit + m * n_heads + head);
+        const uint4 ua = __ldg(reinterpret_cast<const uint4*>(gate_a + m * HC + j0));
+        const uint4 ub = __ldg(reinterpret_cast<const uint4*>(gate_b + m * HC + j0));
+        const __half2* ha = reinterpret_cast<const __half2*>(&ua);
+        const __half2* hb = reinterpret_cast<const __half2*>(&ub);
+        __nv_bfloat16 ah[8], al[8], bh[8], bl[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float2 fa = __half22float2(ha[i >> 1]);
+            const float2 fb = __half22float2(hb[i >> 1]);
+            const float ad = (i & 1) ? fa.y : fa.x;   // dropout-scaled gates
+            const float bd = (i & 1) ? fb.y : fb.x;
+            float sa = 1.f, sb = 1.f;
+            if (drop_p > 0.f) {
+                const uint64_t idx = (uint64_t)m * (uint64_t)HC + (uint64_t)(j0 + i);
+                sa = dropout_scale(drop_p, seed, 10u, idx);
+                sb = dropout_scale(drop_p, seed, 11u, idx);
+            }
+            const float a = ad * (sa != 0.f ? keep_inv : 0.f);  // undo the 1/(1-p) scaling where kept
+            const float b = bd * (sb != 0.f ? keep_inv : 0.f);
+            const float dA = dl * w[i];
+            const float dpa = dA * bd * sa * (1.f - a * a);
+            const float dpb = dA * ad * sb * b * (1.f - b);
+            s_a[i] += dpa; s_b[i] += dpb; s_w[i] = fmaf(dl, ad * bd, s_w[i]);
+            split_bf16(dpa, ah[i], al[i]);
+            split_bf16(dpb, bh[i], bl[i]);
+        }
+        if (threadIdx.x % 64 == 0) s_c += dl;  // one thread per head
+        const long long o = m * (long long)(n_heads * 1024) + packed0;
+        *reinterpret_cast<uint4*>(dpre + o) = make_uint4(pack_bf16x2(ah[0], ah[1]), pack_bf16x2(ah[2], ah[3]), pack_bf16x2(ah[4], ah[5]), pack_bf16x2(ah[6], ah[7]));
+        *reinterpret_cast<uint4*>(dpre + o + 128) = make_uint4(pack_bf16x2(bh[0], bh[1]), pack_bf16x2(bh[2], bh[3]), pack_bf16x2(bh[4], bh[5]), pack_bf16x2(bh[6], bh[7]));
+        if (nplanes > 1) {
+            *reinterpret_cast<uint4*>(dpre + plane_stride + o) = make_uint4(pack_bf16x2(al[0], al[1]), pack_bf16x2(al[2], al[3]), pack_bf16x2(al[4], al[5]), pack_bf16x2(al[6], al[7]));
+            *reinterpret_cast<uint4*>(dpre + plane_stride + o + 128) = make_uint4(pack_bf16x2(bl[0], bl[1]), pack_bf16x2(bl[2], bl[3]), pack_bf16x2(bl[4], bl[5]), pack_bf16x2(bl[6], bl[7]));
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        atomicAdd(dba + j0 + i, s_a[i]);
+        atomicAdd(dbb + j0 + i, s_b[i]);
+        atomicAdd(dwc + j0 + i, s_w[i]);
+    }
+    if (threadIdx.x % 64 == 0) atomicAdd(dbc + head, s_c);
+}
+
+// G[bag, c] = sum_{t in bag} (hi + lo)[t, c]  — per-bag column sums of a planes tensor (stain-encoding backward).
+__global__ void __launch_bounds__(128)
+bag_colsum_planes_kernel(const __nv_bfloat16* __restrict__ planes, long long plane_stride, int nplanes, int C,
+                         const int* __restrict__ cu, float* __restrict__ out) {
+    const int bag = blockIdx.y;
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c >= C) return;
+    const int t0 = cu[bag], t1 = cu[bag + 1];
+    float s = 0.f;
+    for (int t = t0; t < t1; ++t) {
+        float v = __bfloat162float(planes[(long long)t * C + c]);
+        if (nplanes > 1) v += __bfloat162float(planes[plane_stride + (long long)t * C + c]);
+        s += v;
+    }
+    out[(long long)bag * C + c] = s;
+}
+
+// rowbias[r, n] = sum_s emb[code[r], s] * W1[n, d_in + s]   (stain encodings folded into a per-bag bias)
+__global__ void stain_rowbias_kernel(const float* __restrict__ emb, const int* __restrict__ code, const float* __restrict__ w1,
+                                     int ldw, int d_in, int se_dim, int n_out, float* __restrict__ rowbias) {
+    const int r = blockIdx.x;
+    const float* e = emb + (long long)code[r] * se_dim;
+    for (int n = threadIdx.x; n < n_out; n += blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < se_dim; ++k) s = fmaf(__ldg(e + k), __ldg(w1 + (long long)n * ldw + d_in + k), s);
+        rowbias[(long long)r * n_out + n] = s;
+    }
+}
+// Backward of the per-bag bias: G [R, n_out] = per-bag column sums of dz1.
+//   dW1[n, d_in + s] += sum_r G[r, n] emb[code r, s];   demb[code r, s] += sum_n G[r, n] W1[n, d_in + s]
+__global__ void stain_rowbias_bwd_kernel(const float* __restrict__ G, const float* __restrict__ emb, const int* __restrict__ code,
+                                         const float* __restrict__ w1, int ldw, int d_in, int se_dim, int n_out, int R,
+                                         float* __restrict__ dw1, float* __restrict__ demb) {
+    // grid.x = n_out blocks for dW1 rows, then R blocks for demb rows
+    const int bid = blockIdx.x;
+    if (bid < n_out) {
+        const int n = bid;
+        for (int s = threadIdx.x; s < se_dim; s += blockDim.x) {
+            float acc = 0.f;
+            for (int r = 0; r < R; ++r) acc = fmaf(__ldg(G + (long long)r * n_out + n), __ldg(emb + (long long)code[r] * se_dim + s), acc);
+            dw1[(long long)n * ldw + d_in + s] += acc;
+        }
+    } else {
+        const int r = bid - n_out;
+        for (int s = threadIdx.x; s < se_dim; s += blockDim.x) {
+            float acc = 0.f;
+            for (int n = 0; n < n_out; ++n) acc = fmaf(__ldg(G + (long long)r * n_out + n), __ldg(w1 + (long long)n * ldw + d_in + s), acc);
+            atomicAdd(demb + (long long)code[r] * se_dim + s, acc);
+        }
+    }
+}
+
+// out[c] (+)= sum_m x[m, c]  for a small fp32 matrix (bias grads of the skinny projections).
+__global__ void colsum_f32_kernel(const float* __restrict__ x, long long M, int C, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float s = 0.f;
+    for (long long m = blockIdx.y; m < M; m += gridDim.y) s += __ldg(x + m * C + c);
+    atomicAdd(out + c, s);
+}
+
+}  // namespace mdl
+
+using namespace mdl;
+
+extern "C" {
+
+int mdl_split_planes(const float* x, long long rows, int cols, long long ld, void* planes, long long plane_stride, int nplanes, void* stream) {
+    MDL_REQUIRE(cols % 4 == 0 && ld % 4 == 0, "split_planes: cols and ld must be multiples of 4");
+    if (rows == 0) return 0;
+    const long long total = rows * (cols / 4);
+    split_planes_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ld, (__nv_bfloat16*)planes, plane_stride, nplanes);
+    MDL_CHECK_LAUNCH();
+    return 0;
+}
+
+int mdl_gather_split(const float* src, const int* idx, long long n, void* planes, long long plane_stride, int nplanes, void* stream) {
+    if (n == 0) return 0;
+    gather_split_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, idx, n, (__nv_bfloat16*)planes, plane_stride, nplanes);
+    MDL_CHECK_LAUNCH();
+    return 0;
+}
+
+int mdl_gather_f32(const float* src, const int* idx, long long n, float* dst, void* stream) {
+    if (n == 0) return 0;
+    gather_f32_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, idx, n, dst);
+    MDL_CHECK_LAUNCH();
+    return 0;
+}
+
+int mdl_scatter_f32(const float* src, const int* idx, long long n, float* dst, int accumulate, void* stream) {
+    if (n == 0) return 0;
+    scatter_f32_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, idx, n, dst, accumulate);
+    MDL_CHECK_LAUNCH();
+    return 0;
+}
+
+int mdl_row2bag(const int* cu_seqlens, int n_bags, int* row2bag, long long rows, void* stream) {
+    if (rows == 0) return 0;
+    row2bag_kernel<<<grid_for(rows, 256), 256, 0, (cudaStream_t)stream>>>(cu_seqlens, n_bags, row2bag, rows);
+    MDL_CHECK_LAUNCH();
+    return 0;
+}
+
+int mdl_ln_gelu_fwd(const float* z, long long M, int C, const float* gamma, const float* beta, float eps,
+                    float drop_p, unsigned long long seed, unsigned stream_id,
+                    void* planes, long long plane_stride, int nplanes, float* mean, float* rstd, void* stream) {
+    MDL_REQUIRE(C == 512 || C == 2048, "ln_gelu_fwd: C must be 512 or 2048 (got %d)", C);
+    if (M == 0) return 0;
+    const int rows_per_block = C == 512 ? 8 : 2;
+    const int grid = grid_for(M, rows_per_block, 8);
+    if (C == 512)
+        ln_gelu_fwd_kernel<512><<<grid, 256, 0, (cudaStream_t)stream>>>(z, M, gamma, beta, eps, drop_p, seed, stream_id, (__nv_bfloat16*)planes, plane_stride, nplanes, mean, rstd);
+    else
+        ln_gelu_fwd_kernel<2048><<<grid, 256, 0, (cudaStream_t)stream>>>(z, M, gamma, beta, eps, drop_p, seed, stream_id, (__nv_bfloat16*)planes, plane_stride, nplanes, mean, rstd);
+    MDL_CHECK_LAUNCH();
+    return 0;
+}
+
+int mdl_ln_gelu_bwd(const float* z, long long M, int C, const float* gamma, const float* beta, const float* mean, const float* rstd,
+                    const float* dh_a, const float* dh_b,
+                    const float* pool_p0, const float* pool_dS0, const int* pool_seg0,
+                    const float* pool_p1, const float* pool_dS1, const int* pool_seg1, int n_heads,
+                    float drop_p, unsigned long long seed, unsigned stream_id,
+                    void* dz_planes, long long plane_stride, int nplanes,
+                    float* dgamma, float* dbeta, float* dbias, void* stream) {
+    MDL_REQUIRE(C == 512 || C == 2048, "ln_gelu_bwd: C must be 512 or 2048 (got %d)", C);
+    MDL_REQUIRE(n_heads > 0 && C % n_heads == 0, "ln_gelu_bwd: bad n_heads");
+    if (M == 0) return 0;
+    PoolTerm t0{pool_p0, pool_dS0, pool_seg0}, t1{pool_p1, pool_dS1, pool_seg1};
+    const int rows_per_block = C == 512 ? 8 : 2;
+    const int grid = grid_for(M, rows_per_block * 8, 4);  // several rows per block so the column atomics amortise
+    if (C == 512)
+        ln_gelu_bwd_kernel<512><<<grid, 256, 0, (cudaStream_t)stream>>>(z, M, gamma, beta, mean, rstd, dh_a, dh_b, t0, t1, n_heads, drop_p, seed, stream_id, (__nv_bfloat16*)dz_planes, plane_stride, nplanes, dgamma, dbeta, dbias);
+    else
+        ln_gelu_bwd_kernel<2048><<<grid, 256, 0, (cudaStream_t)stream>>>(z, M, gamma, beta, mean, rstd, dh_a, dh_b, t0, t1, n_heads, drop_p, seed, stream_id, (__nv_bfloat16*)dz_planes, plane_stride, nplanes, dgamma, dbeta, dbias);
+    MDL_CHECK_LAUNCH();
+    return 0;
+}
+
+int mdl_gate_bwd(const void* gate_a, const void* gate_b, const float* dlogit, const float* wc, long long M, int n_heads,
+                 float drop_p, unsigned long long seed, void* dpre_planes, long long plane_stride, int nplanes,
+                 float* dba, float* dbb, float* dwc, float* dbc, void* stream) {
+    MDL_REQUIRE(n_heads == 4, "gate_bwd: only n_heads == 4 is built (got %d)", n_heads);
+    if (M == 0) return 0;
+    const int grid = grid_for(M, 16, 4);
+    gate_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)gate_a, (const __half*)gate_b, dlogit, wc, M, n_heads, drop_p, seed,
+                                                           (__nv_bfloat16*)dpre_planes, plane_stride, nplanes, dba, dbb, dwc, dbc);
+    MDL_CHECK_LAUNCH();
+    return 0;
+}
+
+int mdl_bag_colsum_planes(const void* planes, long long plane_stride, int nplanes, int C, const int* cu_seqlens, int n_bags, float* out, void* stream) {
+    if (n_bags == 0) return 0;
+    dim3 grid((C + 127) / 128, n_bags);
+    bag_colsum_planes_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)planes, plane_stride, nplanes, C, cu_seqlens, out);
+    MDL_CHECK_LAUNCH();
+    return 0;
+}
+
+int mdl_stain_rowbias(const float* emb, const int* code, const float* w1, int ldw, int d_in, int se_dim, int n_out, int R, float* rowbias, void* stream) {
+    if (R == 0) return 0;
+    stain_rowbias_kernel<<<R, 256, 0, (cudaStream_t)stream>>>(emb, code, w1, ldw, d_in, se_dim, n_out, rowbias);
+    MDL_CHECK_LAUNCH();
+    return 0;
+}
+
+int mdl_stain_rowbias_bwd(const float* G, const float* emb, const int* code, const float* w1, int ldw, int d_in, int se_dim, int n_out, int R,
+                          float* dw1, float* demb, void* stream) {
+    if (R == 0) return 0;
+    stain_rowbias_bwd_kernel<<<n_out + R, 32, 0, (cudaStream_t)stream>>>(G, emb, code, w1, ldw, d_in, se_dim, n_out, R, dw1, demb);
+    MDL_CHECK_LAUNCH();
+    return 0;
+}
+
+int mdl_colsum_f32(const float* x, long long M, int C, float* out, void* stream) {
+    if (M == 0) return 0;
+    dim3 grid((C + 127) / 128, (unsigned)((M + 63) / 64 > 64 ? 64 : (M + 63) / 64));
+    colsum_f32_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x, M, C, out);
+    MDL_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,460 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a with TMA-fed 128B-swizzled operands and TMEM accumulators.
+//
+// Operands are "split planes": an fp32 matrix X is held in HBM as two bf16 matrices (hi, lo) with X ~= hi + lo.
+// nsplit = 3 evaluates hi*hi + hi*lo + lo*hi in one fp32 TMEM accumulator (fp32-grade products on the bf16
+// tensor pipe, |err| ~ 2^-16); nsplit = 1 uses the hi planes only (plain bf16, what the reference's autocast
+// scripts compute).  The three passes are just three TMA coordinate schedules over the same kernel.
+//
+// Roles (192 threads): warp 0 = TMA producer (1 lane), warp 1 = TMEM owner + MMA issuer (1 lane),
+// warps 2..5 = epilogue (TMEM lane quadrant = warp_id % 4).  Two 256-column accumulator stages let the epilogue of
+// tile i overlap the MMAs of tile i+1.  Grid = min(#work units, 148): one CTA per SM, static round-robin.
+//
+// Modes
+//   kKMajor : C[M,N] = A[M,K] * B[N,K]^T, both operands contiguous along K (forward and dgrad GEMMs).
+//   kMNMajor: C[M,N] = sum_t A[t,M]^T B[t,N], both operands contiguous along their output index (wgrad;
+//             t = tokens), split over t across CTAs with fp32 red.add accumulation.
+// Epilogues
+//   EPI_STORE : C = acc + bias[n] + rowbias[row2bag[m], n]               (fp32 store)
+//   EPI_GATED : per head h, logit[m,h] = sum_j tanh(a_j+ba_j) * sigmoid(b_j+bb_j) * wc_j + bc  over 4 n-tiles
+//               holding 128 'a' and 128 'b' columns each; optionally stores the (dropout-scaled) gates as fp16.
+//   EPI_ATOMIC: C += acc (red.global.add.f32), used by split-K wgrad.
+#include "common.cuh"
+#include "madeleine_b200.h"
+#include <cuda.h>
+#include <mutex>
+
+namespace mdl {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int GEMM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+
+enum { EPI_STORE = 0, EPI_GATED = 1, EPI_ATOMIC = 2 };
+
+struct GemmArgs {
+    int M, N;                 // output extent
+    int k_blocks;             // contraction length / BLOCK_K (per pass)
+    int nsplit;               // 1 or 3 passes
+    int num_m_tiles, num_n_tiles;
+    int n_inner;              // consecutive n-tiles processed by one work unit (EPI_GATED: 4)
+    int ksplit;               // split-K factor (kMNMajor), else 1
+    int grp_n_tiles, a_koff;  // kKMajor: A k-offset = (n_tile / grp_n_tiles) * a_koff
+    int grp_m_tiles, b_coff;  // kMNMajor: B column offset = (m_tile / grp_m_tiles) * b_coff
+    float* out; int ldc;
+    const float* bias;        // [N] or null
+    const float* rowbias;     // [R, N] or null (per-bag bias, stain encodings)
+    const int* row2bag;       // [M]
+    // gated epilogue
+    const float* ba; const float* bb; const float* wc; const float* bc;  // [H*512], [H*512], [H*512], [H]
+    float* logits;            // [M, H]
+    __half* gate_a; __half* gate_b;  // [M, H*512] or null
+    float drop_p; unsigned long long seed;
+    int n_heads;
+};
+
+template <int BLOCK_N>
+struct SmemLayout {
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+    static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + tmem ptr + alignment slack
+};
+
+template <int BLOCK_N, bool kMNMajor, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmArgs p) {
+    using L = SmemLayout<BLOCK_N>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
+    const uint32_t bar_base = smem_base + L::BAR_OFFSET;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tmem_full_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+    auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+    const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 4);
+    volatile uint32_t* tmem_ptr_generic =
+        reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar(s), 1); mbar_init(tmem_empty_bar(s), 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr_addr, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_generic;
+
+    const int num_units = p.num_m_tiles * (p.num_n_tiles / p.n_inner) * p.ksplit;
+    const int n_groups = p.num_n_tiles / p.n_inner;
+    const int iters_total = p.k_blocks;  // k-blocks over the whole contraction
+
+    // unit -> (m_tile, n_group, k range). n_group varies fastest so CTAs running concurrently share the A tile in L2.
+    auto decode = [&](int unit, int& m_tile, int& n_group, int& kb0, int& kb1) {
+        const int ks = unit % p.ksplit;
+        const int mn = unit / p.ksplit;
+        n_group = mn % n_groups;
+        m_tile = mn / n_groups;
+        const int per = (iters_total + p.ksplit - 1) / p.ksplit;
+        kb0 = ks * per;
+        kb1 = min(iters_total, kb0 + per);
+    };
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+                int m_tile, n_group, kb0, kb1;
+                decode(unit, m_tile, n_group, kb0, kb1);
+                for (int inner = 0; inner < p.n_inner; ++inner) {
+                    const int n_tile = n_group * p.n_inner + inner;
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        for (int pass = 0; pass < p.nsplit; ++pass) {
+                            const int plane_a = pass == 2 ? 1 : 0;
+                            const int plane_b = pass == 1 ? 1 : 0;
+                            mbar_wait(empty_bar(stage), phase ^ 1u);
+                            const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
+                            const uint32_t sb = sa + L::A_BYTES;
+                            mbar_arrive_expect_tx(full_bar(stage), L::STAGE_BYTES);
+                            if constexpr (!kMNMajor) {
+                                const int a_k0 = (n_tile / p.grp_n_tiles) * p.a_koff;
+                                tma_load_3d(sa, &tmap_a, full_bar(stage), a_k0 + kb * BLOCK_K, m_tile * BLOCK_M, plane_a);
+                                tma_load_3d(sb, &tmap_b, full_bar(stage), kb * BLOCK_K, n_tile * BLOCK_N, plane_b);
+                            } else {
+                                const int b_c0 = (m_tile / p.grp_m_tiles) * p.b_coff;
+#pragma unroll
+                                for (int j = 0; j < BLOCK_M / 64; ++j)
+                                    tma_load_3d(sa + j * (64 * BLOCK_K * 2), &tmap_a, full_bar(stage),
+                                                m_tile * BLOCK_M + 64 * j, kb * BLOCK_K, plane_a);
+#pragma unroll
+                                for (int j = 0; j < BLOCK_N / 64; ++j)
+                                    tma_load_3d(sb + j * (64 * BLOCK_K * 2), &tmap_b, full_bar(stage),
+                                                b_c0 + n_tile * BLOCK_N + 64 * j, kb * BLOCK_K, plane_b);
+                            }
+                            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, kMNMajor, kMNMajor);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+                int m_tile, n_group, kb0, kb1;
+                decode(unit, m_tile, n_group, kb0, kb1);
+                for (int inner = 0; inner < p.n_inner; ++inner) {
+                    mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+                    uint32_t accumulate = 0;
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        for (int pass = 0; pass < p.nsplit; ++pass) {
+                            mbar_wait(full_bar(stage), phase);
+                            tc_fence_after();
+                            const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
+                            const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                                uint64_t da, db;
+                                if constexpr (!kMNMajor) {
+                                    // K-major: rows of 128 B, 8-row atoms 1024 B apart; step 16 elements = 32 B along the row.
+                                    da = make_umma_desc_sw128(sa + k * (UMMA_K * 2), 16, 1024);
+                                    db = make_umma_desc_sw128(sb + k * (UMMA_K * 2), 16, 1024);
+                                } else {
+                                    // MN-major: 64-element (128 B) chunks along M/N, LBO = one [64 x BLOCK_K] box,
+                                    // 8-row K atoms 1024 B apart; step 16 rows = 2048 B.
+                                    da = make_umma_desc_sw128(sa + k * (UMMA_K * 128), 64 * BLOCK_K * 2, 1024);
+                                    db = make_umma_desc_sw128(sb + k * (UMMA_K * 128), 64 * BLOCK_K * 2, 1024);
+                                }
+                                umma_bf16(tmem_d, da, db, idesc, accumulate);
+                                accumulate = 1;
+                            }
+                            umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+                            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                        }
+                    }
+                    umma_commit(tmem_full_bar(acc));
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue warps =====================
+        const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+            int m_tile, n_group, kb0, kb1;
+            decode(unit, m_tile, n_group, kb0, kb1);
+            const int m = m_tile * BLOCK_M + quad * 32 + lane;
+            const bool row_ok = m < p.M;
+            float gated_partial = 0.f;
+            for (int inner = 0; inner < p.n_inner; ++inner) {
+                const int n_tile = n_group * p.n_inner + inner;
+                mbar_wait(tmem_full_bar(acc), acc_phase);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+                const bool have_k = kb1 > kb0;  // empty split-K slice: accumulator is stale, skip
+                if constexpr (EPI == EPI_STORE) {
+                    int bag = 0;
+                    if (p.rowbias != nullptr && row_ok) bag = p.row2bag[m];
+#pragma unroll 1
+                    for (int c = 0; c < BLOCK_N / 32; ++c) {
+                        uint32_t r[32];
+                        tmem_ld_32x32(t_row + c * 32, r);
+                        tmem_ld_wait();
+                        if (row_ok) {
+                            const int n0 = n_tile * BLOCK_N + c * 32;
+                            float* dst = p.out + (size_t)m * p.ldc + n0;
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                float4 v;
+                                v.x = __uint_as_float(r[i]); v.y = __uint_as_float(r[i + 1]);
+                                v.z = __uint_as_float(r[i + 2]); v.w = __uint_as_float(r[i + 3]);
+                                if (p.bias != nullptr) {
+                                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
+                                    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                                }
+                                if (p.rowbias != nullptr) {
+                                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.rowbias + (size_t)bag * p.N + n0 + i));
+                                    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                                }
+                                *reinterpret_cast<float4*>(dst + i) = v;
+                            }
+                        }
+                    }
+                } else if constexpr (EPI == EPI_ATOMIC) {
+#pragma unroll 1
+                    for (int c = 0; c < BLOCK_N / 32; ++c) {
+                        uint32_t r[32];
+                        tmem_ld_32x32(t_row + c * 32, r);
+                        tmem_ld_wait();
+                        if (row_ok && have_k) {
+                            float* dst = p.out + (size_t)m * p.ldc + n_tile * BLOCK_N + c * 32;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) atomicAdd(dst + i, __uint_as_float(r[i]));
+                        }
+                    }
+                } else {  // EPI_GATED
+                    const int head = n_group;          // one work unit = (m_tile, head); inner = 128-wide gate group
+                    const int j_base = head * 512 + inner * 128;
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t ra[32], rb[32];
+                        tmem_ld_32x32(t_row + c * 32, ra);
+                        tmem_ld_32x32(t_row + 128 + c * 32, rb);
+                        tmem_ld_wait();
+                        const int j0 = j_base + c * 32;
+                        uint32_t ha[16], hb[16];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            float a = tanh_acc(__uint_as_float(ra[i]) + __ldg(p.ba + j0 + i));
+                            float b = sigmoid_acc(__uint_as_float(rb[i]) + __ldg(p.bb + j0 + i));
+                            if (p.drop_p > 0.f) {
+                                const uint64_t idx = (uint64_t)m * (uint64_t)(p.n_heads * 512) + (uint64_t)(j0 + i);
+                                a *= dropout_scale(p.drop_p, p.seed, 10u, idx);
+                                b *= dropout_scale(p.drop_p, p.seed, 11u, idx);
+                            }
+                            gated_partial = fmaf(a * b, __ldg(p.wc + j0 + i), gated_partial);
+                            if (p.gate_a != nullptr) {
+                                const uint32_t ua = __half_as_ushort(__float2half_rn(a)), ub = __half_as_ushort(__float2half_rn(b));
+                                if (i & 1) { ha[i >> 1] |= ua << 16; hb[i >> 1] |= ub << 16; }
+                                else { ha[i >> 1] = ua; hb[i >> 1] = ub; }
+                            }
+                        }
+                        if (p.gate_a != nullptr && row_ok) {
+                            uint4* da = reinterpret_cast<uint4*>(p.gate_a + (size_t)m * (p.n_heads * 512) + j0);
+                            uint4* db = reinterpret_cast<uint4*>(p.gate_b + (size_t)m * (p.n_heads * 512) + j0);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                da[i] = make_uint4(ha[4 * i], ha[4 * i + 1], ha[4 * i + 2], ha[4 * i + 3]);
+                                db[i] = make_uint4(hb[4 * i], hb[4 * i + 1], hb[4 * i + 2], hb[4 * i + 3]);
+                            }
+                        }
+                    }
+                    if (inner == p.n_inner - 1 && row_ok)
+                        p.logits[(size_t)m * p.n_heads + head] = gated_partial + __ldg(p.bc + head);
+                }
+                (void)have_k;
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side: tensor maps and launch
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+    });
+    return fn;
+}
+
+// bf16 planes tensor [planes][rows][cols] (cols contiguous, row stride ld elements, plane stride in elements);
+// box = [box_cols=64][box_rows][1], 128B swizzle, OOB -> zeros.
+static int make_plane_tmap(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld,
+                           long long plane_stride, int planes, int box_rows) {
+    PFN_encodeTiled enc = get_encode_fn();
+    MDL_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the CUDA driver");
+    MDL_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15u) == 0, "TMA base pointer must be 16-byte aligned");
+    MDL_REQUIRE((ld * 2) % 16 == 0 && (plane_stride * 2) % 16 == 0, "TMA strides must be multiples of 16 bytes");
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)planes};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane_stride * 2};
+    cuuint32_t box[3] = {64u, (cuuint32_t)box_rows, 1u};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MDL_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld)", (int)r, rows, cols, ld);
+    return 0;
+}
+
+template <int BLOCK_N, bool kMNMajor, int EPI>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t stream) {
+    using L = SmemLayout<BLOCK_N>;
+    auto kern = gemm_tcgen05_kernel<BLOCK_N, kMNMajor, EPI>;
+    static bool attr_set = false;  // per instantiation
+    if (!attr_set) {
+        MDL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        attr_set = true;
+    }
+    const int units = args.num_m_tiles * (args.num_n_tiles / args.n_inner) * args.ksplit;
+    if (units == 0) return 0;
+    int sms = kNumSMs;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = units < sms ? units : sms;
+    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, args);
+    MDL_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace mdl
+
+using namespace mdl;
+
+extern "C" {
+
+int mdl_gemm_nt(const void* a_planes, long long a_rows, long long a_cols, long long lda, long long a_plane_stride,
+                const void* b_planes, long long b_rows, long long b_cols, long long ldb, long long b_plane_stride,
+                float* out, long long ldc, int M, int N, int K, int nsplit,
+                int grp_n_cols, int a_koff,
+                const float* bias, const float* rowbias, const int* row2bag, void* stream) {
+    MDL_REQUIRE(nsplit == 1 || nsplit == 3, "nsplit must be 1 or 3");
+    MDL_REQUIRE(K % BLOCK_K == 0, "K (%d) must be a multiple of %d", K, BLOCK_K);
+    MDL_REQUIRE(N % 128 == 0, "N (%d) must be a multiple of 128", N);
+    MDL_REQUIRE(M > 0, "M must be positive");
+    const int planes = nsplit == 3 ? 2 : 1;
+    const int bn = (N % 256 == 0) ? 256 : 128;
+    CUtensorMap ta, tb;
+    int rc = make_plane_tmap(&ta, a_planes, a_rows, a_cols, lda, a_plane_stride, planes, BLOCK_M);
+    if (rc) return rc;
+    rc = make_plane_tmap(&tb, b_planes, b_rows, b_cols, ldb, b_plane_stride, planes, bn);
+    if (rc) return rc;
+    GemmArgs g{};
+    g.M = M; g.N = N; g.k_blocks = K / BLOCK_K; g.nsplit = nsplit;
+    g.num_m_tiles = (M + BLOCK_M - 1) / BLOCK_M; g.num_n_tiles = N / bn; g.n_inner = 1; g.ksplit = 1;
+    MDL_REQUIRE(grp_n_cols <= 0 || grp_n_cols % bn == 0, "grp_n_cols (%d) must be a multiple of the N tile (%d)", grp_n_cols, bn);
+    MDL_REQUIRE(ldc % 4 == 0, "ldc must be a multiple of 4");
+    g.grp_n_tiles = grp_n_cols > 0 ? grp_n_cols / bn : (1 << 30); g.a_koff = a_koff;
+    g.grp_m_tiles = 1 << 30; g.b_coff = 0;
+    g.out = out; g.ldc = (int)ldc; g.bias = bias; g.rowbias = rowbias; g.row2bag = row2bag;
+    if (bn == 256) return launch_gemm<256, false, EPI_STORE>(ta, tb, g, (cudaStream_t)stream);
+    return launch_gemm<128, false, EPI_STORE>(ta, tb, g, (cudaStream_t)stream);
+}
+
+int mdl_gemm_gated(const void* a_planes, long long a_rows, long long a_cols, long long lda, long long a_plane_stride,
+                   const void* b_planes, long long b_plane_stride,
+                   int M, int n_heads, int nsplit,
+                   const float* ba, const float* bb, const float* wc, const float* bc,
+                   float* logits, void* gate_a, void* gate_b, float drop_p, unsigned long long seed, void* stream) {
+    MDL_REQUIRE(nsplit == 1 || nsplit == 3, "nsplit must be 1 or 3");
+    MDL_REQUIRE(M > 0 && n_heads > 0, "bad sizes");
+    const int planes = nsplit == 3 ? 2 : 1;
+    const int K = 512, N = n_heads * 1024;
+    CUtensorMap ta, tb;
+    int rc = make_plane_tmap(&ta, a_planes, a_rows, a_cols, lda, a_plane_stride, planes, BLOCK_M);
+    if (rc) return rc;
+    rc = make_plane_tmap(&tb, b_planes, N, K, K, b_plane_stride, planes, 256);
+    if (rc) return rc;
+    GemmArgs g{};
+    g.M = M; g.N = N; g.k_blocks = K / BLOCK_K; g.nsplit = nsplit;
+    g.num_m_tiles = (M + BLOCK_M - 1) / BLOCK_M; g.num_n_tiles = N / 256; g.n_inner = 4; g.ksplit = 1;
+    g.grp_n_tiles = 4; g.a_koff = 512; g.grp_m_tiles = 1 << 30; g.b_coff = 0;
+    g.ba = ba; g.bb = bb; g.wc = wc; g.bc = bc; g.logits = logits;
+    g.gate_a = reinterpret_cast<__half*>(gate_a); g.gate_b = reinterpret_cast<__half*>(gate_b);
+    g.drop_p = drop_p; g.seed = seed; g.n_heads = n_heads;
+    return launch_gemm<256, false, EPI_GATED>(ta, tb, g, (cudaStream_t)stream);
+}
+
+int mdl_gemm_tn_accum(const void* a_planes, long long a_cols, long long lda, long long a_plane_stride,
+                      const void* b_planes, long long b_cols, long long ldb, long long b_plane_stride,
+                      long long tokens, float* out, long long ldc, int M, int N, int nsplit,
+                      int grp_m_rows, int b_coff, int ksplit, void* stream) {
+    MDL_REQUIRE(grp_m_rows <= 0 || grp_m_rows % BLOCK_M == 0, "grp_m_rows (%d) must be a multiple of %d", grp_m_rows, BLOCK_M);
+    MDL_REQUIRE(nsplit == 1 || nsplit == 3, "nsplit must be 1 or 3");
+    MDL_REQUIRE(M % BLOCK_M == 0 && N % 256 == 0, "wgrad output must be a multiple of 128 x 256 (got %d x %d)", M, N);
+    MDL_REQUIRE(tokens > 0, "tokens must be positive");
+    const int planes = nsplit == 3 ? 2 : 1;
+    CUtensorMap ta, tb;
+    int rc = make_plane_tmap(&ta, a_planes, tokens, a_cols, lda, a_plane_stride, planes, BLOCK_K);
+    if (rc) return rc;
+    rc = make_plane_tmap(&tb, b_planes, tokens, b_cols, ldb, b_plane_stride, planes, BLOCK_K);
+    if (rc) return rc;
+    GemmArgs g{};
+    g.M = M; g.N = N; g.k_blocks = (int)((tokens + BLOCK_K - 1) / BLOCK_K); g.nsplit = nsplit;
+    g.num_m_tiles = M / BLOCK_M; g.num_n_tiles = N / 256; g.n_inner = 1;
+    const int mn_tiles = g.num_m_tiles * g.num_n_tiles;
+    if (ksplit <= 0) {
+        // aim for ~4 work units per SM, never more splits than k-blocks
+        ksplit = (4 * kNumSMs + mn_tiles - 1) / mn_tiles;
+    }
+    if (ksplit > g.k_blocks) ksplit = g.k_blocks;
+    if (ksplit < 1) ksplit = 1;
+    g.ksplit = ksplit;
+    g.grp_n_tiles = 1 << 30; g.a_koff = 0;
+    g.grp_m_tiles = grp_m_rows > 0 ? grp_m_rows / BLOCK_M : (1 << 30); g.b_coff = b_coff;
+    g.out = out; g.ldc = (int)ldc;
+    return launch_gemm<256, true, EPI_ATOMIC>(ta, tb, g, (cudaStream_t)stream);
+}
+
+}  // extern "C"

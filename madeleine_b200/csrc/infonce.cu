@@ -1,0 +1,173 @@
+// Fused symmetric InfoNCE with in-batch negatives (reference: madeleine/utils/loss.py:111-127).
+//   q^ = q / max(|q|, 1e-12), k^ likewise;  L = q^ k^T;  nll_r[i] = lse_j(L[i,:]/tau) - L[i,i]/tau;
+//   nll_c[j] = lse_i(L[:,j]/tau) - L[j,j]/tau  (symmetric term).
+// Forward writes L, the two log-sum-exp vectors and the per-sample nll vectors; backward turns per-sample upstream
+// weights into dL and then into dq, dk through the normalisation.  m <= a few thousand, D arbitrary (multiple of 4);
+// the problem is latency-bound, so the kernels are sized for launch count, not bandwidth.
+#include "common.cuh"
+#include "madeleine_b200.h"
+
+namespace mdl {
+
+__global__ void __launch_bounds__(256)
+infonce_norm_kernel(const float* __restrict__ q, const float* __restrict__ k, int m, int D, float* __restrict__ qn, float* __restrict__ kn) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + warp;
+    if (row >= 2 * m) return;
+    const float* x = row < m ? q + (long long)row * D : k + (long long)(row - m) * D;
+    float s = 0.f;
+    for (int d = lane; d < D; d += 32) { const float v = __ldg(x + d); s = fmaf(v, v, s); }
+    s = warp_sum(s);
+    if (lane == 0) {
+        const float inv = 1.f / fmaxf(sqrtf(s), 1e-12f);
+        if (row < m) qn[row] = inv; else kn[row - m] = inv;
+    }
+}
+
+// L[i, j] = sum_d (q[i,d] * qn[i]) * (k[j,d] * kn[j]); block = one i, warps sweep j.
+__global__ void __launch_bounds__(256)
+infonce_logits_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ qn, const float* __restrict__ kn,
+                      int m, int D, float* __restrict__ L) {
+    extern __shared__ float qs[];  // normalised q_i
+    const int i = blockIdx.x;
+    const float qi = qn[i];
+    for (int d = threadIdx.x; d < D; d += blockDim.x) qs[d] = __ldg(q + (long long)i * D + d) * qi;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int j = warp; j < m; j += 8) {
+        const float kj = kn[j];
+        float s = 0.f;
+        for (int d = lane; d < D; d += 32) s = fmaf(qs[d], __ldg(k + (long long)j * D + d) * kj, s);
+        s = warp_sum(s);
+        if (lane == 0) L[(long long)i * m + j] = s;
+    }
+}
+
+// warp w < m: row w;  m <= w < 2m: column w-m.  lse of L/tau and nll against the diagonal.
+__global__ void __launch_bounds__(256)
+infonce_lse_kernel(const float* __restrict__ L, int m, float inv_tau, float* __restrict__ lse_r, float* __restrict__ lse_c,
+                   float* __restrict__ nll_r, float* __restrict__ nll_c) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = blockIdx.x * 8 + warp;
+    if (w >= 2 * m) return;
+    const bool is_row = w < m;
+    const int a = is_row ? w : w - m;
+    const long long base = is_row ? (long long)a * m : a, stride = is_row ? 1 : m;
+    float mx = -INFINITY;
+    for (int t = lane; t < m; t += 32) mx = fmaxf(mx, __ldg(L + base + t * stride) * inv_tau);
+    mx = warp_max(mx);
+    float s = 0.f;
+    for (int t = lane; t < m; t += 32) s += expf(__ldg(L + base + t * stride) * inv_tau - mx);
+    s = warp_sum(s);
+    if (lane == 0) {
+        const float lse = mx + logf(s);
+        const float nll = lse - __ldg(L + (long long)a * m + a) * inv_tau;
+        if (is_row) { lse_r[a] = lse; nll_r[a] = nll; } else { lse_c[a] = lse; nll_c[a] = nll; }
+    }
+}
+
+// loss = scale_r * sum nll_r + scale_c * sum nll_c   (single block)
+__global__ void __launch_bounds__(256)
+infonce_reduce_kernel(const float* __restrict__ nll_r, const float* __restrict__ nll_c, int m, float scale_r, float scale_c, float* __restrict__ loss) {
+    __shared__ float scratch[33];
+    float s = 0.f;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) s += scale_r * nll_r[i] + (scale_c != 0.f ? scale_c * nll_c[i] : 0.f);
+    s = block_sum(s, scratch);
+    if (threadIdx.x == 0) *loss = s;
+}
+
+// G[i,j] = inv_tau * ( w_r[i] * (softmax_row[i,j] - d_ij) + w_c[j] * (softmax_col[i,j] - d_ij) )
+__global__ void __launch_bounds__(256)
+infonce_dlogits_kernel(const float* __restrict__ L, const float* __restrict__ lse_r, const float* __restrict__ lse_c,
+                       const float* __restrict__ w_r, const float* __restrict__ w_c, int m, float inv_tau, float* __restrict__ G) {
+    const long long total = (long long)m * m;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / m), j = (int)(idx % m);
+        const float l = __ldg(L + idx) * inv_tau;
+        const float dij = i == j ? 1.f : 0.f;
+        float g = __ldg(w_r + i) * (expf(l - __ldg(lse_r + i)) - dij);
+        if (w_c != nullptr) g += __ldg(w_c + j) * (expf(l - __ldg(lse_c + j)) - dij);
+        G[idx] = g * inv_tau;
+    }
+}
+
+// rows 0..m-1: dq_i ; rows m..2m-1: dk_j.   dx = (dxh - xh (xh . dxh)) * inv_norm,  dxh_i = sum_j G[i,j] kh_j  (or G^T qh).
+__global__ void __launch_bounds__(128)
+infonce_grads_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ qn, const float* __restrict__ kn,
+                     const float* __restrict__ G, int m, int D, float* __restrict__ dq, float* __restrict__ dk) {
+    __shared__ float scratch[33];
+    extern __shared__ float gs[];  // coefficients G[i,:] * kn[:]  (or G[:,j] * qn[:])
+    const int row = blockIdx.x;
+    const bool is_q = row < m;
+    const int a = is_q ? row : row - m;
+    const float* self = is_q ? q : k;
+    const float* other = is_q ? k : q;
+    const float* other_n = is_q ? kn : qn;
+    const float self_n = is_q ? qn[a] : kn[a];
+    for (int t = threadIdx.x; t < m; t += blockDim.x)
+        gs[t] = (is_q ? __ldg(G + (long long)a * m + t) : __ldg(G + (long long)t * m + a)) * __ldg(other_n + t);
+    __syncthreads();
+    float dot = 0.f;
+    // each thread owns columns d = threadIdx.x + 128*u
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float acc = 0.f;
+        for (int t = 0; t < m; ++t) acc = fmaf(gs[t], __ldg(other + (long long)t * D + d), acc);
+        const float xh = __ldg(self + (long long)a * D + d) * self_n;
+        dot = fmaf(acc, xh, dot);
+        (is_q ? dq : dk)[(long long)a * D + d] = acc;  // stash dxh, fixed up below
+    }
+    dot = block_sum(dot, scratch);
+    const bool clamped = self_n >= 1e12f;  // |x| < eps: F.normalize divides by eps, a constant
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float* dst = (is_q ? dq : dk) + (long long)a * D + d;
+        const float xh = __ldg(self + (long long)a * D + d) * self_n;
+        *dst = clamped ? *dst * self_n : (*dst - xh * dot) * self_n;
+    }
+}
+
+}  // namespace mdl
+
+using namespace mdl;
+
+extern "C" {
+
+int mdl_infonce_fwd(const float* q, const float* k, int m, int D, float temperature, int symmetric, int reduction,
+                    float* qn, float* kn, float* L, float* lse_r, float* lse_c, float* nll_r, float* nll_c, float* loss, void* stream) {
+    MDL_REQUIRE(m > 0 && D > 0, "infonce: empty input");
+    MDL_REQUIRE(temperature > 0.f, "infonce: temperature must be positive");
+    MDL_REQUIRE((size_t)D * sizeof(float) <= 48 * 1024, "infonce: D too large (%d)", D);
+    cudaStream_t st = (cudaStream_t)stream;
+    const float inv_tau = 1.f / temperature;
+    infonce_norm_kernel<<<(2 * m + 7) / 8, 256, 0, st>>>(q, k, m, D, qn, kn);
+    MDL_CHECK_LAUNCH();
+    infonce_logits_kernel<<<m, 256, D * sizeof(float), st>>>(q, k, qn, kn, m, D, L);
+    MDL_CHECK_LAUNCH();
+    infonce_lse_kernel<<<(2 * m + 7) / 8, 256, 0, st>>>(L, m, inv_tau, lse_r, lse_c, nll_r, nll_c);
+    MDL_CHECK_LAUNCH();
+    if (loss != nullptr && reduction != 0) {  // 1 = mean, 2 = sum
+        const float base = reduction == 1 ? 1.f / m : 1.f;
+        const float sr = symmetric ? 0.5f * base : base, sc = symmetric ? 0.5f * base : 0.f;
+        infonce_reduce_kernel<<<1, 256, 0, st>>>(nll_r, nll_c, m, sr, sc, loss);
+        MDL_CHECK_LAUNCH();
+    }
+    return 0;
+}
+
+int mdl_infonce_bwd(const float* q, const float* k, int m, int D, float temperature,
+                    const float* qn, const float* kn, const float* L, const float* lse_r, const float* lse_c,
+                    const float* w_r, const float* w_c, float* G, float* dq, float* dk, void* stream) {
+    MDL_REQUIRE(m > 0 && D > 0, "infonce: empty input");
+    MDL_REQUIRE((size_t)m * sizeof(float) <= 40 * 1024, "infonce_bwd: m too large (%d)", m);
+    cudaStream_t st = (cudaStream_t)stream;
+    const float inv_tau = 1.f / temperature;
+    const long long total = (long long)m * m;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+    infonce_dlogits_kernel<<<blocks, 256, 0, st>>>(L, lse_r, lse_c, w_r, w_c, m, inv_tau, G);
+    MDL_CHECK_LAUNCH();
+    infonce_grads_kernel<<<2 * m, 128, m * sizeof(float), st>>>(q, k, qn, kn, G, m, D, dq, dk);
+    MDL_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,586 @@
+"""Host orchestration of the sm_100a kernels: weight packing, the encoder forward/backward sequence and the
+autograd Functions that put them behind the reference's module API.
+
+PyTorch is used here for device memory (torch.empty/zeros), streams and autograd bookkeeping only; every
+arithmetic step of the hot path is one of the C-ABI kernels in libmadeleine_b200.so.  There is no CPU path.
+
+Layouts
+  tokens are bag-packed rows [M = sum N_i]; bag r owns rows [cu[r], cu[r+1]);
+  activations that feed a GEMM are bf16 "planes" [nplanes, M, C] (hi[, lo]);
+  the 2048-wide pre-attention features are kept head-major (c' = h*512 + e) — the reference's
+  'b t (e c) -> b t e c' rearrange (Model.py:396) makes head h read channels h::4, which is a row permutation of
+  pre_attn.8 / LayerNorm(2048) and a column permutation of token_projector / projector, applied at pack time.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import call, stream_ptr
+
+HID = 512          # wsi_encoder_hidden_dim the kernels are built for
+GATE = 512         # BatchedABMIL hidden_dim (Model.py:71)
+TOK = 128          # token_projector out (Model.py:80-83)
+LN_EPS = 1e-5
+ACT_CODES = {"softmax": 0, "leaky_relu": 1, "relu": 2, "sigmoid": 3}
+
+_step_counter = [0]
+
+
+def resolve_precision(requested: Optional[str]) -> str:
+    """'fp32' (3-pass split-bf16 tcgen05, fp32-grade) or 'bf16' (1 pass).  'auto' follows torch autocast, which is
+    how the reference picks bf16 (--precision bfloat16 → torch.amp.autocast, trainer.py:108)."""
+    req = (requested or os.environ.get("MADELEINE_B200_PRECISION", "auto")).lower()
+    if req in ("fp32", "float32", "fp32x3", "bf16x3"):
+        return "fp32"
+    if req in ("bf16", "bfloat16"):
+        return "bf16"
+    if req != "auto":
+        raise ValueError(f"unknown precision {requested!r}; use 'auto', 'fp32' or 'bf16'")
+    if torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") in (torch.bfloat16, torch.float16):
+        return "bf16"
+    return "fp32"
+
+
+# --------------------------------------------------------------------------------------------------------------
+# weight packing
+# --------------------------------------------------------------------------------------------------------------
+@dataclass
+class _Seg:
+    off: int
+    shape: Tuple[int, ...]
+
+    @property
+    def numel(self):
+        n = 1
+        for s in self.shape:
+            n *= s
+        return n
+
+
+class PackSpec:
+    """Index maps from kernel-layout buffers into a flat 'master' concatenation of the module parameters."""
+
+    def __init__(self, param_shapes: Sequence[Tuple[int, ...]], n_heads: int, d_in_total: int, device):
+        H = n_heads
+        C = HID * H
+        self.n_heads, self.C, self.d_in_total = H, C, d_in_total
+        offs, o = [], 0
+        for shp in param_shapes:
+            offs.append(o)
+            n = 1
+            for s in shp:
+                n *= s
+            o += n
+        self.master_numel = o
+        self.param_offsets = offs
+        self.param_shapes = list(param_shapes)
+        P = {name: i for i, name in enumerate(PARAM_ORDER(H))}
+        off = lambda name: offs[P[name]]  # noqa: E731
+        ar = torch.arange
+        # head-major permutation: packed channel c' = h*HID + e  <-  reference channel e*H + h
+        cp = ar(C)
+        perm = (cp % HID) * H + (cp // HID)
+
+        bf, f32, gr = [], [], []          # lists of (name, idx tensor, shape)
+
+        def mat(base, rows_src, cols_src, ld):
+            return base + rows_src[:, None] * ld + cols_src[None, :]
+
+        k512 = ar(HID)
+        w1 = mat(off("pre0.w"), ar(HID), k512, d_in_total)                 # [512, 512] (stain columns excluded)
+        w2 = mat(off("pre4.w"), ar(HID), k512, HID)
+        w3 = mat(off("pre8.w"), perm, k512, HID)                           # [2048, 512] head-major rows
+        # gated weights: packed row p = h*1024 + g*256 + is_b*128 + i, gate column j = g*128 + i
+        pr = ar(H * 1024)
+        ph, pin = pr // 1024, pr % 1024
+        pj = (pin // 256) * 128 + (pin % 128)
+        pis_b = (pin % 256) // 128
+        base_a = torch.tensor([off(f"a{h}.w") for h in range(H)])
+        base_b = torch.tensor([off(f"b{h}.w") for h in range(H)])
+        row_base = torch.where(pis_b.bool(), base_b[ph], base_a[ph]) + pj * HID
+        wab = row_base[:, None] + k512[None, :]                              # [H*1024, 512]
+        wabT = wab.view(H, 1024, HID).transpose(1, 2).reshape(H * HID, 1024)  # [H*512 (h,k), 1024 (packed n)]
+        tp = mat(off("tp.w"), ar(TOK), perm, C)                             # [128, 2048] head-major columns
+        for name, idx in (("w1", w1), ("w2", w2), ("w2T", w2.t()), ("w3", w3), ("w3T", w3.t()), ("wab", wab),
+                          ("wabT", wabT), ("tp", tp), ("tpT", tp.t())):
+            bf.append((name, idx.contiguous()))
+        hj = ar(H * GATE)
+        hh, jj = hj // GATE, hj % GATE
+        vec = {
+            "b1": off("pre0.b") + k512, "g1": off("ln1.w") + k512, "be1": off("ln1.b") + k512,
+            "b2": off("pre4.b") + k512, "g2": off("ln5.w") + k512, "be2": off("ln5.b") + k512,
+            "b3": off("pre8.b") + perm, "g3": off("ln9.w") + perm, "be3": off("ln9.b") + perm,
+            "ba": torch.tensor([off(f"a{h}.b") for h in range(H)])[hh] + jj,
+            "bb": torch.tensor([off(f"b{h}.b") for h in range(H)])[hh] + jj,
+            "wc": torch.tensor([off(f"c{h}.w") for h in range(H)])[hh] + jj,
+            "bc": torch.tensor([off(f"c{h}.b") for h in range(H)]),
+            "btp": off("tp.b") + ar(TOK),
+            "wp": mat(off("proj.w"), ar(HID), perm, C),                      # [512, 2048] head-major columns
+            "bp": off("proj.b") + ar(HID),
+        }
+        for name, idx in vec.items():
+            f32.append((name, idx.contiguous()))
+        # gradient buffer: same layouts as the forward operands it mirrors
+        for name, idx in (("w1", w1), ("w2", w2), ("w3", w3), ("wab", wab), ("tp", tp)):
+            gr.append((name, idx.contiguous()))
+        for name, idx in vec.items():
+            gr.append((name, idx.contiguous()))
+
+        def layout(items):
+            segs, o2, flat = {}, 0, []
+            for name, idx in items:
+                n = idx.numel()
+                n_pad = (n + 63) // 64 * 64           # keep every segment 256-byte aligned (TMA / float4)
+                segs[name] = _Seg(o2, tuple(idx.shape))
+                flat.append(idx.reshape(-1))
+                if n_pad != n:
+                    flat.append(idx.reshape(-1)[:1].expand(n_pad - n))
+                o2 += n_pad
+            return segs, o2, torch.cat(flat).to(torch.int32)
+
+        self.bf_segs, self.bf_numel, bf_idx = layout(bf)
+        self.f32_segs, self.f32_numel, f32_idx = layout(f32)
+        self.gr_segs, self.gr_numel, gr_idx = layout(gr)
+        assert self.master_numel < 2 ** 31
+        self.bf_idx = bf_idx.to(device)
+        self.f32_idx = f32_idx.to(device)
+        # padded grad slots must not scatter: compact (position, master index) lists without padding
+        pos, dst = [], []
+        for name, idx in gr:
+            s = self.gr_segs[name]
+            pos.append(torch.arange(s.off, s.off + idx.numel()))
+            dst.append(idx.reshape(-1))
+        self.gr_pos = torch.cat(pos).to(torch.int32).to(device)
+        self.gr_dst = torch.cat(dst).to(torch.int32).to(device)
+        self.off = off
+        self.P = P
+
+
+def PARAM_ORDER(n_heads: int) -> List[str]:
+    names = ["pre0.w", "pre0.b", "ln1.w", "ln1.b", "pre4.w", "pre4.b", "ln5.w", "ln5.b", "pre8.w", "pre8.b", "ln9.w", "ln9.b"]
+    for h in range(n_heads):
+        names += [f"a{h}.w", f"a{h}.b", f"b{h}.w", f"b{h}.b", f"c{h}.w", f"c{h}.b"]
+    names += ["tp.w", "tp.b", "proj.w", "proj.b", "emb.w"]
+    return names
+
+
+class PackedWeights:
+    """Kernel-layout copies of the parameters for one precision; rebuilt whenever a parameter changes."""
+
+    def __init__(self, spec: PackSpec, params: Sequence[torch.Tensor], nplanes: int):
+        dev = params[0].device
+        st = stream_ptr(dev)
+        self.spec, self.nplanes = spec, nplanes
+        master = torch.cat([p.detach().reshape(-1).float() for p in params])
+        self.master = master
+        self.bf = torch.empty(nplanes, spec.bf_numel, dtype=torch.bfloat16, device=dev)
+        call("mdl_gather_split", master, spec.bf_idx, spec.bf_numel, self.bf, spec.bf_numel, nplanes, st)
+        self.f32 = torch.empty(spec.f32_numel, dtype=torch.float32, device=dev)
+        call("mdl_gather_f32", master, spec.f32_idx, spec.f32_numel, self.f32, st)
+
+    def planes(self, name):
+        """(tensor view of plane 0 start, rows, cols, plane_stride)."""
+        s = self.spec.bf_segs[name]
+        return self.bf[0, s.off:], s.shape[0], s.shape[1], self.spec.bf_numel
+
+    def vec(self, name):
+        s = self.spec.f32_segs[name]
+        return self.f32[s.off:s.off + s.numel]
+
+
+# --------------------------------------------------------------------------------------------------------------
+# thin kernel wrappers
+# --------------------------------------------------------------------------------------------------------------
+def _planes_empty(nplanes, M, C, dev):
+    return torch.empty(nplanes, M, C, dtype=torch.bfloat16, device=dev)
+
+
+def split_planes(x: torch.Tensor, nplanes: int) -> torch.Tensor:
+    M, C = x.shape
+    out = _planes_empty(nplanes, M, C, x.device)
+    call("mdl_split_planes", x, M, C, x.stride(0), out, M * C, nplanes, stream_ptr(x.device))
+    return out
+
+
+def gemm_nt(a: torch.Tensor, K: int, bw: Tuple, out_cols: int, nsplit: int, bias=None, rowbias=None, row2bag=None,
+            grp_n_cols: int = 0, a_koff: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M, N] = a[:, :K(+offsets)] @ B^T (+bias). a: planes [np, M, Ca]; bw = (ptr tensor, rows, cols, plane_stride)."""
+    npl, M, Ca = a.shape
+    bt, b_rows, b_cols, b_ps = bw
+    N = out_cols
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    call("mdl_gemm_nt", a, M, Ca, Ca, M * Ca, bt, b_rows, b_cols, b_cols, b_ps, out, out.stride(0), M, N, K, nsplit,
+         grp_n_cols, a_koff, bias, rowbias, row2bag, stream_ptr(a.device))
+    return out
+
+
+def gemm_tn_accum(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, nsplit: int, grp_m_rows: int = 0, b_coff: int = 0):
+    """out[Mo, No] += a^T b over tokens. a: planes [np, T, Ca] (Mo <= Ca), b: planes [np, T, Cb]."""
+    npl, T, Ca = a.shape
+    _, Tb, Cb = b.shape
+    assert T == Tb
+    Mo, No = out.shape
+    call("mdl_gemm_tn_accum", a, Ca, Ca, T * Ca, b, Cb, Cb, T * Cb, T, out, out.stride(0), Mo, No, nsplit, grp_m_rows, b_coff, 0,
+         stream_ptr(a.device))
+    return out
+
+
+def ln_gelu_fwd(z, gamma, beta, nplanes, drop_p, seed, stream_id):
+    M, C = z.shape
+    planes = _planes_empty(nplanes, M, C, z.device)
+    mean = torch.empty(M, dtype=torch.float32, device=z.device)
+    rstd = torch.empty(M, dtype=torch.float32, device=z.device)
+    call("mdl_ln_gelu_fwd", z, M, C, gamma, beta, LN_EPS, drop_p, seed, stream_id, planes, M * C, nplanes, mean, rstd, stream_ptr(z.device))
+    return planes, mean, rstd
+
+
+def ln_gelu_bwd(z, gamma, beta, mean, rstd, dh_a, dh_b, pool_terms, n_heads, nplanes, drop_p, seed, stream_id, dgamma, dbeta, dbias):
+    M, C = z.shape
+    dz = _planes_empty(nplanes, M, C, z.device)
+    t = list(pool_terms) + [(None, None, None)] * (2 - len(pool_terms))
+    call("mdl_ln_gelu_bwd", z, M, C, gamma, beta, mean, rstd, dh_a, dh_b, t[0][0], t[0][1], t[0][2], t[1][0], t[1][1], t[1][2],
+         n_heads, drop_p, seed, stream_id, dz, M * C, nplanes, dgamma, dbeta, dbias, stream_ptr(z.device))
+    return dz
+
+
+# --------------------------------------------------------------------------------------------------------------
+# encoder forward / backward
+# --------------------------------------------------------------------------------------------------------------
+@dataclass
+class EncodeOptions:
+    n_heads: int = 4
+    activation: str = "softmax"
+    precision: str = "fp32"          # resolved: 'fp32' | 'bf16'
+    training: bool = False           # nn.Module.training → dropout active
+    want_tokens: bool = False        # fused token_projector → tokens [M, 128]
+    want_projector: bool = False     # fused projector → [R, 512] instead of pooled [R, 512, H]
+    want_ref_feats: bool = False     # pre-attention features in reference order [M, 512, H] (ABMILEmbedder API)
+    d_in: int = 512
+    se_dim: int = 0
+    views: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None  # n_views=3: (tok_idx, cu2, row2seg2)
+    seed: int = 0
+
+
+def _nsplit(precision):
+    return (3, 2) if precision == "fp32" else (1, 1)
+
+
+class _Saved:
+    pass
+
+
+def encoder_forward(x: torch.Tensor, cu: torch.Tensor, codes: Optional[torch.Tensor], pw: PackedWeights, opt: EncodeOptions,
+                    keep_for_backward: bool):
+    """Runs pre_attn → gated attention → pooling (→ projector, token_projector). Returns (outputs dict, saved)."""
+    dev = x.device
+    st = stream_ptr(dev)
+    nsplit, npl = _nsplit(opt.precision)
+    H = opt.n_heads
+    C = HID * H
+    M = x.shape[0]
+    R = cu.numel() - 1
+    p_pre = 0.1 if opt.training else 0.0      # nn.Dropout(0.1) x3, Model.py:354,358,362
+    p_gate = 0.25 if opt.training else 0.0    # nn.Dropout(0.25) on both gates, abmil.py:33-35
+    sv = _Saved()
+    sv.opt, sv.pw, sv.cu, sv.M, sv.R = opt, pw, cu, M, R
+
+    row2bag = torch.empty(M, dtype=torch.int32, device=dev)
+    call("mdl_row2bag", cu, R, row2bag, M, st)
+    sv.row2bag = row2bag
+
+    rowbias = None
+    if opt.se_dim > 0:
+        spec = pw.spec
+        w1 = pw.master[spec.off("pre0.w"):]
+        emb = pw.master[spec.off("emb.w"):]
+        rowbias = torch.empty(R, HID, dtype=torch.float32, device=dev)
+        call("mdl_stain_rowbias", emb, codes, w1, spec.d_in_total, opt.d_in, opt.se_dim, HID, R, rowbias, st)
+    sv.codes = codes
+
+    xp = split_planes(x, npl)
+    z1 = gemm_nt(xp, HID, pw.planes("w1"), HID, nsplit, bias=pw.vec("b1"), rowbias=rowbias, row2bag=row2bag)
+    h1, mean1, rstd1 = ln_gelu_fwd(z1, pw.vec("g1"), pw.vec("be1"), npl, p_pre, opt.seed, 1)
+    z2 = gemm_nt(h1, HID, pw.planes("w2"), HID, nsplit, bias=pw.vec("b2"))
+    h2, mean2, rstd2 = ln_gelu_fwd(z2, pw.vec("g2"), pw.vec("be2"), npl, p_pre, opt.seed, 2)
+    z3 = gemm_nt(h2, HID, pw.planes("w3"), C, nsplit, bias=pw.vec("b3"))
+    h3, mean3, rstd3 = ln_gelu_fwd(z3, pw.vec("g3"), pw.vec("be3"), npl, p_pre, opt.seed, 3)
+    if not keep_for_backward:
+        del z1, z2, z3, h1, h2
+
+    logits = torch.empty(M, H, dtype=torch.float32, device=dev)
+    gate_a = gate_b = None
+    if keep_for_backward:
+        gate_a = torch.empty(M, H * GATE, dtype=torch.float16, device=dev)
+        gate_b = torch.empty(M, H * GATE, dtype=torch.float16, device=dev)
+    wab, _, _, wab_ps = pw.planes("wab")
+    call("mdl_gemm_gated", h3, M, C, C, M * C, wab, wab_ps, M, H, nsplit, pw.vec("ba"), pw.vec("bb"), pw.vec("wc"), pw.vec("bc"),
+         logits, gate_a, gate_b, p_gate, opt.seed, st)
+
+    act = ACT_CODES[opt.activation]
+    pooled = torch.empty(R, C, dtype=torch.float32, device=dev)
+    attn_p = torch.empty(M, H, dtype=torch.float32, device=dev) if keep_for_backward else None
+    call("mdl_pool_fwd", h3, M * C, npl, logits, cu, None, R, M, H, HID, pooled, attn_p, act, 0, st)
+    outs = {"logits": logits}
+    pooled_views = None
+    if opt.views is not None:
+        tok_idx, cu2, row2seg2 = opt.views
+        R2 = cu2.numel() - 1
+        pooled_views = torch.empty(R2, C, dtype=torch.float32, device=dev)
+        attn_p2 = torch.zeros(M, H, dtype=torch.float32, device=dev) if keep_for_backward else None
+        call("mdl_pool_fwd", h3, M * C, npl, logits, cu2, tok_idx, R2, tok_idx.numel(), H, HID, pooled_views, attn_p2, act, 0, st)
+        sv.attn_p2, sv.pooled_views = attn_p2, pooled_views
+    # all slide vectors that go through the projector: [whole views | half views]
+    slide_hm = pooled if pooled_views is None else torch.cat([pooled, pooled_views], dim=0)
+    if opt.want_projector:
+        emb = torch.empty(slide_hm.shape[0], HID, dtype=torch.float32, device=dev)
+        call("mdl_skinny_linear_fwd", slide_hm, pw.vec("wp"), pw.vec("bp"), slide_hm.shape[0], C, HID, emb, st)
+        outs["slide"] = emb
+    else:
+        # reference layout [*, E, H] (c = e*H + h) from head-major [*, H, E]
+        outs["slide"] = slide_hm.view(-1, H, HID).transpose(1, 2).contiguous()
+    if opt.want_tokens:
+        outs["tokens"] = gemm_nt(h3, C, pw.planes("tp"), TOK, nsplit, bias=pw.vec("btp"))
+    if opt.want_ref_feats:
+        ref = torch.empty(M, HID, H, dtype=torch.float32, device=dev)
+        call("mdl_planes_to_ref_order", h3, M * C, npl, M, H, HID, ref, st)
+        outs["ref_feats"] = ref
+    if keep_for_backward:
+        sv.xp, sv.z1, sv.mean1, sv.rstd1, sv.h1 = xp, z1, mean1, rstd1, h1
+        sv.z2, sv.mean2, sv.rstd2, sv.h2 = z2, mean2, rstd2, h2
+        sv.z3, sv.mean3, sv.rstd3, sv.h3 = z3, mean3, rstd3, h3
+        sv.logits, sv.gate_a, sv.gate_b, sv.attn_p, sv.pooled, sv.slide_hm = logits, gate_a, gate_b, attn_p, pooled, slide_hm
+        sv.p_pre, sv.p_gate = p_pre, p_gate
+    return outs, sv
+
+
+def encoder_backward(sv, d_slide: Optional[torch.Tensor], d_logits: Optional[torch.Tensor], d_tokens: Optional[torch.Tensor],
+                     d_ref_feats: Optional[torch.Tensor]) -> torch.Tensor:
+    """Returns the flat master-layout gradient of all parameters."""
+    opt, pw = sv.opt, sv.pw
+    spec = pw.spec
+    dev = sv.h3.device
+    st = stream_ptr(dev)
+    nsplit, npl = _nsplit(opt.precision)
+    H = opt.n_heads
+    C = HID * H
+    M, R = sv.M, sv.R
+    act = ACT_CODES[opt.activation]
+
+    gp = torch.zeros(spec.gr_numel, dtype=torch.float32, device=dev)
+
+    def g(name):
+        s = spec.gr_segs[name]
+        v = gp[s.off:s.off + s.numel]
+        return v.view(s.shape) if len(s.shape) > 1 else v
+
+    # ---- projector / pooled gradient (head-major) ----
+    n_slide = sv.slide_hm.shape[0]
+    if d_slide is None:
+        dS_all = torch.zeros(n_slide, C, dtype=torch.float32, device=dev)
+    elif opt.want_projector:
+        d_slide = d_slide.contiguous().float()
+        dS_all = torch.empty(n_slide, C, dtype=torch.float32, device=dev)
+        call("mdl_skinny_linear_bwd", d_slide, sv.slide_hm, pw.vec("wp"), n_slide, C, HID, dS_all, g("wp"), g("bp"), st)
+    else:
+        dS_all = d_slide.float().reshape(n_slide, HID, H).transpose(1, 2).contiguous().view(n_slide, C)
+    dS = dS_all[:R]
+
+    # ---- pooling backward: dlogit ----
+    dlogit = torch.empty(M, H, dtype=torch.float32, device=dev)
+    accumulate = 0
+    if d_logits is not None:
+        dlogit.copy_(d_logits.reshape(M, H))
+        accumulate = 1
+    call("mdl_pool_bwd_dlogit", sv.h3, M * C, npl, dS, sv.pooled, sv.attn_p, sv.cu, None, R, M, H, HID, dlogit, accumulate,
+         sv.logits, act, 0, st)
+    pool_terms = [(sv.attn_p, dS, sv.row2bag)]
+    if opt.views is not None:
+        tok_idx, cu2, row2seg2 = opt.views
+        dS2 = dS_all[R:]
+        call("mdl_pool_bwd_dlogit", sv.h3, M * C, npl, dS2, sv.pooled_views, sv.attn_p2, cu2, tok_idx, cu2.numel() - 1, tok_idx.numel(),
+             H, HID, dlogit, 1, sv.logits, act, 0, st)
+        pool_terms.append((sv.attn_p2, dS2, row2seg2))
+
+    # ---- gated attention backward ----
+    dpre = _planes_empty(npl, M, H * 1024, dev)
+    call("mdl_gate_bwd", sv.gate_a, sv.gate_b, dlogit, pw.vec("wc"), M, H, sv.p_gate, opt.seed, dpre, M * H * 1024, npl,
+         g("ba"), g("bb"), g("wc"), g("bc"), st)
+    dh3_attn = gemm_nt(dpre, 1024, pw.planes("wabT"), C, nsplit, grp_n_cols=HID, a_koff=1024)
+    gemm_tn_accum(dpre, sv.h3, g("wab"), nsplit, grp_m_rows=1024, b_coff=HID)
+    del dpre
+
+    # ---- token projector backward ----
+    dh3_tok = None
+    if d_tokens is not None:
+        d_tokens = d_tokens.reshape(M, TOK).contiguous().float()
+        dtp = split_planes(d_tokens, npl)
+        dh3_tok = gemm_nt(dtp, TOK, pw.planes("tpT"), C, nsplit)
+        gemm_tn_accum(dtp, sv.h3, g("tp"), nsplit)
+        call("mdl_colsum_f32", d_tokens, M, TOK, g("btp"), st)
+    if d_ref_feats is not None:
+        # gradient w.r.t. the reference-order features → head-major, added as a second dh source
+        extra = d_ref_feats.float().reshape(M, HID, H).transpose(1, 2).contiguous().view(M, C)
+        dh3_tok = extra if dh3_tok is None else dh3_tok.add_(extra)
+
+    # ---- layer 3 → 2 → 1 ----
+    dz3 = ln_gelu_bwd(sv.z3, pw.vec("g3"), pw.vec("be3"), sv.mean3, sv.rstd3, dh3_attn, dh3_tok, pool_terms, H, npl,
+                      sv.p_pre, opt.seed, 3, g("g3"), g("be3"), g("b3"))
+    del dh3_attn, dh3_tok
+    dh2 = gemm_nt(dz3, C, pw.planes("w3T"), HID, nsplit)
+    gemm_tn_accum(dz3, sv.h2, g("w3"), nsplit)
+    del dz3
+    dz2 = ln_gelu_bwd(sv.z2, pw.vec("g2"), pw.vec("be2"), sv.mean2, sv.rstd2, dh2, None, [], 1, npl, sv.p_pre, opt.seed, 2,
+                      g("g2"), g("be2"), g("b2"))
+    dh1 = gemm_nt(dz2, HID, pw.planes("w2T"), HID, nsplit)
+    gemm_tn_accum(dz2, sv.h1, g("w2"), nsplit)
+    dz1 = ln_gelu_bwd(sv.z1, pw.vec("g1"), pw.vec("be1"), sv.mean1, sv.rstd1, dh1, None, [], 1, npl, sv.p_pre, opt.seed, 1,
+                      g("g1"), g("be1"), g("b1"))
+    gemm_tn_accum(dz1, sv.xp, g("w1"), nsplit)
+
+    gmaster = torch.zeros(spec.master_numel, dtype=torch.float32, device=dev)
+    # scatter packed grads into parameter layout (gr_pos → gr_dst): gather the compact list, then scatter
+    compact = torch.empty(spec.gr_pos.numel(), dtype=torch.float32, device=dev)
+    call("mdl_gather_f32", gp, spec.gr_pos, spec.gr_pos.numel(), compact, st)
+    call("mdl_scatter_f32", compact, spec.gr_dst, spec.gr_dst.numel(), gmaster, 0, st)
+    if opt.se_dim > 0:
+        G = torch.empty(R, HID, dtype=torch.float32, device=dev)
+        call("mdl_bag_colsum_planes", dz1, M * HID, npl, HID, sv.cu, R, G, st)
+        w1 = pw.master[spec.off("pre0.w"):]
+        emb = pw.master[spec.off("emb.w"):]
+        call("mdl_stain_rowbias_bwd", G, emb, sv.codes, w1, spec.d_in_total, opt.d_in, opt.se_dim, HID, R,
+             gmaster[spec.off("pre0.w"):], gmaster[spec.off("emb.w"):], st)
+    return gmaster
+
+
+class EncodeFn(torch.autograd.Function):
+    """autograd wrapper: (x, *params) → (slide, logits, tokens?, ref_feats?)."""
+
+    @staticmethod
+    def forward(ctx, holder, x, *params):
+        opt, cu, codes, pw = holder["opt"], holder["cu"], holder["codes"], holder["pw"]
+        need_grad = holder["need_grad"]
+        outs, sv = encoder_forward(x, cu, codes, pw, opt, keep_for_backward=need_grad)
+        ctx.sv = sv if need_grad else None
+        ctx.n_params = len(params)
+        ctx.param_meta = [(p.shape, p.requires_grad) for p in params]
+        ret = [outs["slide"], outs["logits"]]
+        ret.append(outs.get("tokens"))
+        ret.append(outs.get("ref_feats"))
+        ctx.set_materialize_grads(False)   # unused outputs arrive as None, not as dense zero tensors
+        return tuple(ret)
+
+    @staticmethod
+    def backward(ctx, d_slide, d_logits, d_tokens, d_ref):
+        sv = ctx.sv
+        if sv is None:
+            raise RuntimeError("madeleine_b200: backward called on a forward that ran without grad state")
+        gmaster = encoder_backward(sv, d_slide, d_logits, d_tokens, d_ref)
+        spec = sv.pw.spec
+        grads = []
+        for i, (shape, req) in enumerate(ctx.param_meta):
+            if not req:
+                grads.append(None)
+                continue
+            o = spec.param_offsets[i]
+            n = 1
+            for s in shape:
+                n *= s
+            grads.append(gmaster[o:o + n].view(shape))
+        ctx.sv = None
+        return (None, None, *grads)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# InfoNCE
+# --------------------------------------------------------------------------------------------------------------
+_RED = {"none": 0, "mean": 1, "sum": 2}
+
+
+class InfoNCEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, temperature, symmetric, reduction):
+        m, D = q.shape
+        dev = q.device
+        q = q.contiguous().float()
+        k = k.contiguous().float()
+        f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)  # noqa: E731
+        qn, kn, L, lse_r, lse_c, nll_r, nll_c = f(m), f(m), f(m, m), f(m), f(m), f(m), f(m)
+        loss = f(())
+        red = _RED[reduction]
+        call("mdl_infonce_fwd", q, k, m, D, float(temperature), int(bool(symmetric)), red, qn, kn, L, lse_r, lse_c, nll_r, nll_c,
+             loss if red else None, stream_ptr(dev))
+        ctx.save_for_backward(q, k, qn, kn, L, lse_r, lse_c)
+        ctx.cfg = (float(temperature), bool(symmetric), reduction, m, D)
+        if red == 0:
+            return 0.5 * nll_r + 0.5 * nll_c if symmetric else nll_r
+        return loss
+
+    @staticmethod
+    def backward(ctx, go):
+        q, k, qn, kn, L, lse_r, lse_c = ctx.saved_tensors
+        temperature, symmetric, reduction, m, D = ctx.cfg
+        dev = q.device
+        go = go.float()
+        if reduction == "none":
+            w = go.reshape(m)
+        else:
+            w = go.reshape(1).expand(m) * (1.0 / m if reduction == "mean" else 1.0)
+        w_r = (0.5 * w if symmetric else w).contiguous()
+        w_c = w_r if symmetric else None
+        G = torch.empty(m, m, dtype=torch.float32, device=dev)
+        dq = torch.empty_like(q)
+        dk = torch.empty_like(k)
+        call("mdl_infonce_bwd", q, k, m, D, temperature, qn, kn, L, lse_r, lse_c, w_r, w_c, G, dq, dk, stream_ptr(dev))
+        return dq, dk, None, None, None
+
+
+def info_nce(query, positive_key, temperature=0.1, reduction="mean", symmetric=False):
+    _lib.require_cuda(query, "InfoNCE query")
+    _lib.require_cuda(positive_key, "InfoNCE positive_key")
+    return InfoNCEFn.apply(query, positive_key, temperature, symmetric, reduction)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Graph-OT local loss
+# --------------------------------------------------------------------------------------------------------------
+class GOTFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v, q):
+        m, n, D = v.shape
+        dev = v.device
+        v = v.contiguous().float()
+        q = q.contiguous().float()
+        max_n = call("mdl_got_max_tokens")
+        if n > max_n:
+            raise RuntimeError(f"madeleine_b200 GOT kernel supports at most {max_n} tokens per problem (got {n}); "
+                               "the reference's subsampling quirk (loss.py:281-284) bounds n by the number of cases")
+        ws_bytes = call("mdl_got_workspace_bytes", m, n, D)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        extrema = torch.empty(6, dtype=torch.float32, device=dev)
+        st = stream_ptr(dev)
+        call("mdl_got_extrema", v, q, m, n, D, ws, extrema, st)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        wd = torch.empty(m, dtype=torch.float32, device=dev)
+        gwd = torch.empty(m, dtype=torch.float32, device=dev)
+        dv = torch.empty_like(v)
+        dq = torch.empty_like(q)
+        call("mdl_got_fwd_bwd", v, q, m, n, D, ws, extrema, loss, wd, gwd, dv, dq, st)
+        ctx.save_for_backward(dv, dq)
+        ctx.parts = (wd, gwd)
+        return loss
+
+    @staticmethod
+    def backward(ctx, go):
+        dv, dq = ctx.saved_tensors
+        return dv * go, dq * go
+
+
+def got_loss(v, q):
+    _lib.require_cuda(v, "GOT tokens")
+    return GOTFn.apply(v, q)

@@ -1,0 +1,117 @@
+"""CPU-side checks: the C-ABI library loads, exports every symbol include/madeleine_b200.h declares, the ctypes
+table matches the header, and the host-side weight packing index maps are correct (no GPU compute)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from madeleine_b200 import _lib, ops
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(REPO, "include", "madeleine_b200.h")
+
+
+def header_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mdl_\w+)\s*\(", text)))
+
+
+def test_header_and_ctypes_table_agree():
+    assert sorted(_lib.exported_symbols()) == header_symbols()
+
+
+def test_library_loads_and_exports_every_symbol():
+    lib = _lib.load()
+    for name in header_symbols():
+        assert hasattr(lib, name), f"{name} missing from {_lib.LIB_PATH}"
+    assert lib.mdl_built_arch() == 100
+    assert isinstance(lib.mdl_last_error(), bytes)
+
+
+def test_argument_counts_match_header():
+    text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    for name, argtypes in _lib.SIGNATURES.items():
+        m = re.search(r"\b" + name + r"\s*\((.*?)\)\s*;", text, flags=re.S)
+        assert m, name
+        args = m.group(1).strip()
+        n = 0 if args in ("", "void") else len(args.split(","))
+        assert n == len(argtypes), f"{name}: header has {n} args, ctypes table {len(argtypes)}"
+
+
+def test_cpu_tensor_rejected_without_fallback():
+    from madeleine_b200.utils.loss import InfoNCE
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        InfoNCE(temperature=0.1)(torch.zeros(4, 8), torch.zeros(4, 8))
+    with pytest.raises(ValueError):
+        InfoNCE()(torch.zeros(4, 8, 2), torch.zeros(4, 8))
+    assert InfoNCE()(torch.zeros(4, 8), torch.zeros(4, 8), negative_keys=torch.zeros(3, 8)) is None  # reference quirk
+
+
+def _params(n_heads=4, se=True, n_mod=3):
+    from weights import make_state_dict
+    sd = make_state_dict(3, n_mod=n_mod, stain_encoding=se)
+    names = ["wsi_embedders.pre_attn.0", "wsi_embedders.pre_attn.1", "wsi_embedders.pre_attn.4", "wsi_embedders.pre_attn.5",
+             "wsi_embedders.pre_attn.8", "wsi_embedders.pre_attn.9"]
+    ps = []
+    for n in names:
+        ps += [sd[n + ".weight"], sd[n + ".bias"]]
+    for h in range(n_heads):
+        for part in ("attention_a.0", "attention_b.0", "attention_c"):
+            ps += [sd[f"wsi_embedders.attn.{h}.{part}.weight"], sd[f"wsi_embedders.attn.{h}.{part}.bias"]]
+    ps += [sd["token_projector.weight"], sd["token_projector.bias"], sd["projector.weight"], sd["projector.bias"]]
+    if se:
+        ps.append(sd["embedding.weight"])
+    return sd, ps
+
+
+def test_pack_spec_index_maps():
+    sd, ps = _params()
+    spec = ops.PackSpec([tuple(p.shape) for p in ps], 4, 544, "cpu")
+    master = torch.cat([p.reshape(-1) for p in ps])
+    assert spec.master_numel == master.numel()
+
+    def bf(name):
+        s = spec.bf_segs[name]
+        return master[spec.bf_idx[s.off:s.off + s.numel].long()].view(s.shape)
+
+    def f32(name):
+        s = spec.f32_segs[name]
+        return master[spec.f32_idx[s.off:s.off + s.numel].long()].view(s.shape)
+
+    W1, W2, W3 = (sd[f"wsi_embedders.pre_attn.{i}.weight"] for i in (0, 4, 8))
+    assert torch.equal(bf("w1"), W1[:, :512])
+    assert torch.equal(bf("w2"), W2) and torch.equal(bf("w2T"), W2.t())
+    # head-major rows: packed row h*512+e <- reference row e*4+h  (einops 'b t (e c) -> b t e c', head = c)
+    w3p = W3.view(512, 4, 512).permute(1, 0, 2).reshape(2048, 512)
+    assert torch.equal(bf("w3"), w3p) and torch.equal(bf("w3T"), w3p.t())
+    g3 = sd["wsi_embedders.pre_attn.9.weight"].view(512, 4).t().reshape(-1)
+    assert torch.equal(f32("g3"), g3)
+    wab = bf("wab").view(4, 4, 2, 128, 512)
+    for h in range(4):
+        Wa = sd[f"wsi_embedders.attn.{h}.attention_a.0.weight"]
+        Wb = sd[f"wsi_embedders.attn.{h}.attention_b.0.weight"]
+        assert torch.equal(wab[h, :, 0].reshape(512, 512), Wa)
+        assert torch.equal(wab[h, :, 1].reshape(512, 512), Wb)
+        assert torch.equal(bf("wabT")[h * 512:(h + 1) * 512], bf("wab")[h * 1024:(h + 1) * 1024].t())
+        assert torch.equal(f32("wc")[h * 512:(h + 1) * 512], sd[f"wsi_embedders.attn.{h}.attention_c.weight"][0])
+        assert f32("bc")[h] == sd[f"wsi_embedders.attn.{h}.attention_c.bias"][0]
+    tp = sd["token_projector.weight"].view(128, 512, 4).permute(0, 2, 1).reshape(128, 2048)
+    assert torch.equal(bf("tp"), tp) and torch.equal(bf("tpT"), tp.t())
+    wp = sd["projector.weight"].view(512, 512, 4).permute(0, 2, 1).reshape(512, 2048)
+    assert torch.equal(f32("wp"), wp)
+    # the gradient scatter list is injective and covers every parameter except W1's stain columns and the embedding
+    dst = spec.gr_dst.long()
+    assert dst.unique().numel() == dst.numel()
+    covered = torch.zeros(spec.master_numel, dtype=torch.bool)
+    covered[dst] = True
+    expect = torch.ones(spec.master_numel, dtype=torch.bool)
+    o = spec.off("pre0.w")
+    w1mask = torch.zeros(512, 544, dtype=torch.bool)
+    w1mask[:, 512:] = True
+    expect[o:o + 512 * 544] = ~w1mask.reshape(-1)
+    e = spec.off("emb.w")
+    expect[e:e + 3 * 32] = False
+    assert torch.equal(covered, expect)

@@ -1,0 +1,145 @@
+"""tcgen05 GEMM parity: every mode/epilogue against fp64 torch math and the CUDA-core cross-check kernel."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from madeleine_b200 import ops  # noqa: E402
+from madeleine_b200._lib import call, stream_ptr  # noqa: E402
+
+DEV = "cuda"
+
+
+def _st():
+    return stream_ptr(torch.device(DEV))
+
+
+def planes_f64(p):
+    return p.double().sum(0)
+
+
+def ref_nt(ap, bp, nsplit):
+    if nsplit == 1:
+        return ap[0].double() @ bp[0].double().t()
+    ah, al, bh, bl = ap[0].double(), ap[1].double(), bp[0].double(), bp[1].double()
+    return ah @ bh.t() + ah @ bl.t() + al @ bh.t()
+
+
+@pytest.mark.parametrize("nsplit", [1, 3])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 512), (300, 512, 512), (1000, 2048, 512), (257, 128, 2048),
+                                   (64, 128, 128), (4096, 512, 2048)])
+def test_gemm_nt(M, N, K, nsplit):
+    npl = 2 if nsplit == 3 else 1
+    torch.manual_seed(M + N + K)
+    A = torch.randn(M, K, device=DEV)
+    B = torch.randn(N, K, device=DEV)
+    ap, bp = ops.split_planes(A, npl), ops.split_planes(B, npl)
+    out = ops.gemm_nt(ap, K, (bp, N, K, N * K), N, nsplit)
+    ref = ref_nt(ap, bp, nsplit)
+    scale = float(ref.abs().max())
+    torch.testing.assert_close(out.double(), ref, rtol=1e-5, atol=1e-5 * scale)
+    simt = torch.empty(M, N, device=DEV)
+    call("mdl_gemm_nt_simt", ap, K, M * K, bp, K, N * K, simt, N, M, N, K, nsplit, _st())
+    torch.testing.assert_close(out, simt, rtol=1e-5, atol=1e-5 * scale)
+    if nsplit == 3:  # fp32-grade: close to the exact fp32 product
+        exact = A.double() @ B.double().t()
+        assert float((out.double() - exact).abs().max()) < 3e-5 * scale
+
+
+def test_gemm_nt_bias_rowbias():
+    M, N, K, R = 500, 512, 512, 4
+    A = torch.randn(M, K, device=DEV)
+    B = torch.randn(N, K, device=DEV)
+    bias = torch.randn(N, device=DEV)
+    rowbias = torch.randn(R, N, device=DEV)
+    r2b = torch.randint(0, R, (M,), device=DEV, dtype=torch.int32)
+    ap, bp = ops.split_planes(A, 2), ops.split_planes(B, 2)
+    out = ops.gemm_nt(ap, K, (bp, N, K, N * K), N, 3, bias=bias, rowbias=rowbias, row2bag=r2b)
+    ref = ref_nt(ap, bp, 3) + bias.double() + rowbias.double()[r2b.long()]
+    torch.testing.assert_close(out.double(), ref, rtol=1e-5, atol=1e-4)
+
+
+def test_gemm_nt_grouped_koffset():
+    """Per-head operand slabs: out[:, h*512:(h+1)*512] = A[:, h*1024:(h+1)*1024] @ B[h*512:(h+1)*512, :]^T."""
+    M, H = 300, 4
+    A = torch.randn(M, H * 1024, device=DEV)
+    B = torch.randn(H * 512, 1024, device=DEV)
+    ap, bp = ops.split_planes(A, 2), ops.split_planes(B, 2)
+    out = ops.gemm_nt(ap, 1024, (bp, H * 512, 1024, H * 512 * 1024), H * 512, 3, grp_n_cols=512, a_koff=1024)
+    a64, b64 = planes_f64(ap), planes_f64(bp)
+    ref = torch.cat([a64[:, h * 1024:(h + 1) * 1024] @ b64[h * 512:(h + 1) * 512].t() for h in range(H)], dim=1)
+    torch.testing.assert_close(out.double(), ref, rtol=1e-4, atol=2e-3)
+
+
+@pytest.mark.parametrize("nsplit", [1, 3])
+@pytest.mark.parametrize("T,Mo,No", [(64, 128, 256), (1000, 512, 512), (5000, 128, 2048), (777, 2048, 512)])
+def test_gemm_tn_accum(T, Mo, No, nsplit):
+    npl = 2 if nsplit == 3 else 1
+    A = torch.randn(T, Mo, device=DEV)
+    B = torch.randn(T, No, device=DEV)
+    ap, bp = ops.split_planes(A, npl), ops.split_planes(B, npl)
+    out = torch.zeros(Mo, No, device=DEV)
+    ops.gemm_tn_accum(ap, bp, out, nsplit)
+    if nsplit == 1:
+        ref = ap[0].double().t() @ bp[0].double()
+    else:
+        ref = ap[0].double().t() @ bp[0].double() + ap[0].double().t() @ bp[1].double() + ap[1].double().t() @ bp[0].double()
+    scale = float(ref.abs().max())
+    torch.testing.assert_close(out.double(), ref, rtol=1e-4, atol=1e-5 * scale)
+    # accumulates on top of existing values
+    ops.gemm_tn_accum(ap, bp, out, nsplit)
+    torch.testing.assert_close(out.double(), 2 * ref, rtol=1e-4, atol=2e-5 * scale)
+
+
+def test_gemm_tn_grouped():
+    """Per-head wgrad: out[h*1024:(h+1)*1024, :] += A[:, h*1024:...]^T @ B[:, h*512:(h+1)*512]."""
+    T, H = 900, 4
+    A = torch.randn(T, H * 1024, device=DEV)
+    B = torch.randn(T, H * 512, device=DEV)
+    ap, bp = ops.split_planes(A, 2), ops.split_planes(B, 2)
+    out = torch.zeros(H * 1024, 512, device=DEV)
+    ops.gemm_tn_accum(ap, bp, out, 3, grp_m_rows=1024, b_coff=512)
+    a64, b64 = planes_f64(ap), planes_f64(bp)
+    ref = torch.cat([a64[:, h * 1024:(h + 1) * 1024].t() @ b64[:, h * 512:(h + 1) * 512] for h in range(H)], dim=0)
+    torch.testing.assert_close(out.double(), ref, rtol=1e-4, atol=2e-3)
+
+
+@pytest.mark.parametrize("nsplit", [1, 3])
+@pytest.mark.parametrize("M", [100, 128, 1000])
+def test_gemm_gated(M, nsplit):
+    H = 4
+    npl = 2 if nsplit == 3 else 1
+    X = torch.randn(M, H * 512, device=DEV)
+    Wa = torch.randn(H, 512, 512, device=DEV) / 22.6
+    Wb = torch.randn(H, 512, 512, device=DEV) / 22.6
+    ba, bb, wc = (torch.randn(H * 512, device=DEV) * 0.1 for _ in range(3))
+    bc = torch.randn(H, device=DEV)
+    packed = torch.cat([torch.cat([Wa[h, g * 128:(g + 1) * 128], Wb[h, g * 128:(g + 1) * 128]]) for h in range(H) for g in range(4)])
+    xp, wp = ops.split_planes(X, npl), ops.split_planes(packed.contiguous(), npl)
+    logits = torch.empty(M, H, device=DEV)
+    ga = torch.empty(M, H * 512, dtype=torch.float16, device=DEV)
+    gb = torch.empty(M, H * 512, dtype=torch.float16, device=DEV)
+    call("mdl_gemm_gated", xp, M, H * 512, H * 512, M * H * 512, wp, wp.shape[1] * wp.shape[2], M, H, nsplit, ba, bb, wc, bc,
+         logits, ga, gb, 0.0, 0, _st())
+    x64 = xp.double().sum(0) if nsplit == 3 else xp[0].double()
+    ref_l, ref_a, ref_b = [], [], []
+    for h in range(H):
+        xh = x64[:, h * 512:(h + 1) * 512]
+        if nsplit == 3:
+            wa64, wb64 = Wa[h].double(), Wb[h].double()
+        else:
+            wa64, wb64 = Wa[h].bfloat16().double(), Wb[h].bfloat16().double()
+        a = torch.tanh(xh @ wa64.t() + ba[h * 512:(h + 1) * 512].double())
+        b = torch.sigmoid(xh @ wb64.t() + bb[h * 512:(h + 1) * 512].double())
+        ref_l.append((a * b) @ wc[h * 512:(h + 1) * 512].double() + bc[h].double())
+        ref_a.append(a)
+        ref_b.append(b)
+    ref_l = torch.stack(ref_l, dim=1)
+    torch.testing.assert_close(logits.double(), ref_l, rtol=1e-4, atol=2e-4)
+    torch.testing.assert_close(ga.double(), torch.cat(ref_a, 1), rtol=2e-3, atol=1e-3)
+    torch.testing.assert_close(gb.double(), torch.cat(ref_b, 1), rtol=2e-3, atol=1e-3)
+    # gates optional
+    logits2 = torch.empty(M, H, device=DEV)
+    call("mdl_gemm_gated", xp, M, H * 512, H * 512, M * H * 512, wp, wp.shape[1] * wp.shape[2], M, H, nsplit, ba, bb, wc, bc,
+         logits2, None, None, 0.0, 0, _st())
+    assert torch.equal(logits, logits2)

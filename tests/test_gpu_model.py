@@ -1,0 +1,200 @@
+"""End-to-end parity of the drop-in modules against fixtures produced by the real reference (tests/golden).
+
+Tolerance for the fp32-grade path is the north star's: rtol 1e-3 / atol 1e-4 on slide embeddings and losses;
+"attention indices" = top-k / argsort of the raw attention logits, bit-exact wherever the reference's own logits
+are separated by more than 1e-5."""
+from argparse import Namespace
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from madeleine.models.Model import MADELEINE, ABMILEmbedder  # noqa: E402  (alias of madeleine_b200)
+from madeleine.utils.loss import InfoNCE, GOT  # noqa: E402
+from madeleine.utils.trainer import calculate_losses  # noqa: E402
+from weights import make_state_dict, make_feats, checksum  # noqa: E402
+
+DEV = torch.device("cuda")
+RTOL, ATOL = 1e-3, 1e-4
+
+
+def cfg(mods, precision="fp32"):
+    return Namespace(MODALITIES=mods, wsi_encoder="abmil", patch_embedding_dim=512, wsi_encoder_hidden_dim=512,
+                     activation="softmax", n_heads=4, b200_precision=precision)
+
+
+def build(mods, se, seed, precision="fp32"):
+    model = MADELEINE(cfg(mods, precision), stain_encoding=se)
+    model.load_state_dict(make_state_dict(seed, n_mod=len(mods), stain_encoding=se), strict=True)
+    return model.to(DEV).eval()
+
+
+def close(a, b, rtol=RTOL, atol=ATOL):
+    torch.testing.assert_close(a.detach().float().cpu(), b, rtol=rtol, atol=atol)
+
+
+def test_cfg1_encode_he(golden):
+    g = golden("encoder")["cfg1"]
+    model = build(["HE"], False, g["seed_w"])
+    x = make_feats(g["seed_x"], *g["shape"])
+    with torch.no_grad():
+        out = model.encode_he(x, DEV)
+    assert out.shape == (1, 512)
+    close(out, g["encode_he"])
+
+
+def test_embedder_and_attention_indices(golden):
+    enc = golden("encoder")
+    g = enc["embedder"]
+    model = build(["HE"], False, g["seed_w"])
+    x = make_feats(g["seed_x"], *g["shape"]).to(DEV)
+    with torch.no_grad():
+        slide, tok = model.wsi_embedders(x, return_preattn_feats=True)
+        slide2, raw = model.wsi_embedders(x, return_attention=True)
+    close(slide, g["slide"])
+    close(slide2, g["slide"])
+    close(raw, g["raw_attention"], rtol=1e-3, atol=1e-4)
+    close(tok[:, :4], g["tokens_head"])
+    a = enc["attention"]
+    x4 = make_feats(a["seed_x"], *a["shape"])
+    with torch.no_grad():
+        emb, raw4 = model({"feats": x4}, DEV, train=False, return_attention=True)
+        ev = model({"feats": x4}, DEV, train=False)
+    close(emb, a["emb"])
+    close(raw4, a["raw_attention"])
+    close(ev["HE"], enc["eval"]["emb"])
+    order = raw4.squeeze(2).transpose(1, 2).argsort(dim=-1, descending=True).cpu()
+    ref_sorted = torch.gather(a["raw_attention"].squeeze(2).transpose(1, 2), -1, a["argsort"])
+    gaps_ok = (ref_sorted[..., :-1] - ref_sorted[..., 1:]) > 1e-5
+    same = order == a["argsort"]
+    assert bool((same[..., :-1] | ~gaps_ok).all())
+    assert torch.equal(order[..., :8], a["argsort"][..., :8])        # top-8 attention indices bit-exact
+
+
+def test_n_views3(golden):
+    g = golden("encoder")["n_views3"]
+    model = build(["HE"], False, g["seed_w"])
+    x = make_feats(g["seed_x"], *g["shape"]).to(DEV)
+    np.random.seed(g["np_seed"])
+    with torch.no_grad():
+        slide = model.wsi_embedders(x, n_views=3)
+    assert slide.shape == g["slide"].shape
+    close(slide, g["slide"])
+
+
+def test_ragged_packed(golden):
+    g = golden("encoder")["ragged"]
+    model = build(["HE"], False, g["seed_w"])
+    lens = g["lens"]
+    x = make_feats(g["seed_x"], sum(lens), 512).to(DEV)
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    with torch.no_grad():
+        out = model.encode_packed(x, cu)
+    close(out, g["encode_he"])
+
+
+@pytest.mark.parametrize("tag", ["plain", "stain_enc"])
+def test_forward_train(golden, tag):
+    g = golden("forward_train")[tag]
+    se = tag == "stain_enc"
+    model = build(g["modalities"], se, g["seed_w"])
+    x = make_feats(g["seed_x"], *g["shape"])
+    with torch.no_grad():
+        embs, toks = model({"feats": x}, DEV, train=True, n_views=1)
+    for m in g["modalities"]:
+        assert embs[m].shape == g["embs"][m].shape and toks[m].shape == g["toks"][m].shape
+        close(embs[m], g["embs"][m])
+        close(toks[m], g["toks"][m])
+    if se:
+        with torch.no_grad():
+            ev = model({"feats": x[:1, 1:2]}, DEV, train=False, custom_stain_idx=1)
+        for k, v in g["eval_custom_stain1"].items():
+            close(ev[k], v)
+
+
+def _check_grads(model, digest, rtol=2e-2, atol_rel=5e-3):
+    for name, p in model.named_parameters():
+        d = digest[name]
+        gr = (p.grad if p.grad is not None else torch.zeros_like(p)).detach().float().cpu().flatten()
+        if "full" in d:
+            ref = d["full"]
+            torch.testing.assert_close(gr, ref, rtol=rtol, atol=atol_rel * float(ref.abs().max()) + 2e-6, msg=lambda m: f"{name}: {m}")
+        else:
+            ref = d["samples"]
+            torch.testing.assert_close(gr[d["idx"]], ref, rtol=rtol, atol=atol_rel * float(ref.abs().max()) + 2e-6, msg=lambda m: f"{name}: {m}")
+            assert float(gr.double().norm()) == pytest.approx(float(d["norm"]), rel=2e-2), name
+
+
+def _run_losses(golden, tag, use_local):
+    g = golden("losses_grads")[tag]
+    mods = g["modalities"]
+    model = build(mods, g["stain_encoding"], g["seed_w"])
+    x = make_feats(g["seed_x"], *g["shape"]) * g["labels"][:, :, None, None]
+    args = Namespace(global_loss="info-nce", symmetric_cl=True, local_loss_weight=1.0)
+    embs, toks = model({"feats": x}, DEV, train=True, n_views=1)
+    torch.manual_seed(g["torch_seed"])
+    loss, flag = calculate_losses(mods[1:], InfoNCE(temperature=0.001), GOT if use_local else None, None, embs, toks,
+                                  g["labels"][:, 1:], args)
+    assert flag == g["flag"]
+    close(loss, g["loss"], rtol=1e-3, atol=1e-3)
+    model.zero_grad()
+    loss.backward()
+    _check_grads(model, g["grads"])
+
+
+def test_losses_and_grads_global(golden):
+    _run_losses(golden, "global_only", False)
+
+
+def test_losses_and_grads_global_local(golden):
+    _run_losses(golden, "global_local_se", True)
+
+
+def test_bf16_mode_close_to_reference(golden):
+    """1-pass bf16 (what the reference's autocast scripts compute): looser, documented tolerance."""
+    g = golden("encoder")["cfg1"]
+    model = build(["HE"], False, g["seed_w"], precision="bf16")
+    x = make_feats(g["seed_x"], *g["shape"])
+    with torch.no_grad():
+        out = model.encode_he(x, DEV)
+    close(out, g["encode_he"], rtol=5e-2, atol=2e-2)
+    # 'auto' follows autocast
+    model2 = build(["HE"], False, g["seed_w"], precision="auto")
+    with torch.no_grad(), torch.amp.autocast("cuda", dtype=torch.bfloat16):
+        out2 = model2.encode_he(x, DEV)
+    assert torch.equal(out, out2)
+
+
+def test_deterministic_forward_and_state_dict_roundtrip(golden):
+    g = golden("encoder")["cfg1"]
+    model = build(["HE"], False, g["seed_w"])
+    x = make_feats(g["seed_x"], *g["shape"])
+    with torch.no_grad():
+        a = model.encode_he(x, DEV)
+        b = model.encode_he(x, DEV)
+    assert torch.equal(a, b)
+    sd = {("module." + k): v for k, v in model.state_dict().items()}
+    assert checksum({k[7:]: v.cpu() for k, v in sd.items()}) == pytest.approx(g["w_checksum"], rel=1e-12)
+
+
+def test_cpu_input_fails_loudly():
+    model = MADELEINE(cfg(["HE"]), stain_encoding=False)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model.encode_he(torch.zeros(1, 8, 512), "cpu")
+
+
+def test_train_mode_dropout_runs_and_differs(golden):
+    g = golden("encoder")["cfg1"]
+    model = build(["HE", "ER"], False, 1)
+    x = make_feats(5, 2, 2, 64, 512)
+    model.train()
+    embs, toks = model({"feats": x}, DEV, train=True)
+    loss = embs["ER"].square().sum() + toks["ER"].square().mean()
+    loss.backward()
+    assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+    model.eval()
+    with torch.no_grad():
+        embs2, _ = model({"feats": x}, DEV, train=True)
+    assert not torch.allclose(embs["ER"], embs2["ER"])

@@ -90,10 +90,15 @@ int mdl_gate_bwd(const void* gate_a, const void* gate_b, const float* dlogit, co
 /* ---- attention pooling (the HBM-bound kernel) ---------------------------------------------------------------- */
 /* softmax over tokens + weighted sum (abmil.py:55, Model.py:416-417); activation 0 softmax, 1 leaky_relu, 2 relu,
  * 3 sigmoid (abmil.py:54-63).  out [n_bags, n_heads*head_dim] head-major; attn_p [tokens, n_heads] optional.
- * tok_idx (optional) gathers rows: segment r pools rows tok_idx[cu[r] .. cu[r+1]) (n_views=3, Model.py:427-437). */
+ * tok_idx (optional) gathers rows: segment r pools rows tok_idx[cu[r] .. cu[r+1]) (n_views=3, Model.py:427-437).
+ * Each bag is split over `tsplit` CTAs along tokens (mdl_pool_tsplit suggests a value that fills the 148 SMs); the
+ * partial sums go through `workspace` (mdl_pool_workspace_bytes; may be NULL when tsplit == 1) and are combined in a
+ * fixed order, so results are bit-reproducible. */
+int mdl_pool_tsplit(int n_bags, long long total_tokens, int n_heads, int head_dim);
+long long mdl_pool_workspace_bytes(int n_bags, int n_heads, int head_dim, int tsplit);
 int mdl_pool_fwd(const void* x_planes, long long plane_stride, int nplanes, const float* logits, const int* cu_seqlens,
                  const int* tok_idx, int n_bags, long long total_tokens, int n_heads, int head_dim,
-                 float* out, float* attn_p, int activation, int tsplit, void* stream);
+                 float* out, float* attn_p, int activation, int tsplit, void* workspace, void* stream);
 int mdl_pool_bwd_dlogit(const void* x_planes, long long plane_stride, int nplanes, const float* dS, const float* S,
                         const float* attn_p, const int* cu_seqlens, const int* tok_idx, int n_bags,
                         long long total_tokens, int n_heads, int head_dim, float* dlogit, int accumulate,
@@ -117,7 +122,8 @@ int mdl_stain_rowbias_bwd(const float* G, const float* emb, const int* code, con
 int mdl_colsum_f32(const float* x, long long M, int C, float* out, void* stream);
 
 /* ---- losses ------------------------------------------------------------------------------------------------------ */
-/* InfoNCE with in-batch negatives (madeleine/utils/loss.py:111-127). reduction: 0 none, 1 mean, 2 sum. */
+/* InfoNCE with in-batch negatives (madeleine/utils/loss.py:111-127). reduction: 0 none, 1 mean, 2 sum.
+ * lse_r / lse_c hold 2m floats each: [row max | log-sum]. */
 int mdl_infonce_fwd(const float* q, const float* k, int m, int D, float temperature, int symmetric, int reduction,
                     float* qn, float* kn, float* L, float* lse_r, float* lse_c, float* nll_r, float* nll_c,
                     float* loss, void* stream);

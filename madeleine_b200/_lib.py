@@ -44,7 +44,9 @@ SIGNATURES = {
     "mdl_ln_gelu_bwd": [c_p, c_ll, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_f, c_ull, c_u,
                         c_p, c_ll, c_i, c_p, c_p, c_p, c_p],
     "mdl_gate_bwd": [c_p, c_p, c_p, c_p, c_ll, c_i, c_f, c_ull, c_p, c_ll, c_i, c_p, c_p, c_p, c_p, c_p],
-    "mdl_pool_fwd": [c_p, c_ll, c_i, c_p, c_p, c_p, c_i, c_ll, c_i, c_i, c_p, c_p, c_i, c_i, c_p],
+    "mdl_pool_tsplit": [c_i, c_ll, c_i, c_i],
+    "mdl_pool_workspace_bytes": [c_i, c_i, c_i, c_i],
+    "mdl_pool_fwd": [c_p, c_ll, c_i, c_p, c_p, c_p, c_i, c_ll, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_p],
     "mdl_pool_bwd_dlogit": [c_p, c_ll, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_ll, c_i, c_i, c_p, c_i, c_p, c_i, c_i, c_p],
     "mdl_planes_to_ref_order": [c_p, c_ll, c_i, c_ll, c_i, c_i, c_p, c_p],
     "mdl_skinny_linear_fwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p],
@@ -60,9 +62,10 @@ SIGNATURES = {
     "mdl_got_extrema": [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p],
     "mdl_got_fwd_bwd": [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
 }
-_RESTYPES = {"mdl_got_workspace_bytes": c_ll}
+_RESTYPES = {"mdl_got_workspace_bytes": c_ll, "mdl_pool_workspace_bytes": c_ll}
 # functions that return a value rather than a status code
-_VALUE_FUNCS = {"mdl_version", "mdl_built_arch", "mdl_got_workspace_bytes", "mdl_got_max_tokens"}
+_VALUE_FUNCS = {"mdl_version", "mdl_built_arch", "mdl_got_workspace_bytes", "mdl_got_max_tokens", "mdl_pool_tsplit",
+                "mdl_pool_workspace_bytes"}
 
 
 def exported_symbols():

@@ -1,7 +1,7 @@
 // Fused symmetric InfoNCE with in-batch negatives (reference: madeleine/utils/loss.py:111-127).
 //   q^ = q / max(|q|, 1e-12), k^ likewise;  L = q^ k^T;  nll_r[i] = lse_j(L[i,:]/tau) - L[i,i]/tau;
 //   nll_c[j] = lse_i(L[:,j]/tau) - L[j,j]/tau  (symmetric term).
-// Forward writes L, the two log-sum-exp vectors and the per-sample nll vectors; backward turns per-sample upstream
+// Forward writes L, the two log-sum-exp vectors (as [max | log-sum], 2m floats each) and the per-sample nll vectors; backward turns per-sample upstream
 // weights into dL and then into dq, dk through the normalisation.  m <= a few thousand, D arbitrary (multiple of 4);
 // the problem is latency-bound, so the kernels are sized for launch count, not bandwidth.
 #include "common.cuh"
@@ -60,9 +60,11 @@ infonce_lse_kernel(const float* __restrict__ L, int m, float inv_tau, float* __r
     for (int t = lane; t < m; t += 32) s += expf(__ldg(L + base + t * stride) * inv_tau - mx);
     s = warp_sum(s);
     if (lane == 0) {
-        const float lse = mx + logf(s);
-        const float nll = lse - __ldg(L + (long long)a * m + a) * inv_tau;
-        if (is_row) { lse_r[a] = lse; nll_r[a] = nll; } else { lse_c[a] = lse; nll_c[a] = nll; }
+        // keep max and log-sum apart: (l - max) - log(sum) is exact for the dominant element, l - (max + log(sum)) is
+        // not once |l| ~ 1/tau = 1000 (fp32 spacing 6e-5), and the gradient is the small difference softmax - 1.
+        const float ls = logf(s);
+        const float nll = ls - (__ldg(L + (long long)a * m + a) * inv_tau - mx);
+        if (is_row) { lse_r[a] = mx; lse_r[m + a] = ls; nll_r[a] = nll; } else { lse_c[a] = mx; lse_c[m + a] = ls; nll_c[a] = nll; }
     }
 }
 
@@ -85,8 +87,8 @@ infonce_dlogits_kernel(const float* __restrict__ L, const float* __restrict__ ls
         const int i = (int)(idx / m), j = (int)(idx % m);
         const float l = __ldg(L + idx) * inv_tau;
         const float dij = i == j ? 1.f : 0.f;
-        float g = __ldg(w_r + i) * (expf(l - __ldg(lse_r + i)) - dij);
-        if (w_c != nullptr) g += __ldg(w_c + j) * (expf(l - __ldg(lse_c + j)) - dij);
+        float g = __ldg(w_r + i) * (expf((l - __ldg(lse_r + i)) - __ldg(lse_r + m + i)) - dij);
+        if (w_c != nullptr) g += __ldg(w_c + j) * (expf((l - __ldg(lse_c + j)) - __ldg(lse_c + m + j)) - dij);
         G[idx] = g * inv_tau;
     }
 }

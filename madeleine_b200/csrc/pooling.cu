@@ -10,7 +10,8 @@
 //
 // Work decomposition (forward): one CTA = (bag, head, 256-channel half, token split). The softmax statistics of the
 // (bag, head) column are recomputed per CTA from the logits (N*4 bytes, L2-resident), so CTAs never exchange data;
-// token splits combine with fp32 atomics into a zeroed output.  Each lane streams 16-byte vectors (8 bf16 channels),
+// token splits write partial sums to a workspace and the last CTA to finish (atomic ticket) adds them in split
+// order, so the result is bit-reproducible run to run.  Each lane streams 16-byte vectors (8 bf16 channels),
 // a warp covers 512 contiguous bytes per plane per token, 4 tokens are in flight per warp.
 #include "common.cuh"
 #include "madeleine_b200.h"
@@ -63,8 +64,9 @@ template <int NPLANES>
 __global__ void __launch_bounds__(POOL_THREADS)
 pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long plane_stride, const float* __restrict__ logits,
                 const int* __restrict__ cu, const int* __restrict__ tok_idx, int H, int E, int tsplit,
-                float* __restrict__ out, float* __restrict__ attn_p, int use_atomic, int act) {
+                float* __restrict__ out, float* __restrict__ attn_p, float* __restrict__ partial, int* __restrict__ tickets, int act) {
     __shared__ float scratch[33];
+    __shared__ int is_last;
     __shared__ float part[POOL_WARPS][256];
     const int halves = E / 256;
     const int half = blockIdx.x % halves, split = blockIdx.x / halves;
@@ -130,7 +132,24 @@ pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long plane_stride, con
 #pragma unroll
         for (int w2 = 0; w2 < POOL_WARPS; ++w2) s += part[w2][c];
         float* dst = out + (long long)r * C + h * E + half * 256 + c;
-        if (use_atomic) atomicAdd(dst, s); else *dst = s;
+        if (tsplit == 1) {
+            *dst = s;
+        } else {
+            const int R = gridDim.z;
+            partial[((long long)split * R + r) * C + h * E + half * 256 + c] = s;
+            __threadfence();
+            __syncthreads();
+            int* ticket = tickets + (r * H + h) * halves + half;
+            if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1) == tsplit - 1;
+            __syncthreads();
+            if (is_last) {
+                __threadfence();
+                float t = 0.f;
+                for (int sp = 0; sp < tsplit; ++sp) t += __ldcg(partial + ((long long)sp * R + r) * C + h * E + half * 256 + c);
+                *dst = t;
+                if (threadIdx.x == 0) *ticket = 0;  // ready for the next launch
+            }
+        }
     }
 }
 
@@ -239,23 +258,38 @@ extern "C" {
 
 int mdl_pool_fwd(const void* x_planes, long long plane_stride, int nplanes, const float* logits, const int* cu_seqlens,
                  const int* tok_idx, int n_bags, long long total_tokens, int n_heads, int head_dim,
-                 float* out, float* attn_p, int activation, int tsplit, void* stream) {
+                 float* out, float* attn_p, int activation, int tsplit, void* workspace, void* stream) {
     MDL_REQUIRE(activation >= 0 && activation <= 3, "pool_fwd: unknown activation %d", activation);
     MDL_REQUIRE(head_dim % 256 == 0, "pool_fwd: head_dim must be a multiple of 256 (got %d)", head_dim);
     MDL_REQUIRE(nplanes == 1 || nplanes == 2, "pool_fwd: nplanes must be 1 or 2");
     if (n_bags == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     const int halves = head_dim / 256;
-    if (tsplit <= 0) tsplit = choose_tsplit(n_bags, n_heads, halves, total_tokens);
-    const int use_atomic = tsplit > 1;
-    if (use_atomic) MDL_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n_bags * n_heads * head_dim, st));
+    MDL_REQUIRE(tsplit >= 1 && tsplit <= 64, "pool_fwd: tsplit must be in [1, 64] (use mdl_pool_tsplit), got %d", tsplit);
+    MDL_REQUIRE(tsplit == 1 || workspace != nullptr, "pool_fwd: tsplit > 1 needs a workspace (mdl_pool_workspace_bytes)");
+    float* partial = reinterpret_cast<float*>(workspace);
+    int* tickets = nullptr;
+    if (tsplit > 1) {
+        tickets = reinterpret_cast<int*>(partial + (size_t)tsplit * n_bags * n_heads * head_dim);
+        MDL_CHECK_CUDA(cudaMemsetAsync(tickets, 0, sizeof(int) * (size_t)n_bags * n_heads * halves, st));
+    }
     dim3 grid(halves * tsplit, n_heads, n_bags);
     if (nplanes == 2)
-        pool_fwd_kernel<2><<<grid, POOL_THREADS, 0, st>>>((const __nv_bfloat16*)x_planes, plane_stride, logits, cu_seqlens, tok_idx, n_heads, head_dim, tsplit, out, attn_p, use_atomic, activation);
+        pool_fwd_kernel<2><<<grid, POOL_THREADS, 0, st>>>((const __nv_bfloat16*)x_planes, plane_stride, logits, cu_seqlens, tok_idx, n_heads, head_dim, tsplit, out, attn_p, partial, tickets, activation);
     else
-        pool_fwd_kernel<1><<<grid, POOL_THREADS, 0, st>>>((const __nv_bfloat16*)x_planes, plane_stride, logits, cu_seqlens, tok_idx, n_heads, head_dim, tsplit, out, attn_p, use_atomic, activation);
+        pool_fwd_kernel<1><<<grid, POOL_THREADS, 0, st>>>((const __nv_bfloat16*)x_planes, plane_stride, logits, cu_seqlens, tok_idx, n_heads, head_dim, tsplit, out, attn_p, partial, tickets, activation);
     MDL_CHECK_LAUNCH();
     return 0;
+}
+
+int mdl_pool_tsplit(int n_bags, long long total_tokens, int n_heads, int head_dim) {
+    return choose_tsplit(n_bags, n_heads, head_dim / 256 > 0 ? head_dim / 256 : 1, total_tokens);
+}
+
+long long mdl_pool_workspace_bytes(int n_bags, int n_heads, int head_dim, int tsplit) {
+    if (tsplit <= 1) return 0;
+    const int halves = head_dim / 256 > 0 ? head_dim / 256 : 1;
+    return (long long)sizeof(float) * tsplit * n_bags * n_heads * head_dim + (long long)sizeof(int) * n_bags * n_heads * halves;
 }
 
 int mdl_pool_bwd_dlogit(const void* x_planes, long long plane_stride, int nplanes, const float* dS, const float* S, const float* attn_p,

@@ -231,6 +231,18 @@ def gemm_tn_accum(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, nsplit: i
     return out
 
 
+def pool_fwd(h3, npl, logits, cu, tok_idx, R, total_tokens, H, E, out, attn_p, act, tsplit=0):
+    """Attention pooling; picks the token split and provides the (deterministic) partial-sum workspace."""
+    M, C = h3.shape[1], h3.shape[2]
+    if tsplit <= 0:
+        tsplit = call("mdl_pool_tsplit", R, total_tokens, H, E)
+    ws = None
+    if tsplit > 1:
+        ws = torch.empty(call("mdl_pool_workspace_bytes", R, H, E, tsplit), dtype=torch.uint8, device=h3.device)
+    call("mdl_pool_fwd", h3, M * C, npl, logits, cu, tok_idx, R, total_tokens, H, E, out, attn_p, act, tsplit, ws, stream_ptr(h3.device))
+    return out
+
+
 def ln_gelu_fwd(z, gamma, beta, nplanes, drop_p, seed, stream_id):
     M, C = z.shape
     planes = _planes_empty(nplanes, M, C, z.device)
@@ -325,7 +337,7 @@ def encoder_forward(x: torch.Tensor, cu: torch.Tensor, codes: Optional[torch.Ten
     act = ACT_CODES[opt.activation]
     pooled = torch.empty(R, C, dtype=torch.float32, device=dev)
     attn_p = torch.empty(M, H, dtype=torch.float32, device=dev) if keep_for_backward else None
-    call("mdl_pool_fwd", h3, M * C, npl, logits, cu, None, R, M, H, HID, pooled, attn_p, act, 0, st)
+    pool_fwd(h3, npl, logits, cu, None, R, M, H, HID, pooled, attn_p, act)
     outs = {"logits": logits}
     pooled_views = None
     if opt.views is not None:
@@ -333,7 +345,7 @@ def encoder_forward(x: torch.Tensor, cu: torch.Tensor, codes: Optional[torch.Ten
         R2 = cu2.numel() - 1
         pooled_views = torch.empty(R2, C, dtype=torch.float32, device=dev)
         attn_p2 = torch.zeros(M, H, dtype=torch.float32, device=dev) if keep_for_backward else None
-        call("mdl_pool_fwd", h3, M * C, npl, logits, cu2, tok_idx, R2, tok_idx.numel(), H, HID, pooled_views, attn_p2, act, 0, st)
+        pool_fwd(h3, npl, logits, cu2, tok_idx, R2, tok_idx.numel(), H, HID, pooled_views, attn_p2, act)
         sv.attn_p2, sv.pooled_views = attn_p2, pooled_views
     # all slide vectors that go through the projector: [whole views | half views]
     slide_hm = pooled if pooled_views is None else torch.cat([pooled, pooled_views], dim=0)
@@ -510,7 +522,7 @@ class InfoNCEFn(torch.autograd.Function):
         q = q.contiguous().float()
         k = k.contiguous().float()
         f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)  # noqa: E731
-        qn, kn, L, lse_r, lse_c, nll_r, nll_c = f(m), f(m), f(m, m), f(m), f(m), f(m), f(m)
+        qn, kn, L, lse_r, lse_c, nll_r, nll_c = f(m), f(m), f(m, m), f(2 * m), f(2 * m), f(m), f(m)
         loss = f(())
         red = _RED[reduction]
         call("mdl_infonce_fwd", q, k, m, D, float(temperature), int(bool(symmetric)), red, qn, kn, L, lse_r, lse_c, nll_r, nll_c,

@@ -141,7 +141,10 @@ def test_pool_fwd_bwd(npl, lens, tsplit):
     logits = (torch.randn(M, H, device=DEV) * 3).requires_grad_(True)
     out = torch.empty(R, C, device=DEV)
     attn = torch.empty(M, H, device=DEV)
-    call("mdl_pool_fwd", xp, M * C, npl, logits.detach(), cu, None, R, M, H, E, out, attn, 0, tsplit, _st())
+    ops.pool_fwd(xp, npl, logits.detach(), cu, None, R, M, H, E, out, attn, 0, tsplit)
+    out_again = torch.empty_like(out)
+    ops.pool_fwd(xp, npl, logits.detach(), cu, None, R, M, H, E, out_again, None, 0, tsplit)
+    assert torch.equal(out, out_again)            # split partial sums are combined in a fixed order
     ref_rows, ref_p = [], []
     o = 0
     for n in lens:
@@ -173,7 +176,7 @@ def test_pool_other_activations(act, fn):
     logits = torch.randn(M, H, device=DEV).requires_grad_(True)
     out = torch.empty(2, C, device=DEV)
     attn = torch.empty(M, H, device=DEV)
-    call("mdl_pool_fwd", xp, M * C, 2, logits.detach(), cu, None, 2, M, H, E, out, attn, act, 0, _st())
+    ops.pool_fwd(xp, 2, logits.detach(), cu, None, 2, M, H, E, out, attn, act)
     w = fn(logits)
     xr = planes_f32(xp)
     ref = torch.stack([(xr[a:b].view(b - a, H, E) * w[a:b, :, None]).sum(0).reshape(C) for a, b in ((0, 50), (50, 180))])
@@ -197,7 +200,7 @@ def test_pool_gather_views():
     idx = torch.cat([h + r * T for h in halves for r in range(R)]).to(torch.int32).to(DEV)
     cu2 = torch.arange(0, (2 * R + 1) * (T // 2), T // 2, dtype=torch.int32, device=DEV)
     out = torch.empty(2 * R, C, device=DEV)
-    call("mdl_pool_fwd", xp, R * T * C, 2, logits, cu2, idx, 2 * R, idx.numel(), H, E, out, None, 0, 0, _st())
+    ops.pool_fwd(xp, 2, logits, cu2, idx, 2 * R, idx.numel(), H, E, out, None, 0)
     xr = planes_f32(xp)
     s = 0
     for v, h in enumerate(halves):
@@ -312,7 +315,7 @@ def test_infonce_golden(golden):
         loss.backward()
         torch.testing.assert_close(loss.cpu(), c["loss"], rtol=1e-3, atol=1e-3)
         for got, ref in ((q.grad.cpu(), c["dq"]), (k.grad.cpu(), c["dk"])):
-            torch.testing.assert_close(got, ref, rtol=1e-2, atol=1e-2 * float(ref.abs().max()))
+            torch.testing.assert_close(got, ref, rtol=1e-2, atol=1e-2 * float(ref.abs().max()) + 1e-6)
 
 
 def test_infonce_reductions():

@@ -50,12 +50,11 @@ def test_attention_and_eval(golden):
     emb, raw = oracle.madeleine_forward_attention(sd, x)
     close(emb, g["emb"])
     close(raw, g["raw_attention"])
-    # "attention indices": identical ordering wherever the reference's own logits are separated by > 1e-5
+    # "attention indices": same ranking up to near-ties in the reference's own logits
     order = raw.squeeze(2).transpose(1, 2).argsort(dim=-1, descending=True)
-    ref_sorted = torch.gather(g["raw_attention"].squeeze(2).transpose(1, 2), -1, g["argsort"])
-    gaps_ok = (ref_sorted[..., :-1] - ref_sorted[..., 1:]) > 1e-5
-    same = order == g["argsort"]
-    assert bool((same[..., :-1] | ~gaps_ok).all())
+    ref_logits = g["raw_attention"].squeeze(2).transpose(1, 2)
+    ref_sorted = torch.gather(ref_logits, -1, g["argsort"])
+    assert float((torch.gather(ref_logits, -1, order) - ref_sorted).abs().max()) <= 1e-5
     assert torch.equal(oracle.topk_attention_indices(raw, 8), g["argsort"][..., :8])
     ev = oracle.madeleine_forward_eval(sd, x, ["HE"])
     close(ev["HE"], enc["eval"]["emb"])

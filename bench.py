@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""Headline benchmark of the MADELEINE hot path on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--precision fp32|bf16]
+
+Metric (BASELINE.json): slides/sec (fwd+bwd) at N=2000 x D=512.  One step = BASELINE.json configs[1] per GPU:
+16 cases x 2 stains (HE + one IHC) = 32 bags x 2000 patch embeddings x 512-d, forward through the drop-in
+``MADELEINE.forward(train=True)`` in train mode (dropout on) + symmetric InfoNCE (tau = 0.001) via
+``calculate_losses`` + ``loss.backward()``.  For N > 1 every rank owns 16 more cases (weak scaling); the slide
+embeddings are all-gathered once before the loss and parameter gradients are summed with one all-reduce.
+
+  value    whole-job slides/s with the inputs resident in HBM
+  e2e      same step through the same public call, but fed from pinned HOST memory every step (H2D inside the timed
+           region) and with the loss read back to the host every step
+  roofline the attention-pooling kernel (the metric's "pooling HBM GB/s vs peak"), timed live with CUDA events inside
+           the timed region; `roofline_gemm` reports the tcgen05 GEMMs the same way
+  cpu_baseline / --impl reference: the CPU oracle (torch-CPU restatement of the reference, oracle/) on the host cores,
+           on a bounded sample of the same workload
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from argparse import Namespace
+
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests", "golden"))
+
+CASES_PER_GPU, N_STAINS, N_TOKENS, D_IN = 16, 2, 2000, 512
+MODS = ["HE", "IHC"]
+TAU = 0.001
+METRIC = "slides/sec (fwd+bwd) at N=2000xD=512"
+
+
+def read_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def model_cfg(precision):
+    return Namespace(MODALITIES=MODS, wsi_encoder="abmil", patch_embedding_dim=D_IN, wsi_encoder_hidden_dim=512,
+                     activation="softmax", n_heads=4, b200_precision=precision)
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank, world):
+    """The reference's own CPU path (oracle port) on the host cores; rank 0 only."""
+    if rank != 0:
+        return
+    import oracle
+    from weights import make_state_dict, make_feats
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cases = 2                                                     # bounded sample: 2 cases x 2 stains x 2000 tokens per step
+    sd = {k: v.clone().requires_grad_(True) for k, v in make_state_dict(0, n_mod=2).items()}
+    feats = make_feats(1, cases, N_STAINS, N_TOKENS, D_IN)
+    labels = torch.ones(cases, 1)
+
+    def step():
+        for v in sd.values():
+            v.grad = None
+        embs, toks = oracle.madeleine_forward_train(sd, feats, MODS)
+        loss, _ = oracle.calculate_losses(MODS[1:], embs, toks, labels, temperature=TAU, symmetric=True)
+        loss.backward()
+        return float(loss)
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    value = cases * N_STAINS / dt
+    sample = f"{cases} cases x {N_STAINS} stains x {N_TOKENS} tokens per step, {steps} steps, oracle port (torch CPU, fp32)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "slides/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1] at fixed N=2000 (bounded CPU sample)", "bags_per_step": cases * N_STAINS,
+                   "tokens_per_bag": N_TOKENS, "d_in": D_IN, "loss": "symmetric InfoNCE tau=0.001"},
+        "cpu_baseline": {"value": value, "unit": "slides/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "slides/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def cpu_baseline_quick():
+    import oracle
+    from weights import make_state_dict, make_feats
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cases = 2
+    sd = {k: v.clone().requires_grad_(True) for k, v in make_state_dict(0, n_mod=2).items()}
+    feats = make_feats(1, cases, N_STAINS, N_TOKENS, D_IN)
+    labels = torch.ones(cases, 1)
+    times = []
+    for it in range(4):
+        for v in sd.values():
+            v.grad = None
+        t0 = time.perf_counter()
+        embs, toks = oracle.madeleine_forward_train(sd, feats, MODS)
+        loss, _ = oracle.calculate_losses(MODS[1:], embs, toks, labels, temperature=TAU, symmetric=True)
+        loss.backward()
+        times.append(time.perf_counter() - t0)
+    dt = statistics.median(times[1:])
+    return {"value": cases * N_STAINS / dt, "unit": "slides/s", "cores": cores, "kind": "port",
+            "sample": f"{cases} cases x {N_STAINS} stains x {N_TOKENS} tokens, fwd+bwd, median of 3 after 1 warm-up (oracle port, torch CPU fp32)"}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--eval-mode", action="store_true", help="model.eval(): dropout off")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from madeleine.models.Model import MADELEINE
+    from madeleine.utils.loss import InfoNCE
+    from madeleine.utils.trainer import calculate_losses
+    from madeleine_b200 import _lib, parallel
+    from weights import make_state_dict
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    torch.manual_seed(1234)
+    model = MADELEINE(model_cfg(args.precision), stain_encoding=False)
+    model.load_state_dict(make_state_dict(0, n_mod=2), strict=True)
+    model.to(dev)
+    model.eval() if args.eval_mode else model.train()
+    loss_fn = InfoNCE(temperature=TAU)
+    largs = Namespace(global_loss="info-nce", symmetric_cl=True, local_loss_weight=1.0)
+
+    B = CASES_PER_GPU
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    feats_dev = torch.randn(B, N_STAINS, N_TOKENS, D_IN, generator=g, device=dev)          # 131 MB > 126 MB L2
+    feats_host = [torch.randn(B, N_STAINS, N_TOKENS, D_IN).pin_memory() for _ in range(2)]  # e2e: pinned host buffers
+    labels = torch.ones(B, N_STAINS)
+    labels_dev = labels.to(dev)
+
+    def step(feats):
+        model.zero_grad(set_to_none=True)
+        embs, toks = model({"feats": feats}, device=dev, n_views=1)
+        lab = labels_dev
+        if world > 1:
+            embs, lab = parallel.gather_slide_embeddings(embs, labels_dev)
+        loss, ok = calculate_losses(MODS[1:], loss_fn, None, None, embs, toks, lab[:, 1:], largs)
+        loss.backward()
+        if world > 1:
+            parallel.allreduce_gradients(model)
+        return loss
+
+    def timed(n_steps, feats_fn, read_loss):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n_steps):
+            loss = step(feats_fn(i))
+            if read_loss:
+                loss.item()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / n_steps
+
+    for _ in range(max(args.warmup, 3)):
+        step(feats_dev)
+    torch.cuda.synchronize()
+
+    # ---- device-resident timing, with live per-kernel events for the roofline ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _lib.kernel_events.clear()
+    _lib.timed_kernels = {"mdl_pool_fwd", "mdl_pool_bwd_dlogit", "mdl_gemm_nt", "mdl_gemm_gated", "mdl_gemm_tn_accum"}
+    _lib.launch_count[0] = 0
+    ms_step = timed(args.steps, lambda i: feats_dev, read_loss=False)
+    launches = _lib.launch_count[0] // args.steps
+    _lib.timed_kernels = None
+    clocks = sampler.stop() if rank == 0 else None
+    kt = {name: [a.elapsed_time(b) for a, b in ev] for name, ev in _lib.kernel_events.items()}
+    _lib.kernel_events.clear()
+
+    bags_per_step = B * N_STAINS * world
+    value = bags_per_step / (ms_step * 1e-3)
+
+    # ---- end to end: pinned host inputs copied inside the step, loss read back every step ----
+    e2e = None
+    if not args.no_e2e:
+        for i in range(2):
+            step(feats_host[i % 2])
+        ms_e2e = timed(max(3, args.steps // 2), lambda i: feats_host[i % 2], read_loss=True)
+        e2e = {"value": bags_per_step / (ms_e2e * 1e-3), "unit": "slides/s", "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": feats_host[0].numel() * 4, "d2h_bytes_per_step": 4}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = read_peaks()
+    npl = 2 if args.precision == "fp32" else 1
+    bags_local = B * N_STAINS
+    # algorithmic bytes of ONE pooling launch: per bag N*2048*s + N*4*4 + 2048*4, s = 2*nplanes
+    pool_bytes = bags_local * (N_TOKENS * 2048 * 2 * npl + N_TOKENS * 4 * 4 + 2048 * 4)
+    pool_ms = statistics.mean(kt["mdl_pool_fwd"])
+    pool_gbs = pool_bytes / (pool_ms * 1e-3) / 1e9
+    roofline = {"kernel": "pool_fwd_kernel (attention pooling, forward)", "bound": "hbm", "achieved": pool_gbs, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": pool_gbs / peaks["hbm_gbs"], "traffic": None, "avg_launch_ms": pool_ms,
+                "algorithmic_bytes_per_launch": pool_bytes, "peak_source": peaks["source"]}
+    # tcgen05 GEMMs: algorithmic FLOPs per step (fp32-equivalent, 1x; the 3-pass split issues 3x this on the bf16 pipe)
+    tokens = bags_local * N_TOKENS
+    flops_fwd = tokens * (2 * D_IN * 512 + 2 * 512 * 512 + 2 * 512 * 2048 + 4 * 2 * (2 * 512 * 512) + 2 * 2048 * 128)
+    flops_bwd = tokens * (2 * (2 * 512 * 2048 + 2 * 512 * 512 + 4 * 2 * (2 * 512 * 512)) + 2 * D_IN * 512)
+    gemm_ms = sum(sum(kt.get(k, [])) for k in ("mdl_gemm_nt", "mdl_gemm_gated", "mdl_gemm_tn_accum")) / args.steps
+    passes = 3 if args.precision == "fp32" else 1
+    tf = (flops_fwd + flops_bwd) / (gemm_ms * 1e-3) / 1e12
+    roofline_gemm = {"kernel": "gemm_tcgen05_kernel (all forward/dgrad/wgrad GEMMs of a step)", "bound": "tensor", "achieved": tf,
+                     "achieved_bf16_issue": tf * passes, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": tf / peaks["bf16_tflops_sustained"], "frac_bf16_issue": tf * passes / peaks["bf16_tflops_sustained"],
+                     "ms_per_step": gemm_ms, "note": "algorithmic fp32-equivalent FLOPs; the 3-pass split-bf16 mode issues 3x on the tensor pipe"}
+    pool_bwd_ms = statistics.mean(kt["mdl_pool_bwd_dlogit"]) if kt.get("mdl_pool_bwd_dlogit") else None
+
+    out = {
+        "metric": METRIC, "value": value, "unit": "slides/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (3-pass split-bf16 on tcgen05, fp32 accumulate)" if args.precision == "fp32" else "bf16 (tcgen05, fp32 accumulate)",
+        "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1] at the metric's fixed N=2000: 16 cases x 2 stains per GPU, symmetric InfoNCE tau=0.001, "
+                               "MADELEINE.forward(train=True) + calculate_losses + backward, train mode (dropout on)"
+                               if not args.eval_mode else "same, eval mode",
+                   "bags_per_gpu": bags_local, "tokens_per_bag": N_TOKENS, "d_in": D_IN, "parallelism": f"dp{world} (cases sharded, 1 all-gather of slide embeddings + 1 grad all-reduce)",
+                   "l2": "inputs larger than L2 (131 MB features + >1 GB activations per step, L2 = 126 MB)"},
+        "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "roofline_gemm": roofline_gemm,
+        "kernel_ms_per_step": {k: sum(v) / args.steps for k, v in kt.items()}, "pool_bwd_avg_launch_ms": pool_bwd_ms,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        out["cpu_baseline"] = cpu_baseline_quick()
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

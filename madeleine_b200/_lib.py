@@ -103,6 +103,21 @@ def load():
     return _lib
 
 
+# kernels launched per entry point (memsets not counted) — used for the bench's `gpu_launches` claim
+LAUNCHES = {
+    "mdl_split_planes": 1, "mdl_gather_split": 1, "mdl_gather_f32": 1, "mdl_scatter_f32": 1, "mdl_row2bag": 1,
+    "mdl_gemm_nt": 1, "mdl_gemm_gated": 1, "mdl_gemm_tn_accum": 1, "mdl_gemm_nt_simt": 1, "mdl_gemm_tn_simt": 1,
+    "mdl_ln_gelu_fwd": 1, "mdl_ln_gelu_bwd": 1, "mdl_gate_bwd": 1, "mdl_pool_fwd": 1, "mdl_pool_bwd_dlogit": 1,
+    "mdl_planes_to_ref_order": 1, "mdl_skinny_linear_fwd": 1, "mdl_skinny_linear_bwd": 2, "mdl_stain_rowbias": 1,
+    "mdl_bag_colsum_planes": 1, "mdl_stain_rowbias_bwd": 1, "mdl_colsum_f32": 1, "mdl_infonce_fwd": 4, "mdl_infonce_bwd": 2,
+    "mdl_got_extrema": 2, "mdl_got_fwd_bwd": 2,
+}
+launch_count = [0]
+# optional per-kernel device timing: {name: [(start_event, end_event), ...]} filled when `timed_kernels` is a set of names
+timed_kernels = None
+kernel_events = {}
+
+
 def _conv(a):
     if a is None:
         return None
@@ -114,9 +129,17 @@ def _conv(a):
 def call(name, *args):
     """Call a status-returning entry point with tensors converted to device pointers; raise on failure."""
     lib = load()
-    rc = getattr(lib, name)(*[_conv(a) for a in args])
     if name in _VALUE_FUNCS:
-        return rc
+        return getattr(lib, name)(*[_conv(a) for a in args])
+    launch_count[0] += LAUNCHES.get(name, 0)
+    if timed_kernels is not None and name in timed_kernels:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*[_conv(a) for a in args])
+        e1.record()
+        kernel_events.setdefault(name, []).append((e0, e1))
+    else:
+        rc = getattr(lib, name)(*[_conv(a) for a in args])
     if rc != 0:
         msg = lib.mdl_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"madeleine_b200.{name} failed (code {rc}): {msg}")

@@ -1,0 +1,90 @@
+"""One-process-per-GPU data parallelism for the hot path (replaces the reference's nn.DataParallel,
+madeleine/utils/setup_components.py:185-187).
+
+Cases are sharded across ranks; the encoder is embarrassingly parallel per bag.  The only data-path exchange is ONE
+NCCL all-gather of the slide embeddings (and stain-availability mask) before the contrastive loss; every rank then
+evaluates the full in-batch loss and back-propagates into its own slice, so parameter gradients must be SUMMED
+(not averaged) across ranks — ``allreduce_gradients`` does that with one flat all-reduce.  The messages are tiny
+(82 KB of embeddings per rank, 20 MB of gradients), i.e. latency-bound: NCCL over NVLink/NVSwitch is the right tool
+and there is no compute to overlap a hand-written peer-memory transfer with.
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+import torch.distributed as dist
+
+
+class _AllGatherRows(torch.autograd.Function):
+    """[B_local, ...] → [world * B_local, ...] (rank-major). Backward: this rank's slice of the incoming gradient."""
+
+    @staticmethod
+    def forward(ctx, x):
+        world = dist.get_world_size()
+        x = x.contiguous()
+        out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(out, x)
+        ctx.rows = x.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        r = dist.get_rank()
+        return g[r * ctx.rows:(r + 1) * ctx.rows]
+
+
+def all_gather_rows(x: torch.Tensor) -> torch.Tensor:
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        return x
+    return _AllGatherRows.apply(x)
+
+
+def gather_slide_embeddings(wsi_embs: Dict[str, torch.Tensor], modality_labels: torch.Tensor):
+    """All-gather the per-modality slide embeddings ([B_local, n_views, 512(, n_mod-1)]) and the availability mask in a
+    single collective: everything is packed into one [B_local, F] fp32 buffer, gathered once, and unpacked."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        return wsi_embs, modality_labels
+    keys = list(wsi_embs.keys())
+    B = modality_labels.shape[0]
+    dev = wsi_embs[keys[0]].device
+    # HE carries a stride-0 repeated trailing dim: ship one copy
+    parts, shapes = [], []
+    for k in keys:
+        t = wsi_embs[k]
+        if k == "HE" and t.dim() == 4:
+            t = t[..., 0]
+        shapes.append(tuple(t.shape[1:]))
+        parts.append(t.reshape(B, -1).float())
+    parts.append(modality_labels.to(dev).float().reshape(B, -1))
+    packed = torch.cat(parts, dim=1)
+    gathered = all_gather_rows(packed)
+    out, o = {}, 0
+    n_mod = modality_labels.shape[1]
+    for k, shp in zip(keys, shapes):
+        n = 1
+        for s in shp:
+            n *= s
+        t = gathered[:, o:o + n].reshape((gathered.shape[0],) + shp)
+        if k == "HE":
+            t = t.unsqueeze(-1).expand(*t.shape, n_mod - 1)
+        out[k] = t
+        o += n
+    labels = gathered[:, o:].detach()
+    return out, labels
+
+
+def allreduce_gradients(module: torch.nn.Module):
+    """Sum parameter gradients across ranks with one flat NCCL all-reduce."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        return
+    grads = [p.grad for p in module.parameters() if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    o = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[o:o + n].view_as(g))
+        o += n

@@ -89,7 +89,8 @@ int mdl_gate_bwd(const void* gate_a, const void* gate_b, const float* dlogit, co
 
 /* ---- attention pooling (the HBM-bound kernel) ---------------------------------------------------------------- */
 /* softmax over tokens + weighted sum (abmil.py:55, Model.py:416-417); activation 0 softmax, 1 leaky_relu, 2 relu,
- * 3 sigmoid (abmil.py:54-63).  out [n_bags, n_heads*head_dim] head-major; attn_p [tokens, n_heads] optional.
+ * 3 sigmoid (abmil.py:54-63).  out [n_bags, n_heads*head_dim] head-major; attn_p [tokens, n_heads] receives the
+ * attention weights (required; rows outside every segment are left untouched).
  * tok_idx (optional) gathers rows: segment r pools rows tok_idx[cu[r] .. cu[r+1]) (n_views=3, Model.py:427-437).
  * Each bag is split over `tsplit` CTAs along tokens (mdl_pool_tsplit suggests a value that fills the 148 SMs); the
  * partial sums go through `workspace` (mdl_pool_workspace_bytes; may be NULL when tsplit == 1) and are combined in a

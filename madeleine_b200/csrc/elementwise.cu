@@ -69,82 +69,62 @@ __global__ void row2bag_kernel(const int* __restrict__ cu, int n_bags, int* __re
 }
 
 // ---------------------------------------------------------------------------------------------------
-// LayerNorm + exact GELU (+ dropout) forward.  One warp owns a 512-column segment of a row (16 values per lane,
-// 4 x float4, columns seg*512 + j*128 + lane*4); C/512 warps cooperate on a row.
+// LayerNorm + exact GELU (+ dropout) forward.  One warp owns RPW whole rows (C/32 values per lane per row, float4
+// columns j*128 + lane*4), so the two row reductions are shuffles only and RPW*C/128 16-byte loads are in flight
+// per lane.  No shared memory, no block barriers.
 // ---------------------------------------------------------------------------------------------------
-template <int C>
-__global__ void __launch_bounds__(256)
+template <int C, int RPW>
+__global__ void __launch_bounds__(256, 2)
 ln_gelu_fwd_kernel(const float* __restrict__ z, long long M, const float* __restrict__ gamma, const float* __restrict__ beta,
                    float eps, float drop_p, unsigned long long seed, unsigned stream_id,
                    __nv_bfloat16* __restrict__ planes, long long plane_stride, int nplanes,
                    float* __restrict__ mean_out, float* __restrict__ rstd_out) {
-    constexpr int WPR = C / 512;          // warps per row
-    constexpr int ROWS = 8 / WPR;         // rows per block iteration
-    __shared__ float red[8];
+    constexpr int V = C / 128;            // float4 per lane per row
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int seg = warp % WPR, rib = warp / WPR;
-    float g[16], b[16];
+    const long long warps_total = (long long)gridDim.x * 8;
+    for (long long m0 = ((long long)blockIdx.x * 8 + warp) * RPW; m0 < M; m0 += warps_total * RPW) {
+        float4 v[RPW][V];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int c = seg * 512 + j * 128 + lane * 4;
-        const float4 gv = __ldg(reinterpret_cast<const float4*>(gamma + c));
-        const float4 bv = __ldg(reinterpret_cast<const float4*>(beta + c));
-        g[4 * j] = gv.x; g[4 * j + 1] = gv.y; g[4 * j + 2] = gv.z; g[4 * j + 3] = gv.w;
-        b[4 * j] = bv.x; b[4 * j + 1] = bv.y; b[4 * j + 2] = bv.z; b[4 * j + 3] = bv.w;
-    }
-    const long long iters = (M + (long long)gridDim.x * ROWS - 1) / ((long long)gridDim.x * ROWS);
-    for (long long it = 0; it < iters; ++it) {
-        const long long m = (it * gridDim.x + blockIdx.x) * ROWS + rib;
-        const bool ok = m < M;
-        float v[16];
+        for (int r = 0; r < RPW; ++r) {
+            const bool ok = m0 + r < M;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) t = __ldg(reinterpret_cast<const float4*>(z + m * C + seg * 512 + j * 128 + lane * 4));
-            v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+            for (int j = 0; j < V; ++j)
+                v[r][j] = ok ? __ldg(reinterpret_cast<const float4*>(z + (m0 + r) * C + j * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) s += v[i];
-        s = warp_sum(s);
-        if constexpr (WPR > 1) {
-            __syncthreads();
-            if (lane == 0) red[warp] = s;
-            __syncthreads();
-            s = 0.f;
+        for (int r = 0; r < RPW; ++r) {
+            const long long m = m0 + r;
+            float s = 0.f;
 #pragma unroll
-            for (int w = 0; w < WPR; ++w) s += red[rib * WPR + w];
-        }
-        const float mu = s * (1.f / C);
-        float q = 0.f;
+            for (int j = 0; j < V; ++j) s += (v[r][j].x + v[r][j].y) + (v[r][j].z + v[r][j].w);
+            const float mu = warp_sum(s) * (1.f / C);
+            float q = 0.f;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { const float d = v[i] - mu; q = fmaf(d, d, q); }
-        q = warp_sum(q);
-        if constexpr (WPR > 1) {
-            __syncthreads();
-            if (lane == 0) red[warp] = q;
-            __syncthreads();
-            q = 0.f;
+            for (int j = 0; j < V; ++j) {
+                const float a = v[r][j].x - mu, b = v[r][j].y - mu, c = v[r][j].z - mu, d = v[r][j].w - mu;
+                q += (a * a + b * b) + (c * c + d * d);
+            }
+            const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
+            if (m < M) {
+                if (lane == 0) { mean_out[m] = mu; rstd_out[m] = rstd; }
 #pragma unroll
-            for (int w = 0; w < WPR; ++w) q += red[rib * WPR + w];
-        }
-        const float rstd = rsqrtf(q * (1.f / C) + eps);
-        if (ok) {
-            if (seg == 0 && lane == 0) { mean_out[m] = mu; rstd_out[m] = rstd; }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int c = seg * 512 + j * 128 + lane * 4;
-                __nv_bfloat16 h[4], l[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float y = gelu_erf((v[4 * j + i] - mu) * rstd * g[4 * j + i] + b[4 * j + i]);
-                    y *= dropout_scale(drop_p, seed, stream_id, (uint64_t)m * C + c + i);
-                    split_bf16(y, h[i], l[i]);
+                for (int j = 0; j < V; ++j) {
+                    const int c = j * 128 + lane * 4;
+                    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+                    const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+                    float msk[4];
+                    dropout_scale4(drop_p, seed, stream_id, ((uint64_t)m * C + c) >> 2, msk);
+                    const float y0 = gelu_erf((v[r][j].x - mu) * rstd * g.x + be.x) * msk[0];
+                    const float y1 = gelu_erf((v[r][j].y - mu) * rstd * g.y + be.y) * msk[1];
+                    const float y2 = gelu_erf((v[r][j].z - mu) * rstd * g.z + be.z) * msk[2];
+                    const float y3 = gelu_erf((v[r][j].w - mu) * rstd * g.w + be.w) * msk[3];
+                    __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+                    split_bf16(y0, h0, l0); split_bf16(y1, h1, l1); split_bf16(y2, h2, l2); split_bf16(y3, h3, l3);
+                    const long long o = m * C + c;
+                    *reinterpret_cast<uint2*>(planes + o) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+                    if (nplanes > 1)
+                        *reinterpret_cast<uint2*>(planes + plane_stride + o) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
                 }
-                const long long o = m * C + c;
-                *reinterpret_cast<uint2*>(planes + o) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
-                if (nplanes > 1)
-                    *reinterpret_cast<uint2*>(planes + plane_stride + o) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
             }
         }
     }
@@ -156,7 +136,11 @@ ln_gelu_fwd_kernel(const float* __restrict__ z, long long M, const float* __rest
 //   dy = dh * dropout_scale * gelu'(y),   y = xhat*gamma + beta,  xhat = (z - mean) * rstd
 //   dz = rstd * (dy*gamma - mean_c(dy*gamma) - xhat * mean_c(dy*gamma*xhat))
 // Writes dz as bf16 planes (operand of the following dgrad / wgrad GEMMs) and accumulates the column sums
-// dgamma += dy*xhat, dbeta += dy, dbias += dz with one atomicAdd per column per block.
+// dgamma += dy*xhat, dbeta += dy, dbias += dz.
+//
+// "Column-owner" layout: a thread owns 4 fixed columns for the whole kernel (gamma/beta and the 12 column-sum
+// accumulators live in registers); C/4 threads form a row slot, 512/(C/4) slots per block, U rows per slot per iteration.
+// The two per-row means need one cross-warp exchange per iteration (double-buffered smem, one __syncthreads).
 // ---------------------------------------------------------------------------------------------------
 struct PoolTerm {
     const float* p;        // [M, H] attention probabilities of this view (0 outside the view)
@@ -164,47 +148,38 @@ struct PoolTerm {
     const int* row2seg;    // [M]
 };
 
-template <int C>
-__global__ void __launch_bounds__(256)
+template <int C, int U>
+__global__ void __launch_bounds__(512, 2)
 ln_gelu_bwd_kernel(const float* __restrict__ z, long long M, const float* __restrict__ gamma, const float* __restrict__ beta,
                    const float* __restrict__ mean, const float* __restrict__ rstd_in,
                    const float* __restrict__ dh_a, const float* __restrict__ dh_b, PoolTerm pt0, PoolTerm pt1, int n_heads,
                    float drop_p, unsigned long long seed, unsigned stream_id,
                    __nv_bfloat16* __restrict__ dz_planes, long long plane_stride, int nplanes,
                    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias) {
-    constexpr int WPR = C / 512;
-    constexpr int ROWS = 8 / WPR;
-    __shared__ float red[2][8];
-    __shared__ float colacc[8][512];  // [warp][lane*16 + i] partial column sums, reused per array
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int seg = warp % WPR, rib = warp / WPR;
-    const int e_per_head = C / n_heads;
-    float g[16], b[16], acc_g[16], acc_b[16], acc_z[16];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int c = seg * 512 + j * 128 + lane * 4;
-        const float4 gv = __ldg(reinterpret_cast<const float4*>(gamma + c));
-        const float4 bv = __ldg(reinterpret_cast<const float4*>(beta + c));
-        g[4 * j] = gv.x; g[4 * j + 1] = gv.y; g[4 * j + 2] = gv.z; g[4 * j + 3] = gv.w;
-        b[4 * j] = bv.x; b[4 * j + 1] = bv.y; b[4 * j + 2] = bv.z; b[4 * j + 3] = bv.w;
-    }
-#pragma unroll
-    for (int i = 0; i < 16; ++i) { acc_g[i] = 0.f; acc_b[i] = 0.f; acc_z[i] = 0.f; }
-
-    const long long iters = (M + (long long)gridDim.x * ROWS - 1) / ((long long)gridDim.x * ROWS);
+    constexpr int TPR = C / 4;            // threads per row
+    constexpr int SLOTS = 512 / TPR;      // row slots per block
+    constexpr int WPS = TPR / 32;         // warps per slot
+    __shared__ __align__(16) float red[2][SLOTS][2 * U][WPS];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int slot = tid / TPR, tin = tid % TPR, wslot = tin >> 5;
+    const int c = tin * 4;
+    const int head = c / (C / n_heads);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+    float accg[4] = {0.f, 0.f, 0.f, 0.f}, accb[4] = {0.f, 0.f, 0.f, 0.f}, accz[4] = {0.f, 0.f, 0.f, 0.f};
+    const long long rows_per_iter = (long long)gridDim.x * SLOTS * U;
+    const long long iters = (M + rows_per_iter - 1) / rows_per_iter;
     for (long long it = 0; it < iters; ++it) {
-        const long long m = (it * gridDim.x + blockIdx.x) * ROWS + rib;
-        const bool ok = m < M;
-        float xh[16], dy[16];
-        float mu = 0.f, rs = 0.f;
-        if (ok) { mu = __ldg(mean + m); rs = __ldg(rstd_in + m); }
-        int s0 = 0, s1 = 0;
-        if (ok && pt0.p != nullptr) s0 = __ldg(pt0.row2seg + m);
-        if (ok && pt1.p != nullptr) s1 = __ldg(pt1.row2seg + m);
+        const long long mbase = (it * gridDim.x + blockIdx.x) * (SLOTS * U) + slot * U;
+        float xh[U][4], dy[U][4], rs[U];
+        float s1[U], s2[U];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = seg * 512 + j * 128 + lane * 4;
+        for (int u = 0; u < U; ++u) {
+            const long long m = mbase + u;
+            const bool ok = m < M;
             float4 zv = make_float4(0.f, 0.f, 0.f, 0.f), d = make_float4(0.f, 0.f, 0.f, 0.f);
+            float mu = 0.f;
+            rs[u] = 0.f;
             if (ok) {
                 zv = __ldg(reinterpret_cast<const float4*>(z + m * C + c));
                 if (dh_a != nullptr) d = __ldg(reinterpret_cast<const float4*>(dh_a + m * C + c));
@@ -212,61 +187,71 @@ ln_gelu_bwd_kernel(const float* __restrict__ z, long long M, const float* __rest
                     const float4 t = __ldg(reinterpret_cast<const float4*>(dh_b + m * C + c));
                     d.x += t.x; d.y += t.y; d.z += t.z; d.w += t.w;
                 }
-                const int head = c / e_per_head;
                 if (pt0.p != nullptr) {
                     const float pw = __ldg(pt0.p + m * n_heads + head);
-                    const float4 t = __ldg(reinterpret_cast<const float4*>(pt0.dS + (long long)s0 * C + c));
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(pt0.dS + (long long)__ldg(pt0.row2seg + m) * C + c));
                     d.x = fmaf(pw, t.x, d.x); d.y = fmaf(pw, t.y, d.y); d.z = fmaf(pw, t.z, d.z); d.w = fmaf(pw, t.w, d.w);
                 }
                 if (pt1.p != nullptr) {
                     const float pw = __ldg(pt1.p + m * n_heads + head);
-                    const float4 t = __ldg(reinterpret_cast<const float4*>(pt1.dS + (long long)s1 * C + c));
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(pt1.dS + (long long)__ldg(pt1.row2seg + m) * C + c));
                     d.x = fmaf(pw, t.x, d.x); d.y = fmaf(pw, t.y, d.y); d.z = fmaf(pw, t.z, d.z); d.w = fmaf(pw, t.w, d.w);
                 }
+                mu = __ldg(mean + m);
+                rs[u] = __ldg(rstd_in + m);
             }
+            float msk[4];
+            dropout_scale4(drop_p, seed, stream_id, ((uint64_t)m * C + c) >> 2, msk);
             const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
             const float dd[4] = {d.x, d.y, d.z, d.w};
+            const float gg[4] = {g.x, g.y, g.z, g.w};
+            const float bb[4] = {be.x, be.y, be.z, be.w};
+            s1[u] = 0.f; s2[u] = 0.f;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float x = (zz[i] - mu) * rs;
-                const float y = x * g[4 * j + i] + b[4 * j + i];
-                float t = dd[i] * gelu_erf_grad(y);
-                if (ok) t *= dropout_scale(drop_p, seed, stream_id, (uint64_t)m * C + c + i);
-                xh[4 * j + i] = x;
-                dy[4 * j + i] = ok ? t : 0.f;
+                const float x = (zz[i] - mu) * rs[u];
+                const float t = ok ? dd[i] * msk[i] * gelu_erf_grad(fmaf(x, gg[i], bb[i])) : 0.f;
+                xh[u][i] = x; dy[u][i] = t;
+                const float dx = t * gg[i];
+                s1[u] += dx;
+                s2[u] = fmaf(dx, x, s2[u]);
+                accg[i] = fmaf(t, x, accg[i]);
+                accb[i] += t;
             }
         }
-        float s1sum = 0.f, s2sum = 0.f;
+        // row sums across the slot's WPS warps
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float dx = dy[i] * g[i];
-            s1sum += dx;
-            s2sum = fmaf(dx, xh[i], s2sum);
-            acc_g[i] = fmaf(dy[i], xh[i], acc_g[i]);
-            acc_b[i] += dy[i];
+        for (int u = 0; u < U; ++u) { s1[u] = warp_sum(s1[u]); s2[u] = warp_sum(s2[u]); }
+        const int buf = (int)(it & 1);
+        if (lane == 0) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) { red[buf][slot][2 * u][wslot] = s1[u]; red[buf][slot][2 * u + 1][wslot] = s2[u]; }
         }
-        s1sum = warp_sum(s1sum);
-        s2sum = warp_sum(s2sum);
-        if constexpr (WPR > 1) {
-            __syncthreads();
-            if (lane == 0) { red[0][warp] = s1sum; red[1][warp] = s2sum; }
-            __syncthreads();
-            s1sum = 0.f; s2sum = 0.f;
+        __syncthreads();
+        // lane l fetches the partials of warp (l % WPS) and a WPS-wide xor-shuffle tree adds them: 2U LDS + a few SHFL per
+        // thread instead of WPS * 2U broadcast loads, and a fixed summation order (deterministic).
+        float tot[2 * U];
 #pragma unroll
-            for (int w = 0; w < WPR; ++w) { s1sum += red[0][rib * WPR + w]; s2sum += red[1][rib * WPR + w]; }
+        for (int k = 0; k < 2 * U; ++k) {
+            float t = red[buf][slot][k][lane % WPS];
+#pragma unroll
+            for (int o = WPS / 2; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            tot[k] = t;
         }
-        const float m1 = s1sum * (1.f / C), m2 = s2sum * (1.f / C);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = seg * 512 + j * 128 + lane * 4;
+        for (int u = 0; u < U; ++u) {
+            const float t1 = tot[2 * u], t2 = tot[2 * u + 1];
+            const float m1 = t1 * (1.f / C), m2 = t2 * (1.f / C);
+            const long long m = mbase + u;
+            const float gg[4] = {g.x, g.y, g.z, g.w};
             __nv_bfloat16 h[4], l[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float dzv = ok ? rs * (dy[4 * j + i] * g[4 * j + i] - m1 - xh[4 * j + i] * m2) : 0.f;
-                acc_z[4 * j + i] += dzv;
+                const float dzv = rs[u] * (dy[u][i] * gg[i] - m1 - xh[u][i] * m2);   // rs = 0 for rows past M
+                accz[i] += dzv;
                 split_bf16(dzv, h[i], l[i]);
             }
-            if (ok) {
+            if (m < M) {
                 const long long o = m * C + c;
                 *reinterpret_cast<uint2*>(dz_planes + o) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
                 if (nplanes > 1)
@@ -274,25 +259,12 @@ ln_gelu_bwd_kernel(const float* __restrict__ z, long long M, const float* __rest
             }
         }
     }
-    // column sums: combine the ROWS warps that own the same 512-column segment, then one atomic per column per block.
-    // One 16 KB staging buffer is reused for the three arrays.
-#pragma unroll 1
-    for (int a = 0; a < 3; ++a) {
-        __syncthreads();
+    // column sums: one atomic per column per slot per block (slots own the same columns)
 #pragma unroll
-        for (int i = 0; i < 16; ++i) colacc[warp][lane * 16 + i] = a == 0 ? acc_g[i] : (a == 1 ? acc_b[i] : acc_z[i]);
-        __syncthreads();
-        float* dst = a == 0 ? dgamma : (a == 1 ? dbeta : dbias);
-        // slot = lane*16 + 4*j + i  <->  column seg*512 + j*128 + lane*4 + i
-        for (int idx = threadIdx.x; idx < WPR * 512; idx += blockDim.x) {
-            const int s = idx / 512, slot = idx % 512;
-            const int ln = slot / 16, r = slot % 16, j = r / 4, i = r % 4;
-            const int c = s * 512 + j * 128 + ln * 4 + i;
-            float t = 0.f;
-#pragma unroll
-            for (int rr = 0; rr < ROWS; ++rr) t += colacc[rr * WPR + s][slot];
-            atomicAdd(dst + c, t);
-        }
+    for (int i = 0; i < 4; ++i) {
+        atomicAdd(dgamma + c + i, accg[i]);
+        atomicAdd(dbeta + c + i, accb[i]);
+        atomicAdd(dbias + c + i, accz[i]);
     }
 }
 
@@ -300,9 +272,9 @@ ln_gelu_bwd_kernel(const float* __restrict__ z, long long M, const float* __rest
 // Gated-attention backward (elementwise part).  gate_a/gate_b hold the (dropout-scaled) tanh / sigmoid outputs
 // as fp16 [M, H*512].  Produces d(pre-activation) as bf16 planes in the packed column order of the gated GEMM
 // (per head: 4 groups of [128 a-cols | 128 b-cols]) and the column sums d(ba), d(bb), d(wc), d(bc).
-// One block = one row per iteration; thread t owns gate columns [8t, 8t+8).
+// Thread t owns gate columns [8t, 8t+8) for the whole kernel; a block sweeps rows two at a time.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 gate_bwd_kernel(const __half* __restrict__ gate_a, const __half* __restrict__ gate_b, const float* __restrict__ dlogit,
                 const float* __restrict__ wc, long long M, int n_heads, float drop_p, unsigned long long seed,
                 __nv_bfloat16* __restrict__ dpre, long long plane_stride, int nplanes,
@@ -316,41 +288,56 @@ gate_bwd_kernel(const __half* __restrict__ gate_a, const __half* __restrict__ ga
     for (int i = 0; i < 8; ++i) { w[i] = __ldg(wc + j0 + i); s_a[i] = 0.f; s_b[i] = 0.f; s_w[i] = 0.f; }
     float s_c = 0.f;
     const float keep_inv = drop_p > 0.f ? (1.f - drop_p) : 1.f;
-    for (long long m = blockIdx.x; m < M; m += gridDim.x) {
-        const float dl = __ldg(dlogit + m * n_heads + head);
-        const uint4 ua = __ldg(reinterpret_cast<const uint4*>(gate_a + m * HC + j0));
-        const uint4 ub = __ldg(reinterpret_cast<const uint4*>(gate_b + m * HC + j0));
-        const __half2* ha = reinterpret_cast<const __half2*>(&ua);
-        const __half2* hb = reinterpret_cast<const __half2*>(&ub);
-        __nv_bfloat16 ah[8], al[8], bh[8], bl[8];
+    constexpr int R = 2;
+    for (long long m0 = (long long)blockIdx.x * R; m0 < M; m0 += (long long)gridDim.x * R) {
+        uint4 ua[R], ub[R];
+        float dl[R];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float2 fa = __half22float2(ha[i >> 1]);
-            const float2 fb = __half22float2(hb[i >> 1]);
-            const float ad = (i & 1) ? fa.y : fa.x;   // dropout-scaled gates
-            const float bd = (i & 1) ? fb.y : fb.x;
-            float sa = 1.f, sb = 1.f;
-            if (drop_p > 0.f) {
-                const uint64_t idx = (uint64_t)m * (uint64_t)HC + (uint64_t)(j0 + i);
-                sa = dropout_scale(drop_p, seed, 10u, idx);
-                sb = dropout_scale(drop_p, seed, 11u, idx);
-            }
-            const float a = ad * (sa != 0.f ? keep_inv : 0.f);  // undo the 1/(1-p) scaling where kept
-            const float b = bd * (sb != 0.f ? keep_inv : 0.f);
-            const float dA = dl * w[i];
-            const float dpa = dA * bd * sa * (1.f - a * a);
-            const float dpb = dA * ad * sb * b * (1.f - b);
-            s_a[i] += dpa; s_b[i] += dpb; s_w[i] = fmaf(dl, ad * bd, s_w[i]);
-            split_bf16(dpa, ah[i], al[i]);
-            split_bf16(dpb, bh[i], bl[i]);
+        for (int r = 0; r < R; ++r) {
+            const long long m = m0 + r < M ? m0 + r : m0;
+            ua[r] = __ldg(reinterpret_cast<const uint4*>(gate_a + m * HC + j0));
+            ub[r] = __ldg(reinterpret_cast<const uint4*>(gate_b + m * HC + j0));
+            dl[r] = m0 + r < M ? __ldg(dlogit + m * n_heads + head) : 0.f;
         }
-        if (threadIdx.x % 64 == 0) s_c += dl;  // one thread per head
-        const long long o = m * (long long)(n_heads * 1024) + packed0;
-        *reinterpret_cast<uint4*>(dpre + o) = make_uint4(pack_bf16x2(ah[0], ah[1]), pack_bf16x2(ah[2], ah[3]), pack_bf16x2(ah[4], ah[5]), pack_bf16x2(ah[6], ah[7]));
-        *reinterpret_cast<uint4*>(dpre + o + 128) = make_uint4(pack_bf16x2(bh[0], bh[1]), pack_bf16x2(bh[2], bh[3]), pack_bf16x2(bh[4], bh[5]), pack_bf16x2(bh[6], bh[7]));
-        if (nplanes > 1) {
-            *reinterpret_cast<uint4*>(dpre + plane_stride + o) = make_uint4(pack_bf16x2(al[0], al[1]), pack_bf16x2(al[2], al[3]), pack_bf16x2(al[4], al[5]), pack_bf16x2(al[6], al[7]));
-            *reinterpret_cast<uint4*>(dpre + plane_stride + o + 128) = make_uint4(pack_bf16x2(bl[0], bl[1]), pack_bf16x2(bl[2], bl[3]), pack_bf16x2(bl[4], bl[5]), pack_bf16x2(bl[6], bl[7]));
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (m0 + r >= M) break;
+            const long long m = m0 + r;
+            const __half2* ha = reinterpret_cast<const __half2*>(&ua[r]);
+            const __half2* hb = reinterpret_cast<const __half2*>(&ub[r]);
+            float sa[8], sb[8];
+            {
+                float t[4];
+                const uint64_t idx4 = ((uint64_t)m * (uint64_t)HC + (uint64_t)j0) >> 2;
+                dropout_scale4(drop_p, seed, 10u, idx4, t); sa[0] = t[0]; sa[1] = t[1]; sa[2] = t[2]; sa[3] = t[3];
+                dropout_scale4(drop_p, seed, 10u, idx4 + 1, t); sa[4] = t[0]; sa[5] = t[1]; sa[6] = t[2]; sa[7] = t[3];
+                dropout_scale4(drop_p, seed, 11u, idx4, t); sb[0] = t[0]; sb[1] = t[1]; sb[2] = t[2]; sb[3] = t[3];
+                dropout_scale4(drop_p, seed, 11u, idx4 + 1, t); sb[4] = t[0]; sb[5] = t[1]; sb[6] = t[2]; sb[7] = t[3];
+            }
+            __nv_bfloat16 ah[8], al[8], bh[8], bl[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float2 fa = __half22float2(ha[i >> 1]);
+                const float2 fb = __half22float2(hb[i >> 1]);
+                const float ad = (i & 1) ? fa.y : fa.x;   // dropout-scaled gates
+                const float bd = (i & 1) ? fb.y : fb.x;
+                const float a = ad * (sa[i] != 0.f ? keep_inv : 0.f);  // undo the 1/(1-p) scaling where kept
+                const float b = bd * (sb[i] != 0.f ? keep_inv : 0.f);
+                const float dA = dl[r] * w[i];
+                const float dpa = dA * bd * sa[i] * (1.f - a * a);
+                const float dpb = dA * ad * sb[i] * b * (1.f - b);
+                s_a[i] += dpa; s_b[i] += dpb; s_w[i] = fmaf(dl[r], ad * bd, s_w[i]);
+                split_bf16(dpa, ah[i], al[i]);
+                split_bf16(dpb, bh[i], bl[i]);
+            }
+            if (threadIdx.x % 64 == 0) s_c += dl[r];  // one thread per head
+            const long long o = m * (long long)(n_heads * 1024) + packed0;
+            *reinterpret_cast<uint4*>(dpre + o) = make_uint4(pack_bf16x2(ah[0], ah[1]), pack_bf16x2(ah[2], ah[3]), pack_bf16x2(ah[4], ah[5]), pack_bf16x2(ah[6], ah[7]));
+            *reinterpret_cast<uint4*>(dpre + o + 128) = make_uint4(pack_bf16x2(bh[0], bh[1]), pack_bf16x2(bh[2], bh[3]), pack_bf16x2(bh[4], bh[5]), pack_bf16x2(bh[6], bh[7]));
+            if (nplanes > 1) {
+                *reinterpret_cast<uint4*>(dpre + plane_stride + o) = make_uint4(pack_bf16x2(al[0], al[1]), pack_bf16x2(al[2], al[3]), pack_bf16x2(al[4], al[5]), pack_bf16x2(al[6], al[7]));
+                *reinterpret_cast<uint4*>(dpre + plane_stride + o + 128) = make_uint4(pack_bf16x2(bl[0], bl[1]), pack_bf16x2(bl[2], bl[3]), pack_bf16x2(bl[4], bl[5]), pack_bf16x2(bl[6], bl[7]));
+            }
         }
     }
 #pragma unroll
@@ -471,12 +458,14 @@ int mdl_ln_gelu_fwd(const float* z, long long M, int C, const float* gamma, cons
                     void* planes, long long plane_stride, int nplanes, float* mean, float* rstd, void* stream) {
     MDL_REQUIRE(C == 512 || C == 2048, "ln_gelu_fwd: C must be 512 or 2048 (got %d)", C);
     if (M == 0) return 0;
-    const int rows_per_block = C == 512 ? 8 : 2;
-    const int grid = grid_for(M, rows_per_block, 8);
-    if (C == 512)
-        ln_gelu_fwd_kernel<512><<<grid, 256, 0, (cudaStream_t)stream>>>(z, M, gamma, beta, eps, drop_p, seed, stream_id, (__nv_bfloat16*)planes, plane_stride, nplanes, mean, rstd);
-    else
-        ln_gelu_fwd_kernel<2048><<<grid, 256, 0, (cudaStream_t)stream>>>(z, M, gamma, beta, eps, drop_p, seed, stream_id, (__nv_bfloat16*)planes, plane_stride, nplanes, mean, rstd);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C == 512) {
+        const int grid = grid_for(M, 8 * 2, 6);
+        ln_gelu_fwd_kernel<512, 2><<<grid, 256, 0, st>>>(z, M, gamma, beta, eps, drop_p, seed, stream_id, (__nv_bfloat16*)planes, plane_stride, nplanes, mean, rstd);
+    } else {
+        const int grid = grid_for(M, 8, 4);
+        ln_gelu_fwd_kernel<2048, 1><<<grid, 256, 0, st>>>(z, M, gamma, beta, eps, drop_p, seed, stream_id, (__nv_bfloat16*)planes, plane_stride, nplanes, mean, rstd);
+    }
     MDL_CHECK_LAUNCH();
     return 0;
 }
@@ -489,15 +478,17 @@ int mdl_ln_gelu_bwd(const float* z, long long M, int C, const float* gamma, cons
                     void* dz_planes, long long plane_stride, int nplanes,
                     float* dgamma, float* dbeta, float* dbias, void* stream) {
     MDL_REQUIRE(C == 512 || C == 2048, "ln_gelu_bwd: C must be 512 or 2048 (got %d)", C);
-    MDL_REQUIRE(n_heads > 0 && C % n_heads == 0, "ln_gelu_bwd: bad n_heads");
+    MDL_REQUIRE(n_heads > 0 && C % n_heads == 0 && (C / n_heads) % 4 == 0, "ln_gelu_bwd: bad n_heads");
     if (M == 0) return 0;
     PoolTerm t0{pool_p0, pool_dS0, pool_seg0}, t1{pool_p1, pool_dS1, pool_seg1};
-    const int rows_per_block = C == 512 ? 8 : 2;
-    const int grid = grid_for(M, rows_per_block * 8, 4);  // several rows per block so the column atomics amortise
-    if (C == 512)
-        ln_gelu_bwd_kernel<512><<<grid, 256, 0, (cudaStream_t)stream>>>(z, M, gamma, beta, mean, rstd, dh_a, dh_b, t0, t1, n_heads, drop_p, seed, stream_id, (__nv_bfloat16*)dz_planes, plane_stride, nplanes, dgamma, dbeta, dbias);
-    else
-        ln_gelu_bwd_kernel<2048><<<grid, 256, 0, (cudaStream_t)stream>>>(z, M, gamma, beta, mean, rstd, dh_a, dh_b, t0, t1, n_heads, drop_p, seed, stream_id, (__nv_bfloat16*)dz_planes, plane_stride, nplanes, dgamma, dbeta, dbias);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C == 512) {
+        const int grid = grid_for(M, 4 * 2 * 4, 2);   // several iterations per block so the column atomics amortise
+        ln_gelu_bwd_kernel<512, 2><<<grid, 512, 0, st>>>(z, M, gamma, beta, mean, rstd, dh_a, dh_b, t0, t1, n_heads, drop_p, seed, stream_id, (__nv_bfloat16*)dz_planes, plane_stride, nplanes, dgamma, dbeta, dbias);
+    } else {
+        const int grid = grid_for(M, 1 * 2 * 8, 2);
+        ln_gelu_bwd_kernel<2048, 2><<<grid, 512, 0, st>>>(z, M, gamma, beta, mean, rstd, dh_a, dh_b, t0, t1, n_heads, drop_p, seed, stream_id, (__nv_bfloat16*)dz_planes, plane_stride, nplanes, dgamma, dbeta, dbias);
+    }
     MDL_CHECK_LAUNCH();
     return 0;
 }
@@ -507,7 +498,7 @@ int mdl_gate_bwd(const void* gate_a, const void* gate_b, const float* dlogit, co
                  float* dba, float* dbb, float* dwc, float* dbc, void* stream) {
     MDL_REQUIRE(n_heads == 4, "gate_bwd: only n_heads == 4 is built (got %d)", n_heads);
     if (M == 0) return 0;
-    const int grid = grid_for(M, 16, 4);
+    const int grid = grid_for(M, 32, 3);
     gate_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)gate_a, (const __half*)gate_b, dlogit, wc, M, n_heads, drop_p, seed,
                                                            (__nv_bfloat16*)dpre_planes, plane_stride, nplanes, dba, dbb, dwc, dbc);
     MDL_CHECK_LAUNCH();

@@ -5,8 +5,8 @@
 // tensor pipe, |err| ~ 2^-16); nsplit = 1 uses the hi planes only (plain bf16, what the reference's autocast
 // scripts compute).  The three passes are just three TMA coordinate schedules over the same kernel.
 //
-// Roles (192 threads): warp 0 = TMA producer (1 lane), warp 1 = TMEM owner + MMA issuer (1 lane),
-// warps 2..5 = epilogue (TMEM lane quadrant = warp_id % 4).  Two 256-column accumulator stages let the epilogue of
+// Roles (320 threads): warp 0 = TMA producer (1 lane), warp 1 = TMEM owner + MMA issuer (1 lane),
+// warps 2..9 = epilogue (TMEM lane quadrant = warp_id % 4, two warps per quadrant split the columns).  Two 256-column accumulator stages let the epilogue of
 // tile i overlap the MMAs of tile i+1.  Grid = min(#work units, 148): one CTA per SM, static round-robin.
 //
 // Modes
@@ -29,7 +29,8 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int STAGES = 4;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;   // 2 control warps + 8 epilogue warps
+constexpr int EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
 
 enum { EPI_STORE = 0, EPI_GATED = 1, EPI_ATOMIC = 2 };
@@ -61,7 +62,9 @@ struct SmemLayout {
     static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + tmem ptr + alignment slack
+    static constexpr int AUX_OFFSET = BAR_OFFSET + 256;                 // gated epilogue: ba | bb | wc (3 x 2048 floats) + partials
+    static constexpr int AUX_BYTES = 3 * 2048 * 4 + 2 * 128 * 4;
+    static constexpr int TOTAL = AUX_OFFSET + AUX_BYTES + 1024;         // + alignment slack
 };
 
 template <int BLOCK_N, bool kMNMajor, int EPI>
@@ -85,12 +88,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar(s), 1); mbar_init(tmem_empty_bar(s), 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar(s), 1); mbar_init(tmem_empty_bar(s), EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) {
         tmem_alloc(tmem_ptr_addr, TMEM_COLS);
         tmem_relinquish();
+    }
+    float* aux = reinterpret_cast<float*>(smem_raw + (smem_base + L::AUX_OFFSET - smem_u32(smem_raw)));
+    if constexpr (EPI == EPI_GATED) {
+        const int hc = p.n_heads * 512;   // <= 2048
+        for (int i = threadIdx.x; i < hc; i += GEMM_THREADS) {
+            aux[i] = __ldg(p.ba + i); aux[2048 + i] = __ldg(p.bb + i); aux[4096 + i] = __ldg(p.wc + i);
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -196,9 +206,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
         }
     } else {
-        // ===================== epilogue warps =====================
-        const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+        // ===================== epilogue warps (8) =====================
+        const int quad = warp & 3;             // TMEM lane quadrant this warp may read
+        const int half = (warp - 2) >> 2;      // which half of the tile's columns this warp drains
         int acc = 0; uint32_t acc_phase = 0;
+        int unit_parity = 0;
         for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
             int m_tile, n_group, kb0, kb1;
             decode(unit, m_tile, n_group, kb0, kb1);
@@ -214,8 +226,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 if constexpr (EPI == EPI_STORE) {
                     int bag = 0;
                     if (p.rowbias != nullptr && row_ok) bag = p.row2bag[m];
+                    constexpr int CH = BLOCK_N / 64;   // 32-column chunks per half
 #pragma unroll 1
-                    for (int c = 0; c < BLOCK_N / 32; ++c) {
+                    for (int cc = 0; cc < CH; ++cc) {
+                        const int c = half * CH + cc;
                         uint32_t r[32];
                         tmem_ld_32x32(t_row + c * 32, r);
                         tmem_ld_wait();
@@ -240,22 +254,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         }
                     }
                 } else if constexpr (EPI == EPI_ATOMIC) {
+                    constexpr int CH = BLOCK_N / 64;
 #pragma unroll 1
-                    for (int c = 0; c < BLOCK_N / 32; ++c) {
+                    for (int cc = 0; cc < CH; ++cc) {
+                        const int c = half * CH + cc;
                         uint32_t r[32];
                         tmem_ld_32x32(t_row + c * 32, r);
                         tmem_ld_wait();
                         if (row_ok && have_k) {
                             float* dst = p.out + (size_t)m * p.ldc + n_tile * BLOCK_N + c * 32;
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) atomicAdd(dst + i, __uint_as_float(r[i]));
+                            for (int i = 0; i < 32; i += 4)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(__uint_as_float(r[i])),
+                                             "f"(__uint_as_float(r[i + 1])), "f"(__uint_as_float(r[i + 2])), "f"(__uint_as_float(r[i + 3])) : "memory");
                         }
                     }
                 } else {  // EPI_GATED
                     const int head = n_group;          // one work unit = (m_tile, head); inner = 128-wide gate group
                     const int j_base = head * 512 + inner * 128;
+                    const int HC = p.n_heads * 512;
 #pragma unroll 1
-                    for (int c = 0; c < 4; ++c) {
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const int c = half * 2 + cc;
                         uint32_t ra[32], rb[32];
                         tmem_ld_32x32(t_row + c * 32, ra);
                         tmem_ld_32x32(t_row + 128 + c * 32, rb);
@@ -263,24 +283,33 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         const int j0 = j_base + c * 32;
                         uint32_t ha[16], hb[16];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            float a = tanh_acc(__uint_as_float(ra[i]) + __ldg(p.ba + j0 + i));
-                            float b = sigmoid_acc(__uint_as_float(rb[i]) + __ldg(p.bb + j0 + i));
-                            if (p.drop_p > 0.f) {
-                                const uint64_t idx = (uint64_t)m * (uint64_t)(p.n_heads * 512) + (uint64_t)(j0 + i);
-                                a *= dropout_scale(p.drop_p, p.seed, 10u, idx);
-                                b *= dropout_scale(p.drop_p, p.seed, 11u, idx);
+                        for (int i4 = 0; i4 < 8; ++i4) {
+                            const float4 vba = *reinterpret_cast<const float4*>(aux + j0 + 4 * i4);
+                            const float4 vbb = *reinterpret_cast<const float4*>(aux + 2048 + j0 + 4 * i4);
+                            const float4 vwc = *reinterpret_cast<const float4*>(aux + 4096 + j0 + 4 * i4);
+                            const float fba[4] = {vba.x, vba.y, vba.z, vba.w}, fbb[4] = {vbb.x, vbb.y, vbb.z, vbb.w};
+                            const float fwc[4] = {vwc.x, vwc.y, vwc.z, vwc.w};
+                            float ma[4], mb[4];
+                            const uint64_t idx4 = ((uint64_t)m * (uint64_t)HC + (uint64_t)(j0 + 4 * i4)) >> 2;
+                            dropout_scale4(p.drop_p, p.seed, 10u, idx4, ma);
+                            dropout_scale4(p.drop_p, p.seed, 11u, idx4, mb);
+                            float av[4], bv[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                av[i] = tanh_acc(__uint_as_float(ra[4 * i4 + i]) + fba[i]) * ma[i];
+                                bv[i] = sigmoid_acc(__uint_as_float(rb[4 * i4 + i]) + fbb[i]) * mb[i];
+                                gated_partial = fmaf(av[i] * bv[i], fwc[i], gated_partial);
                             }
-                            gated_partial = fmaf(a * b, __ldg(p.wc + j0 + i), gated_partial);
                             if (p.gate_a != nullptr) {
-                                const uint32_t ua = __half_as_ushort(__float2half_rn(a)), ub = __half_as_ushort(__float2half_rn(b));
-                                if (i & 1) { ha[i >> 1] |= ua << 16; hb[i >> 1] |= ub << 16; }
-                                else { ha[i >> 1] = ua; hb[i >> 1] = ub; }
+                                const __half2 a01 = __floats2half2_rn(av[0], av[1]), a23 = __floats2half2_rn(av[2], av[3]);
+                                const __half2 b01 = __floats2half2_rn(bv[0], bv[1]), b23 = __floats2half2_rn(bv[2], bv[3]);
+                                ha[2 * i4] = *reinterpret_cast<const uint32_t*>(&a01); ha[2 * i4 + 1] = *reinterpret_cast<const uint32_t*>(&a23);
+                                hb[2 * i4] = *reinterpret_cast<const uint32_t*>(&b01); hb[2 * i4 + 1] = *reinterpret_cast<const uint32_t*>(&b23);
                             }
                         }
                         if (p.gate_a != nullptr && row_ok) {
-                            uint4* da = reinterpret_cast<uint4*>(p.gate_a + (size_t)m * (p.n_heads * 512) + j0);
-                            uint4* db = reinterpret_cast<uint4*>(p.gate_b + (size_t)m * (p.n_heads * 512) + j0);
+                            uint4* da = reinterpret_cast<uint4*>(p.gate_a + (size_t)m * HC + j0);
+                            uint4* db = reinterpret_cast<uint4*>(p.gate_b + (size_t)m * HC + j0);
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 da[i] = make_uint4(ha[4 * i], ha[4 * i + 1], ha[4 * i + 2], ha[4 * i + 3]);
@@ -288,8 +317,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             }
                         }
                     }
-                    if (inner == p.n_inner - 1 && row_ok)
-                        p.logits[(size_t)m * p.n_heads + head] = gated_partial + __ldg(p.bc + head);
+                    if (inner == p.n_inner - 1) {
+                        // combine the two column halves of this row: half 1 hands its partial to half 0 through smem
+                        float* part = aux + 6144 + unit_parity * 128;
+                        if (half == 1) part[quad * 32 + lane] = gated_partial;
+                        asm volatile("bar.sync 1, 256;" ::: "memory");
+                        if (half == 0 && row_ok)
+                            p.logits[(size_t)m * p.n_heads + head] = gated_partial + part[quad * 32 + lane] + __ldg(p.bc + head);
+                    }
                 }
                 (void)have_k;
                 tc_fence_before();
@@ -297,6 +332,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
+            unit_parity ^= 1;
         }
     }
 

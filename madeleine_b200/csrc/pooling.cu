@@ -8,8 +8,9 @@
 // delimited by cu_seqlens[R+1]; an optional tok_idx list turns a segment into a gather (n_views = 3 half views).
 // Algorithmic bytes per bag (forward): N*H*E*2*nplanes + N*H*4 + H*E*4.
 //
-// Work decomposition (forward): one CTA = (bag, head, 256-channel half, token split). The softmax statistics of the
-// (bag, head) column are recomputed per CTA from the logits (N*4 bytes, L2-resident), so CTAs never exchange data;
+// Work decomposition (forward): a tiny statistics kernel (one CTA per bag) turns the logits into attention weights
+// p[t, h] once; the streaming kernel runs one CTA per (bag, head, 256-channel half, token chunk of ~192 tokens) so the
+// 148 SMs see thousands of equal, prologue-free work items and the tail is short;
 // token splits write partial sums to a workspace and the last CTA to finish (atomic ticket) adds them in split
 // order, so the result is bit-reproducible run to run.  Each lane streams 16-byte vectors (8 bf16 channels),
 // a warp covers 512 contiguous bytes per plane per token, 4 tokens are in flight per warp.
@@ -60,12 +61,43 @@ __device__ __forceinline__ float attn_weight_grad(float l, float w, int act) {  
     }
 }
 
-template <int NPLANES>
+// attention weights of one (bag, head): p[t, h] = act(logit) (softmax over the bag's tokens, or a pointwise activation).
 __global__ void __launch_bounds__(POOL_THREADS)
-pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long plane_stride, const float* __restrict__ logits,
-                const int* __restrict__ cu, const int* __restrict__ tok_idx, int H, int E, int tsplit,
-                float* __restrict__ out, float* __restrict__ attn_p, float* __restrict__ partial, int* __restrict__ tickets, int act) {
+pool_weights_kernel(const float* __restrict__ logits, const int* __restrict__ cu, const int* __restrict__ tok_idx, int H,
+                    float* __restrict__ attn_p, int act) {
     __shared__ float scratch[33];
+    const int r = blockIdx.x;
+    const int t0 = cu[r], n = cu[r + 1] - t0;
+    {
+        const int h = blockIdx.y;
+        float mx = 0.f, inv = 1.f;
+        if (act == ACT_SOFTMAX) {
+            mx = -INFINITY;
+            for (int i = threadIdx.x; i < n; i += POOL_THREADS) {
+                const long long row = tok_idx ? tok_idx[t0 + i] : (t0 + i);
+                mx = fmaxf(mx, __ldg(logits + row * H + h));
+            }
+            mx = block_max(mx, scratch);
+            float sm = 0.f;
+            for (int i = threadIdx.x; i < n; i += POOL_THREADS) {
+                const long long row = tok_idx ? tok_idx[t0 + i] : (t0 + i);
+                sm += __expf(__ldg(logits + row * H + h) - mx);
+            }
+            sm = block_sum(sm, scratch);
+            inv = n > 0 ? 1.f / sm : 0.f;
+        }
+        for (int i = threadIdx.x; i < n; i += POOL_THREADS) {
+            const long long row = tok_idx ? tok_idx[t0 + i] : (t0 + i);
+            attn_p[row * H + h] = attn_weight(__ldg(logits + row * H + h), mx, inv, act);
+        }
+    }
+}
+
+template <int NPLANES>
+__global__ void __launch_bounds__(POOL_THREADS, 4)
+pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long plane_stride, const float* __restrict__ attn_p,
+                const int* __restrict__ cu, const int* __restrict__ tok_idx, int H, int E, int tsplit,
+                float* __restrict__ out, float* __restrict__ partial, int* __restrict__ tickets) {
     __shared__ int is_last;
     __shared__ float part[POOL_WARPS][256];
     const int halves = E / 256;
@@ -74,25 +106,6 @@ pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long plane_stride, con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t0 = cu[r], n = cu[r + 1] - t0;
     const int C = H * E;
-
-    // softmax statistics of (bag r, head h) over all n tokens (act == ACT_SOFTMAX only)
-    float mx = 0.f, inv = 1.f;
-    if (act == ACT_SOFTMAX) {
-        mx = -INFINITY;
-        for (int i = threadIdx.x; i < n; i += POOL_THREADS) {
-            const long long row = tok_idx ? tok_idx[t0 + i] : (t0 + i);
-            mx = fmaxf(mx, __ldg(logits + row * H + h));
-        }
-        mx = block_max(mx, scratch);
-        float sm = 0.f;
-        for (int i = threadIdx.x; i < n; i += POOL_THREADS) {
-            const long long row = tok_idx ? tok_idx[t0 + i] : (t0 + i);
-            sm += __expf(__ldg(logits + row * H + h) - mx);
-        }
-        sm = block_sum(sm, scratch);
-        inv = n > 0 ? 1.f / sm : 0.f;
-    }
-
     const int per = (n + tsplit - 1) / tsplit;
     const int i_begin = split * per, i_end = min(n, i_begin + per);
     const int col = h * E + half * 256 + lane * 8;
@@ -105,22 +118,20 @@ pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long plane_stride, con
     for (int i = i_begin + warp; i < i_end; i += POOL_WARPS * UNROLL) {
         uint4 vh[UNROLL], vl[UNROLL];
         float w[UNROLL];
-        long long rows[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const int ii = i + u * POOL_WARPS;
             const bool ok = ii < i_end;
             const int pos = ok ? ii : i;
-            rows[u] = tok_idx ? tok_idx[t0 + pos] : (long long)(t0 + pos);
-            vh[u] = ldg_stream(x + rows[u] * C + col);
-            if (NPLANES > 1) vl[u] = ldg_stream(x + plane_stride + rows[u] * C + col);
-            w[u] = ok ? attn_weight(__ldg(logits + rows[u] * H + h), mx, inv, act) : 0.f;
+            const long long row = tok_idx ? tok_idx[t0 + pos] : (long long)(t0 + pos);
+            vh[u] = ldg_stream(x + row * C + col);
+            if (NPLANES > 1) vl[u] = ldg_stream(x + plane_stride + row * C + col);
+            w[u] = ok ? __ldg(attn_p + row * H + h) : 0.f;
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             fma8(acc, w[u], vh[u]);
             if (NPLANES > 1) fma8(acc, w[u], vl[u]);
-            if (attn_p != nullptr && half == 0 && lane == 0 && (i + u * POOL_WARPS) < i_end) attn_p[rows[u] * H + h] = w[u];
         }
     }
 #pragma unroll
@@ -239,12 +250,10 @@ __global__ void planes_to_ref_order_kernel(const __nv_bfloat16* __restrict__ x, 
 }
 
 static int choose_tsplit(int R, int H, int halves, long long total_tokens) {
-    const long long base = (long long)R * H * halves;
-    if (base <= 0) return 1;
-    long long s = (4LL * kNumSMs + base - 1) / base;
-    const long long avg = total_tokens / (R > 0 ? R : 1);
-    const long long max_s = avg / 64 > 1 ? avg / 64 : 1;  // keep >= 64 tokens per split
-    if (s > max_s) s = max_s;
+    (void)H; (void)halves;
+    if (R <= 0) return 1;
+    const long long avg = total_tokens / R;
+    long long s = (avg + 191) / 192;          // ~192 tokens per CTA: thousands of equal work items, short tail
     if (s < 1) s = 1;
     if (s > 64) s = 64;
     return (int)s;
@@ -262,6 +271,7 @@ int mdl_pool_fwd(const void* x_planes, long long plane_stride, int nplanes, cons
     MDL_REQUIRE(activation >= 0 && activation <= 3, "pool_fwd: unknown activation %d", activation);
     MDL_REQUIRE(head_dim % 256 == 0, "pool_fwd: head_dim must be a multiple of 256 (got %d)", head_dim);
     MDL_REQUIRE(nplanes == 1 || nplanes == 2, "pool_fwd: nplanes must be 1 or 2");
+    MDL_REQUIRE(attn_p != nullptr, "pool_fwd: attn_p ([tokens, n_heads] fp32) is required");
     if (n_bags == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     const int halves = head_dim / 256;
@@ -273,11 +283,13 @@ int mdl_pool_fwd(const void* x_planes, long long plane_stride, int nplanes, cons
         tickets = reinterpret_cast<int*>(partial + (size_t)tsplit * n_bags * n_heads * head_dim);
         MDL_CHECK_CUDA(cudaMemsetAsync(tickets, 0, sizeof(int) * (size_t)n_bags * n_heads * halves, st));
     }
+    pool_weights_kernel<<<dim3(n_bags, n_heads), POOL_THREADS, 0, st>>>(logits, cu_seqlens, tok_idx, n_heads, attn_p, activation);
+    MDL_CHECK_LAUNCH();
     dim3 grid(halves * tsplit, n_heads, n_bags);
     if (nplanes == 2)
-        pool_fwd_kernel<2><<<grid, POOL_THREADS, 0, st>>>((const __nv_bfloat16*)x_planes, plane_stride, logits, cu_seqlens, tok_idx, n_heads, head_dim, tsplit, out, attn_p, partial, tickets, activation);
+        pool_fwd_kernel<2><<<grid, POOL_THREADS, 0, st>>>((const __nv_bfloat16*)x_planes, plane_stride, attn_p, cu_seqlens, tok_idx, n_heads, head_dim, tsplit, out, partial, tickets);
     else
-        pool_fwd_kernel<1><<<grid, POOL_THREADS, 0, st>>>((const __nv_bfloat16*)x_planes, plane_stride, logits, cu_seqlens, tok_idx, n_heads, head_dim, tsplit, out, attn_p, partial, tickets, activation);
+        pool_fwd_kernel<1><<<grid, POOL_THREADS, 0, st>>>((const __nv_bfloat16*)x_planes, plane_stride, attn_p, cu_seqlens, tok_idx, n_heads, head_dim, tsplit, out, partial, tickets);
     MDL_CHECK_LAUNCH();
     return 0;
 }

@@ -234,6 +234,8 @@ def gemm_tn_accum(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, nsplit: i
 def pool_fwd(h3, npl, logits, cu, tok_idx, R, total_tokens, H, E, out, attn_p, act, tsplit=0):
     """Attention pooling; picks the token split and provides the (deterministic) partial-sum workspace."""
     M, C = h3.shape[1], h3.shape[2]
+    if attn_p is None:
+        attn_p = torch.empty(M, H, dtype=torch.float32, device=h3.device)
     if tsplit <= 0:
         tsplit = call("mdl_pool_tsplit", R, total_tokens, H, E)
     ws = None

@@ -17,13 +17,15 @@ def calculate_losses(STAINS, loss_fn_interMod, loss_fn_interMod_local, loss_fn_i
     InfoNCE on the two half views), summed.  Returns (loss, at_least_one_stain_flag); loss is -1 when nothing applies."""
     losses = []
     atleast_two_loss_flag = False
-    labels = modality_labels_withoutHE.to(wsi_embs["HE"].device)
-    # one host sync for all stains instead of one .item() per stain
-    counts = labels.bool().sum(dim=0).tolist()
+    dev = wsi_embs["HE"].device
+    # The availability mask comes from the dataloader on the CPU (as in the reference); keeping the case selection on
+    # the host avoids the device sync that boolean-mask indexing of CUDA tensors costs every step.
+    labels = modality_labels_withoutHE.detach().to("cpu").bool()
+    counts = labels.sum(dim=0).tolist()
     for stain_idx, stain in enumerate(STAINS):
         if counts[stain_idx] <= 1:
             continue
-        stain_mask = labels[:, stain_idx].bool()
+        stain_mask = labels[:, stain_idx].nonzero(as_tuple=True)[0].to(dev, non_blocking=True)   # row indices of the cases
         if loss_fn_interMod:
             if args.global_loss != "info-nce":
                 raise AssertionError("invalid global loss")

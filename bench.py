@@ -210,17 +210,17 @@ def main():
     feats_host = [torch.randn(B, N_STAINS, N_TOKENS, D_IN).pin_memory() for _ in range(2)]  # e2e: pinned host buffers
     labels = torch.ones(B, N_STAINS)
     labels_dev = labels.to(dev)
+    labels_global = torch.ones(B * world, N_STAINS)      # the loader knows the whole batch's availability mask (case list)
+    parallel.enable_gradient_sync(world > 1)
 
     def step(feats):
         model.zero_grad(set_to_none=True)
         embs, toks = model({"feats": feats}, device=dev, n_views=1)
         lab = labels                      # availability mask stays on the host (as the reference's dataloader delivers it)
         if world > 1:
-            embs, lab = parallel.gather_slide_embeddings(embs, labels_dev)
+            embs, lab = parallel.gather_slide_embeddings(embs, labels_dev, global_labels_host=labels_global)
         loss, ok = calculate_losses(MODS[1:], loss_fn, None, None, embs, toks, lab[:, 1:], largs)
-        loss.backward()
-        if world > 1:
-            parallel.allreduce_gradients(model)
+        loss.backward()               # world > 1: the encoder backward all-reduces its flat gradient buffer (enable_gradient_sync)
         return loss
 
     def timed(n_steps, feats_fn, read_loss):

@@ -238,6 +238,16 @@ __device__ __forceinline__ uint64_t make_umma_desc_sw128(uint32_t smem_addr, uin
     d |= (uint64_t)2 << 61;
     return d;
 }
+// Same, 64-byte swizzle (layout type 4): rows of 64 B, 8-row atoms 512 B apart.
+__device__ __forceinline__ uint64_t make_umma_desc_sw64(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 D.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, bool a_mn_major, bool b_mn_major) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |

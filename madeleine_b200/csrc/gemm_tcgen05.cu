@@ -10,6 +10,9 @@
 // tile i overlap the MMAs of tile i+1.  Grid = min(#work units, 148): one CTA per SM, static round-robin.
 //
 // Modes
+//   MODE_KF : like MODE_K for the 3-pass split: one pipeline stage holds A_hi, A_lo, B_hi, B_lo of a 32-wide k-block
+//             (64-byte swizzle) and feeds all three products, so every operand byte crosses L2->SM once instead of
+//             A_hi and B_hi twice (the K=512 GEMMs were L2-operand-bandwidth bound: -35 % traffic, same stage depth).
 //   kKMajor : C[M,N] = A[M,K] * B[N,K]^T, both operands contiguous along K (forward and dgrad GEMMs).
 //   kMNMajor: C[M,N] = sum_t A[t,M]^T B[t,N], both operands contiguous along their output index (wgrad;
 //             t = tokens), split over t across CTAs with fp32 red.add accumulation.
@@ -22,6 +25,7 @@
 #include "madeleine_b200.h"
 #include <cuda.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace mdl {
 
@@ -34,6 +38,8 @@ constexpr int EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
 
 enum { EPI_STORE = 0, EPI_GATED = 1, EPI_ATOMIC = 2 };
+enum { MODE_K = 0, MODE_MN = 1, MODE_KF = 2 };
+constexpr int BLOCK_KF = 32;  // fused-pass k-block: 32 bf16 = one 64-byte swizzle row
 
 struct GemmArgs {
     int M, N;                 // output extent
@@ -58,18 +64,23 @@ struct GemmArgs {
 
 template <int BLOCK_N>
 struct SmemLayout {
+    // identical totals in every mode: classic = one plane x 64 k, fused = two planes x 32 k
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
     static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-    static constexpr int AUX_OFFSET = BAR_OFFSET + 256;                 // gated epilogue: ba | bb | wc (3 x 2048 floats) + partials
-    static constexpr int AUX_BYTES = 3 * 2048 * 4 + 2 * 128 * 4;
+    static constexpr int AUX_OFFSET = BAR_OFFSET + 256;
+    // aux region: gated epilogue = ba | bb | wc (3 x 2048 floats) + 2 x 128 partials; store/atomic epilogues = one padded
+    // 32 x 33 fp32 transpose buffer per epilogue warp
+    static constexpr int AUX_BYTES = 8 * 32 * 33 * 4;
     static constexpr int TOTAL = AUX_OFFSET + AUX_BYTES + 1024;         // + alignment slack
 };
 
-template <int BLOCK_N, bool kMNMajor, int EPI>
+template <int BLOCK_N, int MODE, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmArgs p) {
+    constexpr bool kMNMajor = MODE == MODE_MN;
+    constexpr bool kFused = MODE == MODE_KF;
     using L = SmemLayout<BLOCK_N>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
@@ -131,6 +142,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 decode(unit, m_tile, n_group, kb0, kb1);
                 for (int inner = 0; inner < p.n_inner; ++inner) {
                     const int n_tile = n_group * p.n_inner + inner;
+                    if constexpr (kFused) {
+                        const int a_k0 = (n_tile / p.grp_n_tiles) * p.a_koff;
+                        for (int kb = kb0; kb < kb1; ++kb) {
+                            mbar_wait(empty_bar(stage), phase ^ 1u);
+                            const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
+                            const uint32_t sb = sa + L::A_BYTES;
+                            mbar_arrive_expect_tx(full_bar(stage), L::STAGE_BYTES);
+                            tma_load_3d(sa, &tmap_a, full_bar(stage), a_k0 + kb * BLOCK_KF, m_tile * BLOCK_M, 0);
+                            tma_load_3d(sa + L::A_BYTES / 2, &tmap_a, full_bar(stage), a_k0 + kb * BLOCK_KF, m_tile * BLOCK_M, 1);
+                            tma_load_3d(sb, &tmap_b, full_bar(stage), kb * BLOCK_KF, n_tile * BLOCK_N, 0);
+                            tma_load_3d(sb + L::B_BYTES / 2, &tmap_b, full_bar(stage), kb * BLOCK_KF, n_tile * BLOCK_N, 1);
+                            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                        }
+                        continue;
+                    }
                     for (int kb = kb0; kb < kb1; ++kb) {
                         for (int pass = 0; pass < p.nsplit; ++pass) {
                             const int plane_a = pass == 2 ? 1 : 0;
@@ -174,6 +200,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
                     uint32_t accumulate = 0;
+                    if constexpr (kFused) {
+                        for (int kb = kb0; kb < kb1; ++kb) {
+                            mbar_wait(full_bar(stage), phase);
+                            tc_fence_after();
+                            const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
+                            const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+                            for (int k = 0; k < BLOCK_KF / UMMA_K; ++k) {
+                                // rows of 64 B, 8-row atoms 512 B apart; step 16 elements = 32 B along the row
+                                const uint64_t a_hi = make_umma_desc_sw64(sa + k * (UMMA_K * 2), 16, 512);
+                                const uint64_t a_lo = make_umma_desc_sw64(sa + L::A_BYTES / 2 + k * (UMMA_K * 2), 16, 512);
+                                const uint64_t b_hi = make_umma_desc_sw64(sb + k * (UMMA_K * 2), 16, 512);
+                                const uint64_t b_lo = make_umma_desc_sw64(sb + L::B_BYTES / 2 + k * (UMMA_K * 2), 16, 512);
+                                umma_bf16(tmem_d, a_hi, b_hi, idesc, accumulate);
+                                umma_bf16(tmem_d, a_hi, b_lo, idesc, 1u);
+                                umma_bf16(tmem_d, a_lo, b_hi, idesc, 1u);
+                                accumulate = 1;
+                            }
+                            umma_commit(empty_bar(stage));
+                            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                        }
+                        umma_commit(tmem_full_bar(acc));
+                        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                        continue;
+                    }
                     for (int kb = kb0; kb < kb1; ++kb) {
                         for (int pass = 0; pass < p.nsplit; ++pass) {
                             mbar_wait(full_bar(stage), phase);
@@ -223,9 +274,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
                 const bool have_k = kb1 > kb0;  // empty split-K slice: accumulator is stale, skip
-                if constexpr (EPI == EPI_STORE) {
+                if constexpr (EPI == EPI_STORE || EPI == EPI_ATOMIC) {
+                    // TMEM -> registers (thread = row) -> +bias -> warp-private padded smem -> row-contiguous global access:
+                    // 8 lanes cover one 128-byte row segment, so each vector store / reduction touches 4 full lines instead
+                    // of 32 scattered 16-byte pieces.
                     int bag = 0;
-                    if (p.rowbias != nullptr && row_ok) bag = p.row2bag[m];
+                    if (EPI == EPI_STORE && p.rowbias != nullptr && row_ok) bag = p.row2bag[m];
+                    float* stg = aux + (warp - 2) * (32 * 33);
+                    const int m_warp = m_tile * BLOCK_M + quad * 32;
                     constexpr int CH = BLOCK_N / 64;   // 32-column chunks per half
 #pragma unroll 1
                     for (int cc = 0; cc < CH; ++cc) {
@@ -233,41 +289,41 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         uint32_t r[32];
                         tmem_ld_32x32(t_row + c * 32, r);
                         tmem_ld_wait();
-                        if (row_ok) {
-                            const int n0 = n_tile * BLOCK_N + c * 32;
-                            float* dst = p.out + (size_t)m * p.ldc + n0;
+                        const int n0 = n_tile * BLOCK_N + c * 32;
 #pragma unroll
-                            for (int i = 0; i < 32; i += 4) {
-                                float4 v;
-                                v.x = __uint_as_float(r[i]); v.y = __uint_as_float(r[i + 1]);
-                                v.z = __uint_as_float(r[i + 2]); v.w = __uint_as_float(r[i + 3]);
-                                if (p.bias != nullptr) {
-                                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
-                                    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                        for (int i = 0; i < 32; i += 4) {
+                            float4 v;
+                            v.x = __uint_as_float(r[i]); v.y = __uint_as_float(r[i + 1]);
+                            v.z = __uint_as_float(r[i + 2]); v.w = __uint_as_float(r[i + 3]);
+                            if (EPI == EPI_STORE && p.bias != nullptr) {
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
+                                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                            }
+                            if (EPI == EPI_STORE && p.rowbias != nullptr) {
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(p.rowbias + (size_t)bag * p.N + n0 + i));
+                                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                            }
+                            float* d = stg + lane * 33 + i;
+                            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+                        }
+                        __syncwarp();
+                        const int sub = lane >> 3, col4 = (lane & 7) * 4;
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int row = it * 4 + sub;
+                            const float* sp = stg + row * 33 + col4;
+                            const float x0 = sp[0], x1 = sp[1], x2 = sp[2], x3 = sp[3];
+                            if (m_warp + row < p.M) {
+                                float* dst = p.out + (size_t)(m_warp + row) * p.ldc + n0 + col4;
+                                if constexpr (EPI == EPI_STORE) {
+                                    *reinterpret_cast<float4*>(dst) = make_float4(x0, x1, x2, x3);
+                                } else {
+                                    if (have_k)
+                                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x0), "f"(x1), "f"(x2), "f"(x3) : "memory");
                                 }
-                                if (p.rowbias != nullptr) {
-                                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.rowbias + (size_t)bag * p.N + n0 + i));
-                                    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-                                }
-                                *reinterpret_cast<float4*>(dst + i) = v;
                             }
                         }
-                    }
-                } else if constexpr (EPI == EPI_ATOMIC) {
-                    constexpr int CH = BLOCK_N / 64;
-#pragma unroll 1
-                    for (int cc = 0; cc < CH; ++cc) {
-                        const int c = half * CH + cc;
-                        uint32_t r[32];
-                        tmem_ld_32x32(t_row + c * 32, r);
-                        tmem_ld_wait();
-                        if (row_ok && have_k) {
-                            float* dst = p.out + (size_t)m * p.ldc + n_tile * BLOCK_N + c * 32;
-#pragma unroll
-                            for (int i = 0; i < 32; i += 4)
-                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(__uint_as_float(r[i])),
-                                             "f"(__uint_as_float(r[i + 1])), "f"(__uint_as_float(r[i + 2])), "f"(__uint_as_float(r[i + 3])) : "memory");
-                        }
+                        __syncwarp();
                     }
                 } else {  // EPI_GATED
                     const int head = n_group;          // one work unit = (m_tile, head); inner = 128-wide gate group
@@ -367,26 +423,27 @@ static PFN_encodeTiled get_encode_fn() {
 // bf16 planes tensor [planes][rows][cols] (cols contiguous, row stride ld elements, plane stride in elements);
 // box = [box_cols=64][box_rows][1], 128B swizzle, OOB -> zeros.
 static int make_plane_tmap(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld,
-                           long long plane_stride, int planes, int box_rows) {
+                           long long plane_stride, int planes, int box_rows, int box_cols = 64) {
     PFN_encodeTiled enc = get_encode_fn();
     MDL_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the CUDA driver");
     MDL_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15u) == 0, "TMA base pointer must be 16-byte aligned");
     MDL_REQUIRE((ld * 2) % 16 == 0 && (plane_stride * 2) % 16 == 0, "TMA strides must be multiples of 16 bytes");
     cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)planes};
     cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane_stride * 2};
-    cuuint32_t box[3] = {64u, (cuuint32_t)box_rows, 1u};
+    cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1u};
+    const CUtensorMapSwizzle swz = box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     cuuint32_t estr[3] = {1u, 1u, 1u};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MDL_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld)", (int)r, rows, cols, ld);
     return 0;
 }
 
-template <int BLOCK_N, bool kMNMajor, int EPI>
+template <int BLOCK_N, int MODE, int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t stream) {
     using L = SmemLayout<BLOCK_N>;
-    auto kern = gemm_tcgen05_kernel<BLOCK_N, kMNMajor, EPI>;
+    auto kern = gemm_tcgen05_kernel<BLOCK_N, MODE, EPI>;
     static bool attr_set = false;  // per instantiation
     if (!attr_set) {
         MDL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -402,6 +459,16 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
     kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, args);
     MDL_CHECK_LAUNCH();
     return 0;
+}
+
+// The fused-pass schedule is the default for nsplit = 3; MDL_GEMM_FUSED=0 selects the pass-serial one (debug / A-B).
+static bool use_fused() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MDL_GEMM_FUSED");
+        v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
 }
 
 }  // namespace mdl
@@ -421,21 +488,27 @@ int mdl_gemm_nt(const void* a_planes, long long a_rows, long long a_cols, long l
     MDL_REQUIRE(M > 0, "M must be positive");
     const int planes = nsplit == 3 ? 2 : 1;
     const int bn = (N % 256 == 0) ? 256 : 128;
+    const bool fused = nsplit == 3 && use_fused();
+    const int bk = fused ? BLOCK_KF : BLOCK_K;
     CUtensorMap ta, tb;
-    int rc = make_plane_tmap(&ta, a_planes, a_rows, a_cols, lda, a_plane_stride, planes, BLOCK_M);
+    int rc = make_plane_tmap(&ta, a_planes, a_rows, a_cols, lda, a_plane_stride, planes, BLOCK_M, bk);
     if (rc) return rc;
-    rc = make_plane_tmap(&tb, b_planes, b_rows, b_cols, ldb, b_plane_stride, planes, bn);
+    rc = make_plane_tmap(&tb, b_planes, b_rows, b_cols, ldb, b_plane_stride, planes, bn, bk);
     if (rc) return rc;
     GemmArgs g{};
-    g.M = M; g.N = N; g.k_blocks = K / BLOCK_K; g.nsplit = nsplit;
+    g.M = M; g.N = N; g.k_blocks = K / bk; g.nsplit = nsplit;
     g.num_m_tiles = (M + BLOCK_M - 1) / BLOCK_M; g.num_n_tiles = N / bn; g.n_inner = 1; g.ksplit = 1;
     MDL_REQUIRE(grp_n_cols <= 0 || grp_n_cols % bn == 0, "grp_n_cols (%d) must be a multiple of the N tile (%d)", grp_n_cols, bn);
     MDL_REQUIRE(ldc % 4 == 0, "ldc must be a multiple of 4");
     g.grp_n_tiles = grp_n_cols > 0 ? grp_n_cols / bn : (1 << 30); g.a_koff = a_koff;
     g.grp_m_tiles = 1 << 30; g.b_coff = 0;
     g.out = out; g.ldc = (int)ldc; g.bias = bias; g.rowbias = rowbias; g.row2bag = row2bag;
-    if (bn == 256) return launch_gemm<256, false, EPI_STORE>(ta, tb, g, (cudaStream_t)stream);
-    return launch_gemm<128, false, EPI_STORE>(ta, tb, g, (cudaStream_t)stream);
+    if (fused) {
+        if (bn == 256) return launch_gemm<256, MODE_KF, EPI_STORE>(ta, tb, g, (cudaStream_t)stream);
+        return launch_gemm<128, MODE_KF, EPI_STORE>(ta, tb, g, (cudaStream_t)stream);
+    }
+    if (bn == 256) return launch_gemm<256, MODE_K, EPI_STORE>(ta, tb, g, (cudaStream_t)stream);
+    return launch_gemm<128, MODE_K, EPI_STORE>(ta, tb, g, (cudaStream_t)stream);
 }
 
 int mdl_gemm_gated(const void* a_planes, long long a_rows, long long a_cols, long long lda, long long a_plane_stride,
@@ -447,19 +520,22 @@ int mdl_gemm_gated(const void* a_planes, long long a_rows, long long a_cols, lon
     MDL_REQUIRE(M > 0 && n_heads > 0, "bad sizes");
     const int planes = nsplit == 3 ? 2 : 1;
     const int K = 512, N = n_heads * 1024;
+    const bool fused = nsplit == 3 && use_fused();
+    const int bk = fused ? BLOCK_KF : BLOCK_K;
     CUtensorMap ta, tb;
-    int rc = make_plane_tmap(&ta, a_planes, a_rows, a_cols, lda, a_plane_stride, planes, BLOCK_M);
+    int rc = make_plane_tmap(&ta, a_planes, a_rows, a_cols, lda, a_plane_stride, planes, BLOCK_M, bk);
     if (rc) return rc;
-    rc = make_plane_tmap(&tb, b_planes, N, K, K, b_plane_stride, planes, 256);
+    rc = make_plane_tmap(&tb, b_planes, N, K, K, b_plane_stride, planes, 256, bk);
     if (rc) return rc;
     GemmArgs g{};
-    g.M = M; g.N = N; g.k_blocks = K / BLOCK_K; g.nsplit = nsplit;
+    g.M = M; g.N = N; g.k_blocks = K / bk; g.nsplit = nsplit;
     g.num_m_tiles = (M + BLOCK_M - 1) / BLOCK_M; g.num_n_tiles = N / 256; g.n_inner = 4; g.ksplit = 1;
     g.grp_n_tiles = 4; g.a_koff = 512; g.grp_m_tiles = 1 << 30; g.b_coff = 0;
     g.ba = ba; g.bb = bb; g.wc = wc; g.bc = bc; g.logits = logits;
     g.gate_a = reinterpret_cast<__half*>(gate_a); g.gate_b = reinterpret_cast<__half*>(gate_b);
     g.drop_p = drop_p; g.seed = seed; g.n_heads = n_heads;
-    return launch_gemm<256, false, EPI_GATED>(ta, tb, g, (cudaStream_t)stream);
+    if (fused) return launch_gemm<256, MODE_KF, EPI_GATED>(ta, tb, g, (cudaStream_t)stream);
+    return launch_gemm<256, MODE_K, EPI_GATED>(ta, tb, g, (cudaStream_t)stream);
 }
 
 int mdl_gemm_tn_accum(const void* a_planes, long long a_cols, long long lda, long long a_plane_stride,
@@ -490,7 +566,7 @@ int mdl_gemm_tn_accum(const void* a_planes, long long a_cols, long long lda, lon
     g.grp_n_tiles = 1 << 30; g.a_koff = 0;
     g.grp_m_tiles = grp_m_rows > 0 ? grp_m_rows / BLOCK_M : (1 << 30); g.b_coff = b_coff;
     g.out = out; g.ldc = (int)ldc;
-    return launch_gemm<256, true, EPI_ATOMIC>(ta, tb, g, (cudaStream_t)stream);
+    return launch_gemm<256, MODE_MN, EPI_ATOMIC>(ta, tb, g, (cudaStream_t)stream);
 }
 
 }  // extern "C"

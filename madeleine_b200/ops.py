@@ -495,6 +495,9 @@ class EncodeFn(torch.autograd.Function):
         if sv is None:
             raise RuntimeError("madeleine_b200: backward called on a forward that ran without grad state")
         gmaster = encoder_backward(sv, d_slide, d_logits, d_tokens, d_ref)
+        from . import parallel
+        if parallel.gradient_sync_enabled():
+            torch.distributed.all_reduce(gmaster, op=torch.distributed.ReduceOp.SUM)   # one flat 20 MB NCCL all-reduce
         spec = sv.pw.spec
         grads = []
         for i, (shape, req) in enumerate(ctx.param_meta):

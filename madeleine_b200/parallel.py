@@ -40,11 +40,29 @@ def all_gather_rows(x: torch.Tensor) -> torch.Tensor:
     return _AllGatherRows.apply(x)
 
 
-def gather_slide_embeddings(wsi_embs: Dict[str, torch.Tensor], modality_labels: torch.Tensor):
+_GRAD_SYNC = [False]
+
+
+def enable_gradient_sync(flag: bool = True):
+    """When on, the encoder's backward all-reduces (SUM) its flat parameter-gradient buffer once, in place, before
+    handing the per-parameter views to autograd — no concatenation or copy-back (``allreduce_gradients`` then is a no-op
+    for the encoder parameters and must not be called as well)."""
+    _GRAD_SYNC[0] = bool(flag)
+
+
+def gradient_sync_enabled() -> bool:
+    return _GRAD_SYNC[0] and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def gather_slide_embeddings(wsi_embs: Dict[str, torch.Tensor], modality_labels: torch.Tensor, global_labels_host=None):
     """All-gather the per-modality slide embeddings ([B_local, n_views, 512(, n_mod-1)]) and the availability mask in a
-    single collective: everything is packed into one [B_local, F] fp32 buffer, gathered once, and unpacked."""
+    single collective: everything is packed into one [B_local, F] fp32 buffer, gathered once, and unpacked.
+
+    ``global_labels_host`` (optional, CPU tensor [B_global, n_mod]): the availability mask of the whole batch when the
+    loader already knows it (it comes from the case list); it is returned instead of the gathered device copy so the loss
+    glue needs no device->host sync."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
-        return wsi_embs, modality_labels
+        return wsi_embs, (modality_labels if global_labels_host is None else global_labels_host)
     keys = list(wsi_embs.keys())
     B = modality_labels.shape[0]
     dev = wsi_embs[keys[0]].device
@@ -70,7 +88,7 @@ def gather_slide_embeddings(wsi_embs: Dict[str, torch.Tensor], modality_labels: 
             t = t.unsqueeze(-1).expand(*t.shape, n_mod - 1)
         out[k] = t
         o += n
-    labels = gathered[:, o:].detach()
+    labels = gathered[:, o:].detach() if global_labels_host is None else global_labels_host
     return out, labels
 
 

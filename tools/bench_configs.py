@@ -1,0 +1,119 @@
+#!/usr/bin/env python
+"""Timings of the other BASELINE.json configurations on one B200 (JSON lines; copied to profiles/ per round).
+
+  configs[2]: batch=32 cases, 5 stains (ACROBAT shape), T=2048, stain encodings, global InfoNCE + local GOT, fwd+bwd
+  configs[4]: inference, synthetic slides of N=4000 x 512 through the extraction driver (host -> device -> host)
+"""
+import argparse
+import json
+import os
+import sys
+import time
+from argparse import Namespace
+
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests", "golden"))
+
+from madeleine.models.Model import MADELEINE  # noqa: E402
+from madeleine.utils.loss import InfoNCE, GOT  # noqa: E402
+from madeleine.utils.trainer import calculate_losses  # noqa: E402
+from madeleine_b200 import _lib  # noqa: E402
+from madeleine_b200.utils.inference import extract_slide_embeddings  # noqa: E402
+from weights import make_state_dict  # noqa: E402
+
+
+def cfg(mods, precision):
+    return Namespace(MODALITIES=mods, wsi_encoder="abmil", patch_embedding_dim=512, wsi_encoder_hidden_dim=512,
+                     activation="softmax", n_heads=4, b200_precision=precision)
+
+
+def config3(precision, steps, warmup):
+    dev = torch.device("cuda")
+    mods = ["HE", "HER2", "PGR", "KI67", "ER"]
+    model = MADELEINE(cfg(mods, precision), stain_encoding=True)
+    model.load_state_dict(make_state_dict(3, n_mod=5, stain_encoding=True))
+    model.to(dev).train()
+    bs, T = 32, 2048
+    g = torch.Generator().manual_seed(0)
+    labels = (torch.rand(bs, 5, generator=g) < torch.tensor([1.0, 0.46, 0.73, 0.73, 0.73])).float()
+    labels[:, 0] = 1
+    feats = torch.randn(bs, 5, T, 512, device=dev) * labels.to(dev)[:, :, None, None]
+    args = Namespace(global_loss="info-nce", symmetric_cl=True, local_loss_weight=1.0)
+    loss_fn = InfoNCE(temperature=0.001)
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        embs, toks = model({"feats": feats}, device=dev, n_views=1)
+        loss, ok = calculate_losses(mods[1:], loss_fn, GOT, None, embs, toks, labels[:, 1:], args)
+        loss.backward()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    _lib.kernel_events.clear()
+    _lib.timed_kernels = {"mdl_got_fwd_bwd", "mdl_got_extrema", "mdl_infonce_fwd", "mdl_infonce_bwd"}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    _lib.timed_kernels = None
+    ms = e0.elapsed_time(e1) / steps
+    kt = {k: sum(a.elapsed_time(b) for a, b in v) / steps for k, v in _lib.kernel_events.items()}
+    bags = bs * 5
+    print(json.dumps({"config": "BASELINE configs[2]: batch=32, 5 stains, T=2048, stain encodings, InfoNCE + GOT, fwd+bwd, train mode",
+                      "precision": precision, "ms_per_step": ms, "slides_per_s": bags / (ms * 1e-3), "cases_per_s": bs / (ms * 1e-3),
+                      "loss": float(loss), "cases_per_stain": labels[:, 1:].sum(0).tolist(), "loss_kernel_ms_per_step": kt,
+                      "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}))
+
+
+def config5(precision, n_slides, n_tokens):
+    dev = torch.device("cuda")
+    model = MADELEINE(cfg(["HE"], precision), stain_encoding=False)
+    model.load_state_dict(make_state_dict(0))
+    model.to(dev).eval()
+    g = torch.Generator().manual_seed(1)
+    base = torch.randn(n_tokens + 64, 512, generator=g)
+    bags = [base[(i % 64):(i % 64) + n_tokens] for i in range(n_slides)]   # distinct views, no 8 GB of host RAM
+    extract_slide_embeddings(model, bags[:32], dev)                        # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    emb, idx = extract_slide_embeddings(model, bags, dev)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    # device-resident forward only (no H2D), same packing
+    x = torch.randn(32 * n_tokens, 512, device=dev)
+    cu = torch.arange(0, 33 * n_tokens, n_tokens, dtype=torch.int32, device=dev)
+    with torch.no_grad():
+        for _ in range(3):
+            model.encode_packed(x, cu)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            model.encode_packed(x, cu)
+        e1.record()
+        torch.cuda.synchronize()
+    dev_ms = e0.elapsed_time(e1) / 10
+    print(json.dumps({"config": f"BASELINE configs[4]: inference, {n_slides} slides x {n_tokens} x 512, extraction driver (host->device->host)",
+                      "precision": precision, "e2e_slides_per_s": n_slides / dt, "e2e_seconds": dt,
+                      "device_resident_slides_per_s": 32 / (dev_ms * 1e-3), "h2d_bytes_per_slide": n_tokens * 512 * 4,
+                      "embedding_checksum": float(abs(emb).sum())}))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--which", default="3,5")
+    ap.add_argument("--precision", default="fp32")
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--slides", type=int, default=500)
+    a = ap.parse_args()
+    if "3" in a.which:
+        config3(a.precision, a.steps, 2)
+    if "5" in a.which:
+        config5(a.precision, a.slides, 4000)

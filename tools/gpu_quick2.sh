@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out
+echo "=== diag (fused default)"; timeout 300 python tools/diag_gemm.py 2>&1 | grep -E "FAIL|nsplit=3|Traceback|Error" | head -20
+echo "=== tests"; timeout 900 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_model.py -q -m gpu --timeout 300 2>&1 | tail -6
+for f in 1 0; do
+echo "=== bench fused=$f"
+MDL_GEMM_FUSED=$f timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>&1 | tee gpurun_out/bench_fp32_fused$f.log | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print('value',round(d['value']),'ms',round(d['ms_per_step'],3),'e2e',round(d['e2e']['value']) if d['e2e'] else None,'pool frac',round(d['roofline']['frac'],3),'gemm issue frac',round(d['roofline_gemm']['frac_bf16_issue'],3),'clocks',d['clocks'])
+print({k:round(v,3) for k,v in d['kernel_ms_per_step'].items()})"
+done

@@ -119,11 +119,18 @@ __device__ __forceinline__ float tanh_acc(float x) { return fmaf(2.f, sigmoid_ac
 // Stateless counter-based RNG for dropout masks: the same (seed, stream, index) gives the same bit in fwd and bwd.
 // One 64-bit hash serves FOUR consecutive elements (16 bits each), so kernels that touch float4 / 4-column groups
 // pay one hash per vector.  `idx4` is the element index divided by 4.
+// Philox-2x32-style mixing (5 rounds of 32x32->64 multiply + xor): 64 well-mixed bits from ~15 integer instructions.
 __device__ __forceinline__ uint64_t hash_u64(uint64_t seed, uint32_t stream, uint64_t idx4) {
-    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx4 + 1) + ((uint64_t)stream << 40);
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
+    uint32_t c0 = (uint32_t)idx4, c1 = (uint32_t)(idx4 >> 32) ^ (stream * 0x9E3779B9u);
+    uint32_t k = (uint32_t)seed ^ (uint32_t)(seed >> 32) * 0x85EBCA6Bu;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+        const uint64_t p = (uint64_t)c0 * 0xD2511F53u;
+        c0 = (uint32_t)(p >> 32) ^ k ^ c1;
+        c1 = (uint32_t)p;
+        k += 0x9E3779B9u;
+    }
+    return ((uint64_t)c0 << 32) | c1;
 }
 // multiplicative masks for elements 4*idx4 .. 4*idx4+3: 0 (dropped) or 1/(1-p) (kept); p == 0 -> all 1.
 __device__ __forceinline__ void dropout_scale4(float p, uint64_t seed, uint32_t stream, uint64_t idx4, float (&m)[4]) {

@@ -171,6 +171,7 @@ def main():
     ap.add_argument("--eval-mode", action="store_true", help="model.eval(): dropout off")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--with-optimizer", action="store_true", help="also run the fused AdamW step inside every timed step")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -213,6 +214,11 @@ def main():
     labels_global = torch.ones(B * world, N_STAINS)      # the loader knows the whole batch's availability mask (case list)
     parallel.enable_gradient_sync(world > 1)
 
+    optimizer = None
+    if args.with_optimizer:
+        from madeleine_b200.optim import FusedAdamW
+        optimizer = FusedAdamW(model.parameters(), lr=1e-4)       # reference: optim.AdamW(lr=args.lr), lr 1e-4 in the scripts
+
     def step(feats):
         model.zero_grad(set_to_none=True)
         embs, toks = model({"feats": feats}, device=dev, n_views=1)
@@ -221,6 +227,8 @@ def main():
             embs, lab = parallel.gather_slide_embeddings(embs, labels_dev, global_labels_host=labels_global)
         loss, ok = calculate_losses(MODS[1:], loss_fn, None, None, embs, toks, lab[:, 1:], largs)
         loss.backward()               # world > 1: the encoder backward all-reduces its flat gradient buffer (enable_gradient_sync)
+        if optimizer is not None:
+            optimizer.step()
         return loss
 
     def timed(n_steps, feats_fn, read_loss):
@@ -346,6 +354,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": "BASELINE configs[1] at the metric's fixed N=2000: 16 cases x 2 stains per GPU, symmetric InfoNCE tau=0.001, "
                                "MADELEINE.forward(train=True) + calculate_losses + backward, train mode (dropout on)"
+                               + (" + fused AdamW step" if args.with_optimizer else "")
                                if not args.eval_mode else "same, eval mode",
                    "bags_per_gpu": bags_local, "tokens_per_bag": N_TOKENS, "d_in": D_IN, "parallelism": f"dp{world} (cases sharded, 1 all-gather of slide embeddings + 1 grad all-reduce)",
                    "l2": "inputs larger than L2 (131 MB features + >1 GB activations per step, L2 = 126 MB)"},

@@ -142,6 +142,15 @@ int mdl_got_extrema(const float* v, const float* q, int m, int n, int D, void* w
 int mdl_got_fwd_bwd(const float* v, const float* q, int m, int n, int D, void* workspace, const float* extrema,
                     float* loss, float* wd, float* gwd, float* dv, float* dq, void* stream);
 
+/* ---- optimiser (train-step caller) -------------------------------------------------------------- */
+/* Fused multi-tensor AdamW, one launch for all parameters (torch.optim.AdamW semantics; reference:
+ * madeleine/utils/setup_components.py:194-196).  host_* are HOST arrays of n_tensors DEVICE pointers / element counts
+ * (n_tensors <= mdl_adamw_max_tensors()); `step` counts from 1; gradients are multiplied by grad_scale first. */
+int mdl_adamw_max_tensors(void);
+int mdl_adamw_step(int n_tensors, void* const* host_params, void* const* host_grads, void* const* host_exp_avg,
+                   void* const* host_exp_avg_sq, const long long* host_numels, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, int step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

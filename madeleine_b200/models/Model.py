@@ -194,6 +194,10 @@ class MADELEINE(nn.Module):
         self.modalities = config.MODALITIES
         self.stain_encoding = stain_encoding
         self.b200_precision = getattr(config, "b200_precision", None)
+        # a missing stain arrives as an all-zero bag that the reference encodes in full and then
+        # masks out of every loss.  When the batch carries `modality_labels`, such bags are encoded from ONE token (all of
+        # their tokens are identical, so slide and token embeddings are unchanged) — ~27 % less work on ACROBAT.
+        self.b200_skip_missing_bags = bool(getattr(config, "b200_skip_missing_bags", True))
         if self.stain_encoding:
             self.stain_encoding_dim = 32
             self.embedding = nn.Embedding(len(self.modalities), self.stain_encoding_dim)
@@ -221,6 +225,24 @@ class MADELEINE(nn.Module):
         return self.wsi_embedders.run_kernels(x, cu, codes, self._heads(), self.embedding.weight if se else None, se_dim=se,
                                               want_tokens=want_tokens, want_projector=True, want_ref_feats=False, views=views,
                                               precision=self.b200_precision)
+
+    @staticmethod
+    def _compact_plan(present, n_tokens, device):
+        """Row maps for encoding missing (all-zero) bags from a single token.  present: CPU bool [R].
+        Returns (rows [M_c] gather index into the dense [R*T] rows, cu_seqlens [R+1], inv [R*T] map back to packed rows);
+        built from two [R]-sized host tensors, no device sync."""
+        R = present.numel()
+        lens = torch.where(present, torch.tensor(n_tokens), torch.tensor(1))
+        cu_host = torch.zeros(R + 1, dtype=torch.int64)
+        cu_host[1:] = lens.cumsum(0)
+        m_c = int(cu_host[-1])
+        lens_d = lens.to(device, non_blocking=True)
+        starts = (torch.arange(R) * n_tokens - cu_host[:-1]).to(device, non_blocking=True)
+        rows = torch.arange(m_c, device=device) + torch.repeat_interleave(starts, lens_d, output_size=m_c)
+        t_in_bag = torch.arange(R * n_tokens, device=device) % n_tokens
+        pres_rep = torch.repeat_interleave(present.to(device, non_blocking=True).long(), n_tokens, output_size=R * n_tokens)
+        inv = torch.repeat_interleave(cu_host[:-1].to(device, non_blocking=True), n_tokens, output_size=R * n_tokens) + t_in_bag * pres_rep
+        return rows, cu_host.to(torch.int32).to(device, non_blocking=True), inv
 
     # -- reference API --------------------------------------------------------------------------------------------------
     def encode_he(self, feats, device):
@@ -267,7 +289,21 @@ class MADELEINE(nn.Module):
                 # quirk Q1 (Model.py:126-129): flattened row r (slide r // n_mod, modality r % n_mod) receives code r // bs
                 codes = (torch.arange(R, device=all_wsi_feats.device) // bs).to(torch.int32)
             views = ABMILEmbedder.half_views(R, n_tokens, all_wsi_feats.device) if n_views != 1 else None
-            out = self._encode(all_wsi_feats.reshape(R * n_tokens, d_in), cu, codes, want_tokens=True, views=views)
+            flat = all_wsi_feats.reshape(R * n_tokens, d_in)
+            labels = data.get("modality_labels") if isinstance(data, dict) else None
+            compact = None
+            if (self.b200_skip_missing_bags and labels is not None and n_views == 1 and n_tokens > 1
+                    and tuple(labels.shape) == (bs, n_mod)):
+                present = labels.detach().to("cpu").reshape(R) != 0
+                if not bool(present.all()):
+                    compact = self._compact_plan(present, n_tokens, all_wsi_feats.device)
+            if compact is None:
+                out = self._encode(flat, cu, codes, want_tokens=True, views=views)
+            else:
+                rows, cu_c, inv = compact
+                out = self._encode(flat.index_select(0, rows), cu_c, codes, want_tokens=True)
+                out = dict(out)
+                out["tokens"] = out["tokens"].index_select(0, inv)      # missing bags: their single token row, T times
             d_out = out["slide"].shape[-1]
             slide = out["slide"]
             if n_views == 1:

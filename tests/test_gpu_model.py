@@ -213,3 +213,53 @@ def test_train_mode_dropout_runs_and_differs(golden):
     with torch.no_grad():
         embs2, _ = model({"feats": x}, DEV, train=True)
     assert not torch.allclose(embs["ER"], embs2["ER"])
+
+
+def test_skip_missing_bags_matches_full_encoding(golden):
+    """encoding all-zero (missing-stain) bags from one token returns the same slide / token embeddings,
+    loss and gradients as encoding all T identical tokens."""
+    g = golden("losses_grads")["global_local_se"]
+    mods = g["modalities"]
+    x = make_feats(g["seed_x"], *g["shape"]) * g["labels"][:, :, None, None]
+    args = Namespace(global_loss="info-nce", symmetric_cl=True, local_loss_weight=1.0)
+    outs = []
+    for skip in (True, False):
+        c = cfg(mods)
+        c.b200_skip_missing_bags = skip
+        model = MADELEINE(c, stain_encoding=True)
+        model.load_state_dict(make_state_dict(g["seed_w"], n_mod=len(mods), stain_encoding=True))
+        model.to(DEV).eval()
+        embs, toks = model({"feats": x, "modality_labels": g["labels"]}, DEV, train=True, n_views=1)
+        torch.manual_seed(g["torch_seed"])
+        loss, _ = calculate_losses(mods[1:], InfoNCE(temperature=0.001), GOT, None, embs, toks, g["labels"][:, 1:], args)
+        loss.backward()
+        outs.append((embs, toks, loss.detach(), {n: p.grad.clone() for n, p in model.named_parameters()}))
+    (e1, t1, l1, g1), (e0, t0, l0, g0) = outs
+    for m in mods:
+        torch.testing.assert_close(e1[m], e0[m], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(t1[m], t0[m], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(l1, l0, rtol=1e-5, atol=1e-5)
+    close(l1, g["loss"], rtol=1e-3, atol=1e-3)
+    for n in g1:
+        denom = float(g0[n].norm()) + 1e-12
+        assert float((g1[n] - g0[n]).norm()) / denom < 2e-2 or denom < 1e-6, n
+
+
+def test_fused_adamw_matches_torch():
+    from madeleine_b200.optim import FusedAdamW
+    torch.manual_seed(0)
+    shapes = [(512, 544), (512,), (2048, 512), (1, 512), (1,), (128, 2048)]
+    ref_p = [torch.randn(s, device=DEV).requires_grad_(True) for s in shapes]
+    our_p = [p.detach().clone().requires_grad_(True) for p in ref_p]
+    ref = torch.optim.AdamW(ref_p, lr=1e-3)
+    ours = FusedAdamW(our_p, lr=1e-3)
+    sched = torch.optim.lr_scheduler.LinearLR(ours, start_factor=0.5, total_iters=4)
+    sched_ref = torch.optim.lr_scheduler.LinearLR(ref, start_factor=0.5, total_iters=4)
+    for step in range(5):
+        for a, b in zip(ref_p, our_p):
+            gr = torch.randn_like(a)
+            a.grad = gr.clone()
+            b.grad = gr.clone()
+        ref.step(); ours.step(); sched.step(); sched_ref.step()
+    for a, b in zip(ref_p, our_p):
+        torch.testing.assert_close(b, a, rtol=1e-5, atol=1e-6)

@@ -96,21 +96,41 @@ __device__ __forceinline__ float join_bf16(__nv_bfloat16 hi, __nv_bfloat16 lo) {
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
+// two fp32 -> packed (hi, lo) bf16x2 words: one cvt.rn.bf16x2 per plane instead of scalar converts + packing.
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<uint32_t*>(&h);
+    const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xffff0000u);
+    __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
+    lo = *reinterpret_cast<uint32_t*>(&l);
+}
 __device__ __forceinline__ float bf16_lo_of(uint32_t packed) { return __uint_as_float(packed << 16); }
 __device__ __forceinline__ float bf16_hi_of(uint32_t packed) { return __uint_as_float(packed & 0xffff0000u); }
 
-// GELU(x) = x Phi(x) and its derivative Phi(x) + x phi(x) from ONE exponential: erf(|x|/sqrt2) by Abramowitz-Stegun
+// GELU(x) = x Phi(x) and its derivative Phi(x) + x phi(x) from ONE exponential: erfc(|x|/sqrt2) by Abramowitz-Stegun
 // 7.1.26 (|abs err| <= 1.5e-7, far inside the 1e-4 parity budget) uses exp(-x^2/2), which is also the Gaussian pdf.
-__device__ __forceinline__ void gelu_and_grad(float x, float& g, float& dg) {
-    const float u = fabsf(x) * 0.70710678118654752f;
-    const float t = __fdividef(1.f, fmaf(0.3275911f, u, 1.f));
-    const float e = __expf(-u * u);
+//   w = poly(t) * exp(-x^2/2) = erfc(|x|/sqrt2),  t = 1 / (1 + p |x| / sqrt2)
+//   gelu(x) = x - x w / 2 (x >= 0),  x w / 2 (x < 0);   Phi(x) = 1 - w/2 (x >= 0),  w/2 (x < 0)
+__device__ __forceinline__ float erfc_core(float x, float& e) {
+    const float up = fabsf(x) * 0.84932180028801907f;           // |x| / sqrt2 * sqrt(log2 e)  -> exp2(-up^2) = exp(-x^2/2)
+    const float t = __fdividef(1.f, fmaf(0.27273617448364717f, up, 1.f));   // 0.3275911 / sqrt(log2 e)
+    e = exp2f(-up * up);
     const float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
-    const float cdf = 0.5f * (1.f + copysignf(1.f - poly * e, x));
-    g = x * cdf;
-    dg = fmaf(x * e, 0.39894228040143268f, cdf);
+    return poly * e;
 }
-__device__ __forceinline__ float gelu_erf(float x) { float g, dg; gelu_and_grad(x, g, dg); return g; }
+__device__ __forceinline__ float gelu_erf(float x) {
+    float e;
+    const float h = 0.5f * x * erfc_core(x, e);
+    return x >= 0.f ? x - h : h;
+}
+__device__ __forceinline__ void gelu_and_grad(float x, float& g, float& dg) {
+    float e;
+    const float hw = 0.5f * erfc_core(x, e);
+    const float h = x * hw;
+    const bool pos = x >= 0.f;
+    g = pos ? x - h : h;
+    dg = fmaf(x * e, 0.39894228040143268f, pos ? 1.f - hw : hw);
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) { float g, dg; gelu_and_grad(x, g, dg); return dg; }
 // sigmoid / tanh from one ex2 + one rcp each; abs error ~1e-7, saturate correctly at +-inf.
 __device__ __forceinline__ float sigmoid_acc(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }

@@ -75,25 +75,26 @@ __global__ void row2bag_kernel(const int* __restrict__ cu, int n_bags, int* __re
 // ---------------------------------------------------------------------------------------------------
 template <int C, int RPW>
 __global__ void __launch_bounds__(256, 2)
-ln_gelu_fwd_kernel(const float* __restrict__ z, long long M, const float* __restrict__ gamma, const float* __restrict__ beta,
+ln_gelu_fwd_kernel(const float* __restrict__ z, int M, const float* __restrict__ gamma, const float* __restrict__ beta,
                    float eps, float drop_p, unsigned long long seed, unsigned stream_id,
                    __nv_bfloat16* __restrict__ planes, long long plane_stride, int nplanes,
                    float* __restrict__ mean_out, float* __restrict__ rstd_out) {
     constexpr int V = C / 128;            // float4 per lane per row
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long warps_total = (long long)gridDim.x * 8;
-    for (long long m0 = ((long long)blockIdx.x * 8 + warp) * RPW; m0 < M; m0 += warps_total * RPW) {
+    const int warps_total = gridDim.x * 8;
+    const bool drop = drop_p > 0.f;
+    for (int m0 = (blockIdx.x * 8 + warp) * RPW; m0 < M; m0 += warps_total * RPW) {
         float4 v[RPW][V];
 #pragma unroll
         for (int r = 0; r < RPW; ++r) {
-            const bool ok = m0 + r < M;
+            const int mr = m0 + r < M ? m0 + r : m0;                 // clamp: a duplicate row is loaded, never stored
+            const float4* zr = reinterpret_cast<const float4*>(z + (size_t)mr * C) + lane;
 #pragma unroll
-            for (int j = 0; j < V; ++j)
-                v[r][j] = ok ? __ldg(reinterpret_cast<const float4*>(z + (m0 + r) * C + j * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < V; ++j) v[r][j] = __ldg(zr + j * 32);
         }
 #pragma unroll
         for (int r = 0; r < RPW; ++r) {
-            const long long m = m0 + r;
+            const int m = m0 + r;
             float s = 0.f;
 #pragma unroll
             for (int j = 0; j < V; ++j) s += (v[r][j].x + v[r][j].y) + (v[r][j].z + v[r][j].w);
@@ -105,26 +106,31 @@ ln_gelu_fwd_kernel(const float* __restrict__ z, long long M, const float* __rest
                 q += (a * a + b * b) + (c * c + d * d);
             }
             const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
-            if (m < M) {
-                if (lane == 0) { mean_out[m] = mu; rstd_out[m] = rstd; }
+            if (m >= M) continue;
+            if (lane == 0) { mean_out[m] = mu; rstd_out[m] = rstd; }
+            const float nmr = -mu * rstd;
+            const size_t row_off = (size_t)m * C + lane * 4;
+            const float4* gp = reinterpret_cast<const float4*>(gamma) + lane;
+            const float4* bp = reinterpret_cast<const float4*>(beta) + lane;
 #pragma unroll
-                for (int j = 0; j < V; ++j) {
-                    const int c = j * 128 + lane * 4;
-                    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
-                    const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+            for (int j = 0; j < V; ++j) {
+                const float4 g = __ldg(gp + j * 32);
+                const float4 be = __ldg(bp + j * 32);
+                float y0 = gelu_erf(fmaf(fmaf(v[r][j].x, rstd, nmr), g.x, be.x));
+                float y1 = gelu_erf(fmaf(fmaf(v[r][j].y, rstd, nmr), g.y, be.y));
+                float y2 = gelu_erf(fmaf(fmaf(v[r][j].z, rstd, nmr), g.z, be.z));
+                float y3 = gelu_erf(fmaf(fmaf(v[r][j].w, rstd, nmr), g.w, be.w));
+                if (drop) {
                     float msk[4];
-                    dropout_scale4(drop_p, seed, stream_id, ((uint64_t)m * C + c) >> 2, msk);
-                    const float y0 = gelu_erf((v[r][j].x - mu) * rstd * g.x + be.x) * msk[0];
-                    const float y1 = gelu_erf((v[r][j].y - mu) * rstd * g.y + be.y) * msk[1];
-                    const float y2 = gelu_erf((v[r][j].z - mu) * rstd * g.z + be.z) * msk[2];
-                    const float y3 = gelu_erf((v[r][j].w - mu) * rstd * g.w + be.w) * msk[3];
-                    __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-                    split_bf16(y0, h0, l0); split_bf16(y1, h1, l1); split_bf16(y2, h2, l2); split_bf16(y3, h3, l3);
-                    const long long o = m * C + c;
-                    *reinterpret_cast<uint2*>(planes + o) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
-                    if (nplanes > 1)
-                        *reinterpret_cast<uint2*>(planes + plane_stride + o) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+                    dropout_scale4(drop_p, seed, stream_id, (row_off + j * 128) >> 2, msk);
+                    y0 *= msk[0]; y1 *= msk[1]; y2 *= msk[2]; y3 *= msk[3];
                 }
+                uint32_t h01, l01, h23, l23;
+                split_bf16x2(y0, y1, h01, l01);
+                split_bf16x2(y2, y3, h23, l23);
+                __nv_bfloat16* o = planes + row_off + j * 128;
+                *reinterpret_cast<uint2*>(o) = make_uint2(h01, h23);
+                if (nplanes > 1) *reinterpret_cast<uint2*>(o + plane_stride) = make_uint2(l01, l23);
             }
         }
     }
@@ -141,6 +147,7 @@ ln_gelu_fwd_kernel(const float* __restrict__ z, long long M, const float* __rest
 // "Column-owner" layout: a thread owns 4 fixed columns for the whole kernel (gamma/beta and the 12 column-sum
 // accumulators live in registers); C/4 threads form a row slot, 512/(C/4) slots per block, U rows per slot per iteration.
 // The two per-row means need one cross-warp exchange per iteration (double-buffered smem, one __syncthreads).
+// Optional inputs are template flags so the inner loop carries no pointer tests.
 // ---------------------------------------------------------------------------------------------------
 struct PoolTerm {
     const float* p;        // [M, H] attention probabilities of this view (0 outside the view)
@@ -148,9 +155,9 @@ struct PoolTerm {
     const int* row2seg;    // [M]
 };
 
-template <int C, int U>
+template <int C, int U, bool HAS_B, int NPOOL>
 __global__ void __launch_bounds__(512, 2)
-ln_gelu_bwd_kernel(const float* __restrict__ z, long long M, const float* __restrict__ gamma, const float* __restrict__ beta,
+ln_gelu_bwd_kernel(const float* __restrict__ z, int M, const float* __restrict__ gamma, const float* __restrict__ beta,
                    const float* __restrict__ mean, const float* __restrict__ rstd_in,
                    const float* __restrict__ dh_a, const float* __restrict__ dh_b, PoolTerm pt0, PoolTerm pt1, int n_heads,
                    float drop_p, unsigned long long seed, unsigned stream_id,
@@ -159,58 +166,58 @@ ln_gelu_bwd_kernel(const float* __restrict__ z, long long M, const float* __rest
     constexpr int TPR = C / 4;            // threads per row
     constexpr int SLOTS = 512 / TPR;      // row slots per block
     constexpr int WPS = TPR / 32;         // warps per slot
-    __shared__ __align__(16) float red[2][SLOTS][2 * U][WPS];
+    __shared__ float red[2][SLOTS][2 * U][WPS];
     const int tid = threadIdx.x, lane = tid & 31;
     const int slot = tid / TPR, tin = tid % TPR, wslot = tin >> 5;
     const int c = tin * 4;
     const int head = c / (C / n_heads);
     const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
     const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+    const float gg[4] = {g.x, g.y, g.z, g.w};
+    const float bb[4] = {be.x, be.y, be.z, be.w};
     float accg[4] = {0.f, 0.f, 0.f, 0.f}, accb[4] = {0.f, 0.f, 0.f, 0.f}, accz[4] = {0.f, 0.f, 0.f, 0.f};
-    const long long rows_per_iter = (long long)gridDim.x * SLOTS * U;
-    const long long iters = (M + rows_per_iter - 1) / rows_per_iter;
-    for (long long it = 0; it < iters; ++it) {
-        const long long mbase = (it * gridDim.x + blockIdx.x) * (SLOTS * U) + slot * U;
+    const bool drop = drop_p > 0.f;
+    const int rows_per_iter = gridDim.x * SLOTS * U;
+    const int iters = (M + rows_per_iter - 1) / rows_per_iter;
+    for (int it = 0; it < iters; ++it) {
+        const int mbase = (it * gridDim.x + blockIdx.x) * (SLOTS * U) + slot * U;
         float xh[U][4], dy[U][4], rs[U];
         float s1[U], s2[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long long m = mbase + u;
+            const int m = mbase + u;
             const bool ok = m < M;
-            float4 zv = make_float4(0.f, 0.f, 0.f, 0.f), d = make_float4(0.f, 0.f, 0.f, 0.f);
-            float mu = 0.f;
-            rs[u] = 0.f;
-            if (ok) {
-                zv = __ldg(reinterpret_cast<const float4*>(z + m * C + c));
-                if (dh_a != nullptr) d = __ldg(reinterpret_cast<const float4*>(dh_a + m * C + c));
-                if (dh_b != nullptr) {
-                    const float4 t = __ldg(reinterpret_cast<const float4*>(dh_b + m * C + c));
-                    d.x += t.x; d.y += t.y; d.z += t.z; d.w += t.w;
-                }
-                if (pt0.p != nullptr) {
-                    const float pw = __ldg(pt0.p + m * n_heads + head);
-                    const float4 t = __ldg(reinterpret_cast<const float4*>(pt0.dS + (long long)__ldg(pt0.row2seg + m) * C + c));
-                    d.x = fmaf(pw, t.x, d.x); d.y = fmaf(pw, t.y, d.y); d.z = fmaf(pw, t.z, d.z); d.w = fmaf(pw, t.w, d.w);
-                }
-                if (pt1.p != nullptr) {
-                    const float pw = __ldg(pt1.p + m * n_heads + head);
-                    const float4 t = __ldg(reinterpret_cast<const float4*>(pt1.dS + (long long)__ldg(pt1.row2seg + m) * C + c));
-                    d.x = fmaf(pw, t.x, d.x); d.y = fmaf(pw, t.y, d.y); d.z = fmaf(pw, t.z, d.z); d.w = fmaf(pw, t.w, d.w);
-                }
-                mu = __ldg(mean + m);
-                rs[u] = __ldg(rstd_in + m);
+            const int mr = ok ? m : 0;                                  // clamp; contributions of padded rows are zeroed below
+            const size_t off = (size_t)mr * C + c;
+            const float4 zv = __ldg(reinterpret_cast<const float4*>(z + off));
+            float4 d = __ldg(reinterpret_cast<const float4*>(dh_a + off));
+            if (HAS_B) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(dh_b + off));
+                d.x += t.x; d.y += t.y; d.z += t.z; d.w += t.w;
             }
-            float msk[4];
-            dropout_scale4(drop_p, seed, stream_id, ((uint64_t)m * C + c) >> 2, msk);
+            if (NPOOL >= 1) {
+                const float pw = __ldg(pt0.p + (size_t)mr * n_heads + head);
+                const float4 t = __ldg(reinterpret_cast<const float4*>(pt0.dS + (size_t)__ldg(pt0.row2seg + mr) * C + c));
+                d.x = fmaf(pw, t.x, d.x); d.y = fmaf(pw, t.y, d.y); d.z = fmaf(pw, t.z, d.z); d.w = fmaf(pw, t.w, d.w);
+            }
+            if (NPOOL >= 2) {
+                const float pw = __ldg(pt1.p + (size_t)mr * n_heads + head);
+                const float4 t = __ldg(reinterpret_cast<const float4*>(pt1.dS + (size_t)__ldg(pt1.row2seg + mr) * C + c));
+                d.x = fmaf(pw, t.x, d.x); d.y = fmaf(pw, t.y, d.y); d.z = fmaf(pw, t.z, d.z); d.w = fmaf(pw, t.w, d.w);
+            }
+            const float r_ = ok ? __ldg(rstd_in + mr) : 0.f;
+            const float nmr = -__ldg(mean + mr) * r_;
+            rs[u] = r_;
+            float msk[4] = {1.f, 1.f, 1.f, 1.f};
+            if (drop) dropout_scale4(drop_p, seed, stream_id, off >> 2, msk);
             const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
             const float dd[4] = {d.x, d.y, d.z, d.w};
-            const float gg[4] = {g.x, g.y, g.z, g.w};
-            const float bb[4] = {be.x, be.y, be.z, be.w};
+            const float okf = ok ? 1.f : 0.f;
             s1[u] = 0.f; s2[u] = 0.f;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float x = (zz[i] - mu) * rs[u];
-                const float t = ok ? dd[i] * msk[i] * gelu_erf_grad(fmaf(x, gg[i], bb[i])) : 0.f;
+                const float x = fmaf(zz[i], r_, nmr);
+                const float t = dd[i] * (msk[i] * okf) * gelu_erf_grad(fmaf(x, gg[i], bb[i]));
                 xh[u][i] = x; dy[u][i] = t;
                 const float dx = t * gg[i];
                 s1[u] += dx;
@@ -222,7 +229,7 @@ ln_gelu_bwd_kernel(const float* __restrict__ z, long long M, const float* __rest
         // row sums across the slot's WPS warps
 #pragma unroll
         for (int u = 0; u < U; ++u) { s1[u] = warp_sum(s1[u]); s2[u] = warp_sum(s2[u]); }
-        const int buf = (int)(it & 1);
+        const int buf = it & 1;
         if (lane == 0) {
 #pragma unroll
             for (int u = 0; u < U; ++u) { red[buf][slot][2 * u][wslot] = s1[u]; red[buf][slot][2 * u + 1][wslot] = s2[u]; }
@@ -240,22 +247,21 @@ ln_gelu_bwd_kernel(const float* __restrict__ z, long long M, const float* __rest
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const float t1 = tot[2 * u], t2 = tot[2 * u + 1];
-            const float m1 = t1 * (1.f / C), m2 = t2 * (1.f / C);
-            const long long m = mbase + u;
-            const float gg[4] = {g.x, g.y, g.z, g.w};
-            __nv_bfloat16 h[4], l[4];
+            const float m1 = tot[2 * u] * (1.f / C), m2 = tot[2 * u + 1] * (1.f / C);
+            const int m = mbase + u;
+            float dzv[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float dzv = rs[u] * (dy[u][i] * gg[i] - m1 - xh[u][i] * m2);   // rs = 0 for rows past M
-                accz[i] += dzv;
-                split_bf16(dzv, h[i], l[i]);
+                dzv[i] = rs[u] * (fmaf(dy[u][i], gg[i], -m1) - xh[u][i] * m2);   // rs = 0 for rows past M
+                accz[i] += dzv[i];
             }
             if (m < M) {
-                const long long o = m * C + c;
-                *reinterpret_cast<uint2*>(dz_planes + o) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
-                if (nplanes > 1)
-                    *reinterpret_cast<uint2*>(dz_planes + plane_stride + o) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+                uint32_t h01, l01, h23, l23;
+                split_bf16x2(dzv[0], dzv[1], h01, l01);
+                split_bf16x2(dzv[2], dzv[3], h23, l23);
+                __nv_bfloat16* o = dz_planes + (size_t)m * C + c;
+                *reinterpret_cast<uint2*>(o) = make_uint2(h01, h23);
+                if (nplanes > 1) *reinterpret_cast<uint2*>(o + plane_stride) = make_uint2(l01, l23);
             }
         }
     }
@@ -314,29 +320,37 @@ gate_bwd_kernel(const __half* __restrict__ gate_a, const __half* __restrict__ ga
                 dropout_scale4(drop_p, seed, 11u, idx4, t); sb[0] = t[0]; sb[1] = t[1]; sb[2] = t[2]; sb[3] = t[3];
                 dropout_scale4(drop_p, seed, 11u, idx4 + 1, t); sb[4] = t[0]; sb[5] = t[1]; sb[6] = t[2]; sb[7] = t[3];
             }
-            __nv_bfloat16 ah[8], al[8], bh[8], bl[8];
+            float dpa[8], dpb[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float2 fa = __half22float2(ha[i >> 1]);
-                const float2 fb = __half22float2(hb[i >> 1]);
-                const float ad = (i & 1) ? fa.y : fa.x;   // dropout-scaled gates
-                const float bd = (i & 1) ? fb.y : fb.x;
-                const float a = ad * (sa[i] != 0.f ? keep_inv : 0.f);  // undo the 1/(1-p) scaling where kept
-                const float b = bd * (sb[i] != 0.f ? keep_inv : 0.f);
-                const float dA = dl[r] * w[i];
-                const float dpa = dA * bd * sa[i] * (1.f - a * a);
-                const float dpb = dA * ad * sb[i] * b * (1.f - b);
-                s_a[i] += dpa; s_b[i] += dpb; s_w[i] = fmaf(dl[r], ad * bd, s_w[i]);
-                split_bf16(dpa, ah[i], al[i]);
-                split_bf16(dpb, bh[i], bl[i]);
+            for (int i2 = 0; i2 < 4; ++i2) {
+                const float2 fa = __half22float2(ha[i2]);
+                const float2 fb = __half22float2(hb[i2]);
+                const float adv[2] = {fa.x, fa.y}, bdv[2] = {fb.x, fb.y};
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const int i = 2 * i2 + k;
+                    const float ad = adv[k], bd = bdv[k];               // dropout-scaled gates
+                    const float a = ad * (sa[i] != 0.f ? keep_inv : 0.f);  // undo the 1/(1-p) scaling where kept
+                    const float b = bd * (sb[i] != 0.f ? keep_inv : 0.f);
+                    const float dA = dl[r] * w[i];
+                    dpa[i] = dA * bd * sa[i] * (1.f - a * a);
+                    dpb[i] = dA * ad * sb[i] * b * (1.f - b);
+                    s_a[i] += dpa[i]; s_b[i] += dpb[i]; s_w[i] = fmaf(dl[r], ad * bd, s_w[i]);
+                }
             }
             if (threadIdx.x % 64 == 0) s_c += dl[r];  // one thread per head
-            const long long o = m * (long long)(n_heads * 1024) + packed0;
-            *reinterpret_cast<uint4*>(dpre + o) = make_uint4(pack_bf16x2(ah[0], ah[1]), pack_bf16x2(ah[2], ah[3]), pack_bf16x2(ah[4], ah[5]), pack_bf16x2(ah[6], ah[7]));
-            *reinterpret_cast<uint4*>(dpre + o + 128) = make_uint4(pack_bf16x2(bh[0], bh[1]), pack_bf16x2(bh[2], bh[3]), pack_bf16x2(bh[4], bh[5]), pack_bf16x2(bh[6], bh[7]));
+            uint32_t ah[4], al[4], bh[4], bl[4];
+#pragma unroll
+            for (int i2 = 0; i2 < 4; ++i2) {
+                split_bf16x2(dpa[2 * i2], dpa[2 * i2 + 1], ah[i2], al[i2]);
+                split_bf16x2(dpb[2 * i2], dpb[2 * i2 + 1], bh[i2], bl[i2]);
+            }
+            __nv_bfloat16* o = dpre + (size_t)m * (size_t)(n_heads * 1024) + packed0;
+            *reinterpret_cast<uint4*>(o) = make_uint4(ah[0], ah[1], ah[2], ah[3]);
+            *reinterpret_cast<uint4*>(o + 128) = make_uint4(bh[0], bh[1], bh[2], bh[3]);
             if (nplanes > 1) {
-                *reinterpret_cast<uint4*>(dpre + plane_stride + o) = make_uint4(pack_bf16x2(al[0], al[1]), pack_bf16x2(al[2], al[3]), pack_bf16x2(al[4], al[5]), pack_bf16x2(al[6], al[7]));
-                *reinterpret_cast<uint4*>(dpre + plane_stride + o + 128) = make_uint4(pack_bf16x2(bl[0], bl[1]), pack_bf16x2(bl[2], bl[3]), pack_bf16x2(bl[4], bl[5]), pack_bf16x2(bl[6], bl[7]));
+                *reinterpret_cast<uint4*>(o + plane_stride) = make_uint4(al[0], al[1], al[2], al[3]);
+                *reinterpret_cast<uint4*>(o + plane_stride + 128) = make_uint4(bl[0], bl[1], bl[2], bl[3]);
             }
         }
     }
@@ -457,18 +471,38 @@ int mdl_ln_gelu_fwd(const float* z, long long M, int C, const float* gamma, cons
                     float drop_p, unsigned long long seed, unsigned stream_id,
                     void* planes, long long plane_stride, int nplanes, float* mean, float* rstd, void* stream) {
     MDL_REQUIRE(C == 512 || C == 2048, "ln_gelu_fwd: C must be 512 or 2048 (got %d)", C);
+    MDL_REQUIRE(M < (1LL << 31), "ln_gelu_fwd: too many rows");
     if (M == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (C == 512) {
         const int grid = grid_for(M, 8 * 2, 6);
-        ln_gelu_fwd_kernel<512, 2><<<grid, 256, 0, st>>>(z, M, gamma, beta, eps, drop_p, seed, stream_id, (__nv_bfloat16*)planes, plane_stride, nplanes, mean, rstd);
+        ln_gelu_fwd_kernel<512, 2><<<grid, 256, 0, st>>>(z, (int)M, gamma, beta, eps, drop_p, seed, stream_id, (__nv_bfloat16*)planes, plane_stride, nplanes, mean, rstd);
     } else {
         const int grid = grid_for(M, 8, 4);
-        ln_gelu_fwd_kernel<2048, 1><<<grid, 256, 0, st>>>(z, M, gamma, beta, eps, drop_p, seed, stream_id, (__nv_bfloat16*)planes, plane_stride, nplanes, mean, rstd);
+        ln_gelu_fwd_kernel<2048, 1><<<grid, 256, 0, st>>>(z, (int)M, gamma, beta, eps, drop_p, seed, stream_id, (__nv_bfloat16*)planes, plane_stride, nplanes, mean, rstd);
     }
     MDL_CHECK_LAUNCH();
     return 0;
 }
+
+}  // extern "C"
+
+template <int C>
+static void launch_ln_bwd(bool has_b, int npool, int grid, cudaStream_t st, const float* z, int M, const float* gamma, const float* beta,
+                          const float* mean, const float* rstd, const float* dh_a, const float* dh_b, PoolTerm t0, PoolTerm t1, int n_heads,
+                          float drop_p, unsigned long long seed, unsigned stream_id, __nv_bfloat16* dz, long long ps, int npl,
+                          float* dgamma, float* dbeta, float* dbias) {
+#define MDL_LN_BWD(HB, NP) ln_gelu_bwd_kernel<C, 2, HB, NP><<<grid, 512, 0, st>>>(z, M, gamma, beta, mean, rstd, dh_a, dh_b, t0, t1, n_heads, drop_p, seed, stream_id, dz, ps, npl, dgamma, dbeta, dbias)
+    if (!has_b && npool == 0) MDL_LN_BWD(false, 0);
+    else if (!has_b && npool == 1) MDL_LN_BWD(false, 1);
+    else if (!has_b) MDL_LN_BWD(false, 2);
+    else if (npool == 0) MDL_LN_BWD(true, 0);
+    else if (npool == 1) MDL_LN_BWD(true, 1);
+    else MDL_LN_BWD(true, 2);
+#undef MDL_LN_BWD
+}
+
+extern "C" {
 
 int mdl_ln_gelu_bwd(const float* z, long long M, int C, const float* gamma, const float* beta, const float* mean, const float* rstd,
                     const float* dh_a, const float* dh_b,
@@ -479,15 +513,22 @@ int mdl_ln_gelu_bwd(const float* z, long long M, int C, const float* gamma, cons
                     float* dgamma, float* dbeta, float* dbias, void* stream) {
     MDL_REQUIRE(C == 512 || C == 2048, "ln_gelu_bwd: C must be 512 or 2048 (got %d)", C);
     MDL_REQUIRE(n_heads > 0 && C % n_heads == 0 && (C / n_heads) % 4 == 0, "ln_gelu_bwd: bad n_heads");
+    MDL_REQUIRE(M < (1LL << 31), "ln_gelu_bwd: too many rows");
+    MDL_REQUIRE(dh_a != nullptr || dh_b != nullptr, "ln_gelu_bwd: at least one dense upstream gradient is required");
+    MDL_REQUIRE(pool_p0 != nullptr || pool_p1 == nullptr, "ln_gelu_bwd: pool term 1 given without pool term 0");
     if (M == 0) return 0;
+    if (dh_a == nullptr) { dh_a = dh_b; dh_b = nullptr; }
     PoolTerm t0{pool_p0, pool_dS0, pool_seg0}, t1{pool_p1, pool_dS1, pool_seg1};
+    const int npool = pool_p0 == nullptr ? 0 : (pool_p1 == nullptr ? 1 : 2);
     cudaStream_t st = (cudaStream_t)stream;
     if (C == 512) {
         const int grid = grid_for(M, 4 * 2 * 4, 2);   // several iterations per block so the column atomics amortise
-        ln_gelu_bwd_kernel<512, 2><<<grid, 512, 0, st>>>(z, M, gamma, beta, mean, rstd, dh_a, dh_b, t0, t1, n_heads, drop_p, seed, stream_id, (__nv_bfloat16*)dz_planes, plane_stride, nplanes, dgamma, dbeta, dbias);
+        launch_ln_bwd<512>(dh_b != nullptr, npool, grid, st, z, (int)M, gamma, beta, mean, rstd, dh_a, dh_b, t0, t1, n_heads, drop_p, seed, stream_id,
+                           (__nv_bfloat16*)dz_planes, plane_stride, nplanes, dgamma, dbeta, dbias);
     } else {
         const int grid = grid_for(M, 1 * 2 * 8, 2);
-        ln_gelu_bwd_kernel<2048, 2><<<grid, 512, 0, st>>>(z, M, gamma, beta, mean, rstd, dh_a, dh_b, t0, t1, n_heads, drop_p, seed, stream_id, (__nv_bfloat16*)dz_planes, plane_stride, nplanes, dgamma, dbeta, dbias);
+        launch_ln_bwd<2048>(dh_b != nullptr, npool, grid, st, z, (int)M, gamma, beta, mean, rstd, dh_a, dh_b, t0, t1, n_heads, drop_p, seed, stream_id,
+                            (__nv_bfloat16*)dz_planes, plane_stride, nplanes, dgamma, dbeta, dbias);
     }
     MDL_CHECK_LAUNCH();
     return 0;

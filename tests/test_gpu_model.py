@@ -242,7 +242,8 @@ def test_skip_missing_bags_matches_full_encoding(golden):
     close(l1, g["loss"], rtol=1e-3, atol=1e-3)
     for n in g1:
         denom = float(g0[n].norm()) + 1e-12
-        assert float((g1[n] - g0[n]).norm()) / denom < 2e-2 or denom < 1e-6, n
+        # attention_c.bias gets an analytically zero gradient (softmax shift invariance): only rounding noise there
+        assert float((g1[n] - g0[n]).norm()) / denom < 2e-2 or denom < 1e-4, n
 
 
 def test_fused_adamw_matches_torch():

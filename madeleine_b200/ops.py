@@ -566,9 +566,26 @@ def info_nce(query, positive_key, temperature=0.1, reduction="mean", symmetric=F
 # --------------------------------------------------------------------------------------------------------------
 # Graph-OT local loss
 # --------------------------------------------------------------------------------------------------------------
+_got_streams = {}
+
+
+def _side_stream(device, slot):
+    key = (str(device), slot)
+    st = _got_streams.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device)
+        _got_streams[key] = st
+    return st
+
+
 class GOTFn(torch.autograd.Function):
+    """Graph-OT loss; forward computes the loss AND d loss / d tokens in the same launches (backward only scales).
+
+    ``slot >= 0`` runs the kernels on a side stream (one per slot) so that independent per-stain problems — each only
+    <= 65 CTAs — overlap on the 148 SMs; the caller must then call ``got_join`` before consuming the result."""
+
     @staticmethod
-    def forward(ctx, v, q):
+    def forward(ctx, v, q, slot):
         m, n, D = v.shape
         dev = v.device
         v = v.contiguous().float()
@@ -577,17 +594,27 @@ class GOTFn(torch.autograd.Function):
         if n > max_n:
             raise RuntimeError(f"madeleine_b200 GOT kernel supports at most {max_n} tokens per problem (got {n}); "
                                "the reference's subsampling quirk (loss.py:281-284) bounds n by the number of cases")
-        ws_bytes = call("mdl_got_workspace_bytes", m, n, D)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        extrema = torch.empty(6, dtype=torch.float32, device=dev)
-        st = stream_ptr(dev)
-        call("mdl_got_extrema", v, q, m, n, D, ws, extrema, st)
-        loss = torch.empty((), dtype=torch.float32, device=dev)
-        wd = torch.empty(m, dtype=torch.float32, device=dev)
-        gwd = torch.empty(m, dtype=torch.float32, device=dev)
-        dv = torch.empty_like(v)
-        dq = torch.empty_like(q)
-        call("mdl_got_fwd_bwd", v, q, m, n, D, ws, extrema, loss, wd, gwd, dv, dq, st)
+        cur = torch.cuda.current_stream(dev)
+        side = _side_stream(dev, slot) if slot >= 0 else None
+        if side is not None:
+            side.wait_stream(cur)
+        with torch.cuda.stream(side if side is not None else cur):
+            ws_bytes = call("mdl_got_workspace_bytes", m, n, D)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            extrema = torch.empty(6, dtype=torch.float32, device=dev)
+            st = stream_ptr(dev)
+            call("mdl_got_extrema", v, q, m, n, D, ws, extrema, st)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            wd = torch.empty(m, dtype=torch.float32, device=dev)
+            gwd = torch.empty(m, dtype=torch.float32, device=dev)
+            dv = torch.empty_like(v)
+            dq = torch.empty_like(q)
+            call("mdl_got_fwd_bwd", v, q, m, n, D, ws, extrema, loss, wd, gwd, dv, dq, st)
+        if side is not None:
+            for t in (v, q):
+                t.record_stream(side)           # inputs were produced on `cur`, consumed on `side`
+            for t in (loss, dv, dq, wd, gwd):
+                t.record_stream(cur)            # outputs were allocated on `side`, consumed on `cur` after got_join
         ctx.save_for_backward(dv, dq)
         ctx.parts = (wd, gwd)
         return loss
@@ -595,9 +622,16 @@ class GOTFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, go):
         dv, dq = ctx.saved_tensors
-        return dv * go, dq * go
+        return dv * go, dq * go, None
 
 
-def got_loss(v, q):
+def got_loss(v, q, slot: int = -1):
     _lib.require_cuda(v, "GOT tokens")
-    return GOTFn.apply(v, q)
+    return GOTFn.apply(v, q, slot)
+
+
+def got_join(device, slots):
+    """Make the current stream wait for the GOT problems issued on the given side-stream slots."""
+    cur = torch.cuda.current_stream(device)
+    for slot in slots:
+        cur.wait_stream(_side_stream(device, slot))

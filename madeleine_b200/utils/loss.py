@@ -60,7 +60,7 @@ def init_intra_wsi_loss_function(config):
     return InfoNCE(temperature=config["temperature"])
 
 
-def GOT(v_, q_, subsample=None):
+def GOT(v_, q_, subsample=None, _slot=-1):
     """loss.py:278-301. v_, q_ [m, N, 128] token embeddings of the m cases that have this stain → scalar wd + gwd.
 
     Quirk Q3 is reproduced: the permutation is drawn over the *batch* size with torch's global CPU generator and
@@ -69,4 +69,5 @@ def GOT(v_, q_, subsample=None):
         patch_indices = torch.randperm(v_.shape[0])[:subsample].to(v_.device)
         v_ = v_[:, patch_indices, :]
         q_ = q_[:, patch_indices, :]
-    return ops.got_loss(v_, q_)
+    # _slot >= 0 (used by calculate_losses): run on a side stream; the caller joins with ops.got_join before using the value
+    return ops.got_loss(v_, q_, _slot)

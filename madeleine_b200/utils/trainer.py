@@ -4,6 +4,8 @@ import time
 import numpy as np
 import torch
 
+from .. import ops
+from .loss import GOT as _B200_GOT
 from .utils import set_model_precision, smooth_rank_measure
 
 DEVICE = torch.device("cuda" if torch.cuda.is_available() else "cpu")
@@ -16,6 +18,7 @@ def calculate_losses(STAINS, loss_fn_interMod, loss_fn_interMod_local, loss_fn_i
     """trainer.py:20-77 — per stain: select the cases that have it, global InfoNCE (+ weighted GOT, + intra-modality
     InfoNCE on the two half views), summed.  Returns (loss, at_least_one_stain_flag); loss is -1 when nothing applies."""
     losses = []
+    pending_local = []          # (slot, raw GOT loss) issued on side streams, joined once before the final sum
     atleast_two_loss_flag = False
     dev = wsi_embs["HE"].device
     # The availability mask comes from the dataloader on the CPU (as in the reference); keeping the case selection on
@@ -35,13 +38,21 @@ def calculate_losses(STAINS, loss_fn_interMod, loss_fn_interMod_local, loss_fn_i
         if loss_fn_interMod_local:
             he_tokens = token_embs["HE"][:, :, :, stain_idx][stain_mask]
             ihc_tokens = token_embs[stain].squeeze()[stain_mask]
-            losses.append(loss_fn_interMod_local(he_tokens, ihc_tokens, subsample=256) * args.local_loss_weight)
+            if loss_fn_interMod_local is _B200_GOT and he_tokens.is_cuda:
+                # the per-stain OT problems are independent and small (<= 65 CTAs each): overlap them on side streams
+                slot = len(pending_local) % 4
+                pending_local.append((slot, loss_fn_interMod_local(he_tokens, ihc_tokens, subsample=256, _slot=slot)))
+            else:
+                losses.append(loss_fn_interMod_local(he_tokens, ihc_tokens, subsample=256) * args.local_loss_weight)
         if loss_fn_intraMod:
             he1, he2 = wsi_embs["HE"][:, 1, :, stain_idx][stain_mask], wsi_embs["HE"][:, 2, :, stain_idx][stain_mask]
             st1, st2 = wsi_embs[stain][:, 1, :][stain_mask], wsi_embs[stain][:, 2, :][stain_mask]
             losses.append(loss_fn_intraMod(query=he1, positive_key=he2, symmetric=args.symmetric_cl))
             losses.append(loss_fn_intraMod(query=st1, positive_key=st2, symmetric=args.symmetric_cl))
         atleast_two_loss_flag = True
+    if pending_local:
+        ops.got_join(dev, sorted({slot for slot, _ in pending_local}))
+        losses.extend(raw * args.local_loss_weight for _, raw in pending_local)
     if len(losses) > 0:
         loss = sum(losses)
     else:

@@ -61,6 +61,9 @@ int mdl_gemm_tn_accum(const void* a_planes, long long a_cols, long long lda, lon
                       const void* b_planes, long long b_cols, long long ldb, long long b_plane_stride,
                       long long tokens, float* out, long long ldc, int M, int N, int nsplit,
                       int grp_m_rows, int b_coff, int ksplit, void* stream);
+/* Benchmark-only knob for tools/gemm_bounds.py (results are WRONG while set): 1 = skip TMA operand loads,
+ * 2 = skip epilogue global writes in mdl_gemm_nt.  0 restores normal operation. */
+int mdl_gemm_debug_flags(int flags);
 /* CUDA-core cross-checks of the two GEMM shapes above (tests only; never on the product path). */
 int mdl_gemm_nt_simt(const void* a_planes, long long lda, long long a_plane_stride, const void* b_planes, long long ldb,
                      long long b_plane_stride, float* out, long long ldc, int M, int N, int K, int nsplit, void* stream);

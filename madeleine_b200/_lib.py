@@ -38,6 +38,7 @@ SIGNATURES = {
     "mdl_gemm_gated": [c_p, c_ll, c_ll, c_ll, c_ll, c_p, c_ll, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_f,
                        c_ull, c_p],
     "mdl_gemm_tn_accum": [c_p, c_ll, c_ll, c_ll, c_p, c_ll, c_ll, c_ll, c_ll, c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    "mdl_gemm_debug_flags": [c_i],
     "mdl_gemm_nt_simt": [c_p, c_ll, c_ll, c_p, c_ll, c_ll, c_p, c_ll, c_i, c_i, c_i, c_i, c_p],
     "mdl_gemm_tn_simt": [c_p, c_ll, c_ll, c_p, c_ll, c_ll, c_ll, c_p, c_ll, c_i, c_i, c_i, c_p],
     "mdl_ln_gelu_fwd": [c_p, c_ll, c_i, c_p, c_p, c_f, c_f, c_ull, c_u, c_p, c_ll, c_i, c_p, c_p, c_p],

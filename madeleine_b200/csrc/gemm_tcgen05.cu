@@ -21,60 +21,12 @@
 //   EPI_GATED : per head h, logit[m,h] = sum_j tanh(a_j+ba_j) * sigmoid(b_j+bb_j) * wc_j + bc  over 4 n-tiles
 //               holding 128 'a' and 128 'b' columns each; optionally stores the (dropout-scaled) gates as fp16.
 //   EPI_ATOMIC: C += acc (red.global.add.f32), used by split-K wgrad.
-#include "common.cuh"
+#include "gemm_common.cuh"
 #include "madeleine_b200.h"
-#include <cuda.h>
 #include <mutex>
 #include <stdlib.h>
 
 namespace mdl {
-
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;   // 64 bf16 = one 128-byte swizzle row
-constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
-constexpr int GEMM_THREADS = 320;   // 2 control warps + 8 epilogue warps
-constexpr int EPI_WARPS = 8;
-constexpr int TMEM_COLS = 512;
-
-enum { EPI_STORE = 0, EPI_GATED = 1, EPI_ATOMIC = 2 };
-enum { MODE_K = 0, MODE_MN = 1, MODE_KF = 2 };
-constexpr int BLOCK_KF = 32;  // fused-pass k-block: 32 bf16 = one 64-byte swizzle row
-
-struct GemmArgs {
-    int M, N;                 // output extent
-    int k_blocks;             // contraction length / BLOCK_K (per pass)
-    int nsplit;               // 1 or 3 passes
-    int num_m_tiles, num_n_tiles;
-    int n_inner;              // consecutive n-tiles processed by one work unit (EPI_GATED: 4)
-    int ksplit;               // split-K factor (kMNMajor), else 1
-    int grp_n_tiles, a_koff;  // kKMajor: A k-offset = (n_tile / grp_n_tiles) * a_koff
-    int grp_m_tiles, b_coff;  // kMNMajor: B column offset = (m_tile / grp_m_tiles) * b_coff
-    float* out; int ldc;
-    const float* bias;        // [N] or null
-    const float* rowbias;     // [R, N] or null (per-bag bias, stain encodings)
-    const int* row2bag;       // [M]
-    // gated epilogue
-    const float* ba; const float* bb; const float* wc; const float* bc;  // [H*512], [H*512], [H*512], [H]
-    float* logits;            // [M, H]
-    __half* gate_a; __half* gate_b;  // [M, H*512] or null
-    float drop_p; unsigned long long seed;
-    int n_heads;
-};
-
-template <int BLOCK_N>
-struct SmemLayout {
-    // identical totals in every mode: classic = one plane x 64 k, fused = two planes x 32 k
-    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-    static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-    static constexpr int AUX_OFFSET = BAR_OFFSET + 256;
-    // aux region: gated epilogue = ba | bb | wc (3 x 2048 floats) + 2 x 128 partials; store/atomic epilogues = one padded
-    // 32 x 33 fp32 transpose buffer per epilogue warp
-    static constexpr int AUX_BYTES = 8 * 32 * 33 * 4;
-    static constexpr int TOTAL = AUX_OFFSET + AUX_BYTES + 1024;         // + alignment slack
-};
 
 template <int BLOCK_N, int MODE, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -148,6 +100,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             mbar_wait(empty_bar(stage), phase ^ 1u);
                             const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
                             const uint32_t sb = sa + L::A_BYTES;
+                            if (p.debug_flags & 1) { mbar_arrive(full_bar(stage)); if (++stage == STAGES) { stage = 0; phase ^= 1u; } continue; }
                             mbar_arrive_expect_tx(full_bar(stage), L::STAGE_BYTES);
                             tma_load_3d(sa, &tmap_a, full_bar(stage), a_k0 + kb * BLOCK_KF, m_tile * BLOCK_M, 0);
                             tma_load_3d(sa + L::A_BYTES / 2, &tmap_a, full_bar(stage), a_k0 + kb * BLOCK_KF, m_tile * BLOCK_M, 1);
@@ -265,8 +218,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
             int m_tile, n_group, kb0, kb1;
             decode(unit, m_tile, n_group, kb0, kb1);
-            const int m = m_tile * BLOCK_M + quad * 32 + lane;
-            const bool row_ok = m < p.M;
             float gated_partial = 0.f;
             for (int inner = 0; inner < p.n_inner; ++inner) {
                 const int n_tile = n_group * p.n_inner + inner;
@@ -274,115 +225,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
                 const bool have_k = kb1 > kb0;  // empty split-K slice: accumulator is stale, skip
-                if constexpr (EPI == EPI_STORE || EPI == EPI_ATOMIC) {
-                    // TMEM -> registers (thread = row) -> +bias -> warp-private padded smem -> row-contiguous global access:
-                    // 8 lanes cover one 128-byte row segment, so each vector store / reduction touches 4 full lines instead
-                    // of 32 scattered 16-byte pieces.
-                    int bag = 0;
-                    if (EPI == EPI_STORE && p.rowbias != nullptr && row_ok) bag = p.row2bag[m];
-                    float* stg = aux + (warp - 2) * (32 * 33);
-                    const int m_warp = m_tile * BLOCK_M + quad * 32;
-                    constexpr int CH = BLOCK_N / 64;   // 32-column chunks per half
-#pragma unroll 1
-                    for (int cc = 0; cc < CH; ++cc) {
-                        const int c = half * CH + cc;
-                        uint32_t r[32];
-                        tmem_ld_32x32(t_row + c * 32, r);
-                        tmem_ld_wait();
-                        const int n0 = n_tile * BLOCK_N + c * 32;
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            float4 v;
-                            v.x = __uint_as_float(r[i]); v.y = __uint_as_float(r[i + 1]);
-                            v.z = __uint_as_float(r[i + 2]); v.w = __uint_as_float(r[i + 3]);
-                            if (EPI == EPI_STORE && p.bias != nullptr) {
-                                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
-                                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-                            }
-                            if (EPI == EPI_STORE && p.rowbias != nullptr) {
-                                const float4 b = __ldg(reinterpret_cast<const float4*>(p.rowbias + (size_t)bag * p.N + n0 + i));
-                                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-                            }
-                            float* d = stg + lane * 33 + i;
-                            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-                        }
-                        __syncwarp();
-                        const int sub = lane >> 3, col4 = (lane & 7) * 4;
-#pragma unroll
-                        for (int it = 0; it < 8; ++it) {
-                            const int row = it * 4 + sub;
-                            const float* sp = stg + row * 33 + col4;
-                            const float x0 = sp[0], x1 = sp[1], x2 = sp[2], x3 = sp[3];
-                            if (m_warp + row < p.M) {
-                                float* dst = p.out + (size_t)(m_warp + row) * p.ldc + n0 + col4;
-                                if constexpr (EPI == EPI_STORE) {
-                                    *reinterpret_cast<float4*>(dst) = make_float4(x0, x1, x2, x3);
-                                } else {
-                                    if (have_k)
-                                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x0), "f"(x1), "f"(x2), "f"(x3) : "memory");
-                                }
-                            }
-                        }
-                        __syncwarp();
-                    }
-                } else {  // EPI_GATED
-                    const int head = n_group;          // one work unit = (m_tile, head); inner = 128-wide gate group
-                    const int j_base = head * 512 + inner * 128;
-                    const int HC = p.n_heads * 512;
-#pragma unroll 1
-                    for (int cc = 0; cc < 2; ++cc) {
-                        const int c = half * 2 + cc;
-                        uint32_t ra[32], rb[32];
-                        tmem_ld_32x32(t_row + c * 32, ra);
-                        tmem_ld_32x32(t_row + 128 + c * 32, rb);
-                        tmem_ld_wait();
-                        const int j0 = j_base + c * 32;
-                        uint32_t ha[16], hb[16];
-#pragma unroll
-                        for (int i4 = 0; i4 < 8; ++i4) {
-                            const float4 vba = *reinterpret_cast<const float4*>(aux + j0 + 4 * i4);
-                            const float4 vbb = *reinterpret_cast<const float4*>(aux + 2048 + j0 + 4 * i4);
-                            const float4 vwc = *reinterpret_cast<const float4*>(aux + 4096 + j0 + 4 * i4);
-                            const float fba[4] = {vba.x, vba.y, vba.z, vba.w}, fbb[4] = {vbb.x, vbb.y, vbb.z, vbb.w};
-                            const float fwc[4] = {vwc.x, vwc.y, vwc.z, vwc.w};
-                            float ma[4], mb[4];
-                            const uint64_t idx4 = ((uint64_t)m * (uint64_t)HC + (uint64_t)(j0 + 4 * i4)) >> 2;
-                            dropout_scale4(p.drop_p, p.seed, 10u, idx4, ma);
-                            dropout_scale4(p.drop_p, p.seed, 11u, idx4, mb);
-                            float av[4], bv[4];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                av[i] = tanh_acc(__uint_as_float(ra[4 * i4 + i]) + fba[i]) * ma[i];
-                                bv[i] = sigmoid_acc(__uint_as_float(rb[4 * i4 + i]) + fbb[i]) * mb[i];
-                                gated_partial = fmaf(av[i] * bv[i], fwc[i], gated_partial);
-                            }
-                            if (p.gate_a != nullptr) {
-                                const __half2 a01 = __floats2half2_rn(av[0], av[1]), a23 = __floats2half2_rn(av[2], av[3]);
-                                const __half2 b01 = __floats2half2_rn(bv[0], bv[1]), b23 = __floats2half2_rn(bv[2], bv[3]);
-                                ha[2 * i4] = *reinterpret_cast<const uint32_t*>(&a01); ha[2 * i4 + 1] = *reinterpret_cast<const uint32_t*>(&a23);
-                                hb[2 * i4] = *reinterpret_cast<const uint32_t*>(&b01); hb[2 * i4 + 1] = *reinterpret_cast<const uint32_t*>(&b23);
-                            }
-                        }
-                        if (p.gate_a != nullptr && row_ok) {
-                            uint4* da = reinterpret_cast<uint4*>(p.gate_a + (size_t)m * HC + j0);
-                            uint4* db = reinterpret_cast<uint4*>(p.gate_b + (size_t)m * HC + j0);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                da[i] = make_uint4(ha[4 * i], ha[4 * i + 1], ha[4 * i + 2], ha[4 * i + 3]);
-                                db[i] = make_uint4(hb[4 * i], hb[4 * i + 1], hb[4 * i + 2], hb[4 * i + 3]);
-                            }
-                        }
-                    }
-                    if (inner == p.n_inner - 1) {
-                        // combine the two column halves of this row: half 1 hands its partial to half 0 through smem
-                        float* part = aux + 6144 + unit_parity * 128;
-                        if (half == 1) part[quad * 32 + lane] = gated_partial;
-                        asm volatile("bar.sync 1, 256;" ::: "memory");
-                        if (half == 0 && row_ok)
-                            p.logits[(size_t)m * p.n_heads + head] = gated_partial + part[quad * 32 + lane] + __ldg(p.bc + head);
-                    }
-                }
-                (void)have_k;
+                epilogue_tile<BLOCK_N, EPI>(p, aux, t_row, m_tile * BLOCK_M, quad, half, warp - 2, lane, n_tile, n_group, inner, have_k,
+                                            gated_partial, unit_parity);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
@@ -461,11 +305,23 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
     return 0;
 }
 
+static int g_debug_flags = 0;
+
 // The fused-pass schedule is the default for nsplit = 3; MDL_GEMM_FUSED=0 selects the pass-serial one (debug / A-B).
 static bool use_fused() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("MDL_GEMM_FUSED");
+        v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+// CTA-pair kernels are the default for the 3-pass K-major GEMMs with N % 256 == 0; MDL_GEMM_2CTA=0 disables them.
+static bool use_2cta() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MDL_GEMM_2CTA");
         v = (e != nullptr && e[0] == '0') ? 0 : 1;
     }
     return v == 1;
@@ -489,11 +345,12 @@ int mdl_gemm_nt(const void* a_planes, long long a_rows, long long a_cols, long l
     const int planes = nsplit == 3 ? 2 : 1;
     const int bn = (N % 256 == 0) ? 256 : 128;
     const bool fused = nsplit == 3 && use_fused();
+    const bool two_cta = fused && bn == 256 && use_2cta() && g_debug_flags == 0;
     const int bk = fused ? BLOCK_KF : BLOCK_K;
     CUtensorMap ta, tb;
     int rc = make_plane_tmap(&ta, a_planes, a_rows, a_cols, lda, a_plane_stride, planes, BLOCK_M, bk);
     if (rc) return rc;
-    rc = make_plane_tmap(&tb, b_planes, b_rows, b_cols, ldb, b_plane_stride, planes, bn, bk);
+    rc = make_plane_tmap(&tb, b_planes, b_rows, b_cols, ldb, b_plane_stride, planes, two_cta ? 128 : bn, bk);
     if (rc) return rc;
     GemmArgs g{};
     g.M = M; g.N = N; g.k_blocks = K / bk; g.nsplit = nsplit;
@@ -503,6 +360,11 @@ int mdl_gemm_nt(const void* a_planes, long long a_rows, long long a_cols, long l
     g.grp_n_tiles = grp_n_cols > 0 ? grp_n_cols / bn : (1 << 30); g.a_koff = a_koff;
     g.grp_m_tiles = 1 << 30; g.b_coff = 0;
     g.out = out; g.ldc = (int)ldc; g.bias = bias; g.rowbias = rowbias; g.row2bag = row2bag;
+    g.debug_flags = g_debug_flags;
+    if (two_cta) {
+        g.num_m_tiles = (M + 255) / 256;
+        return launch_gemm2_kf(ta, tb, g, EPI_STORE, (cudaStream_t)stream);
+    }
     if (fused) {
         if (bn == 256) return launch_gemm<256, MODE_KF, EPI_STORE>(ta, tb, g, (cudaStream_t)stream);
         return launch_gemm<128, MODE_KF, EPI_STORE>(ta, tb, g, (cudaStream_t)stream);
@@ -510,6 +372,9 @@ int mdl_gemm_nt(const void* a_planes, long long a_rows, long long a_cols, long l
     if (bn == 256) return launch_gemm<256, MODE_K, EPI_STORE>(ta, tb, g, (cudaStream_t)stream);
     return launch_gemm<128, MODE_K, EPI_STORE>(ta, tb, g, (cudaStream_t)stream);
 }
+
+/* benchmark-only knob (tools/gemm_bounds.py): 1 = skip TMA loads, 2 = skip epilogue global writes in mdl_gemm_nt */
+int mdl_gemm_debug_flags(int flags) { g_debug_flags = flags; return 0; }
 
 int mdl_gemm_gated(const void* a_planes, long long a_rows, long long a_cols, long long lda, long long a_plane_stride,
                    const void* b_planes, long long b_plane_stride,
@@ -521,11 +386,12 @@ int mdl_gemm_gated(const void* a_planes, long long a_rows, long long a_cols, lon
     const int planes = nsplit == 3 ? 2 : 1;
     const int K = 512, N = n_heads * 1024;
     const bool fused = nsplit == 3 && use_fused();
+    const bool two_cta = fused && use_2cta();
     const int bk = fused ? BLOCK_KF : BLOCK_K;
     CUtensorMap ta, tb;
     int rc = make_plane_tmap(&ta, a_planes, a_rows, a_cols, lda, a_plane_stride, planes, BLOCK_M, bk);
     if (rc) return rc;
-    rc = make_plane_tmap(&tb, b_planes, N, K, K, b_plane_stride, planes, 256, bk);
+    rc = make_plane_tmap(&tb, b_planes, N, K, K, b_plane_stride, planes, two_cta ? 128 : 256, bk);
     if (rc) return rc;
     GemmArgs g{};
     g.M = M; g.N = N; g.k_blocks = K / bk; g.nsplit = nsplit;
@@ -534,6 +400,10 @@ int mdl_gemm_gated(const void* a_planes, long long a_rows, long long a_cols, lon
     g.ba = ba; g.bb = bb; g.wc = wc; g.bc = bc; g.logits = logits;
     g.gate_a = reinterpret_cast<__half*>(gate_a); g.gate_b = reinterpret_cast<__half*>(gate_b);
     g.drop_p = drop_p; g.seed = seed; g.n_heads = n_heads;
+    if (two_cta) {
+        g.num_m_tiles = (M + 255) / 256;
+        return launch_gemm2_kf(ta, tb, g, EPI_GATED, (cudaStream_t)stream);
+    }
     if (fused) return launch_gemm<256, MODE_KF, EPI_GATED>(ta, tb, g, (cudaStream_t)stream);
     return launch_gemm<256, MODE_K, EPI_GATED>(ta, tb, g, (cudaStream_t)stream);
 }
@@ -547,25 +417,31 @@ int mdl_gemm_tn_accum(const void* a_planes, long long a_cols, long long lda, lon
     MDL_REQUIRE(M % BLOCK_M == 0 && N % 256 == 0, "wgrad output must be a multiple of 128 x 256 (got %d x %d)", M, N);
     MDL_REQUIRE(tokens > 0, "tokens must be positive");
     const int planes = nsplit == 3 ? 2 : 1;
+    const bool two_cta = nsplit == 3 && use_fused() && use_2cta() && M % 256 == 0 &&
+                         (grp_m_rows <= 0 || grp_m_rows % 256 == 0);
+    const int bk = two_cta ? BLOCK_KF : BLOCK_K;
     CUtensorMap ta, tb;
-    int rc = make_plane_tmap(&ta, a_planes, tokens, a_cols, lda, a_plane_stride, planes, BLOCK_K);
+    int rc = make_plane_tmap(&ta, a_planes, tokens, a_cols, lda, a_plane_stride, planes, bk);
     if (rc) return rc;
-    rc = make_plane_tmap(&tb, b_planes, tokens, b_cols, ldb, b_plane_stride, planes, BLOCK_K);
+    rc = make_plane_tmap(&tb, b_planes, tokens, b_cols, ldb, b_plane_stride, planes, bk);
     if (rc) return rc;
     GemmArgs g{};
-    g.M = M; g.N = N; g.k_blocks = (int)((tokens + BLOCK_K - 1) / BLOCK_K); g.nsplit = nsplit;
-    g.num_m_tiles = M / BLOCK_M; g.num_n_tiles = N / 256; g.n_inner = 1;
+    g.M = M; g.N = N; g.k_blocks = (int)((tokens + bk - 1) / bk); g.nsplit = nsplit;
+    const int tile_m = two_cta ? 256 : BLOCK_M;
+    g.num_m_tiles = M / tile_m; g.num_n_tiles = N / 256; g.n_inner = 1;
     const int mn_tiles = g.num_m_tiles * g.num_n_tiles;
+    const int workers = two_cta ? kNumSMs / 2 : kNumSMs;
     if (ksplit <= 0) {
-        // aim for ~4 work units per SM, never more splits than k-blocks
-        ksplit = (4 * kNumSMs + mn_tiles - 1) / mn_tiles;
+        // aim for ~4 work units per worker (CTA or CTA pair), never more splits than k-blocks
+        ksplit = (4 * workers + mn_tiles - 1) / mn_tiles;
     }
     if (ksplit > g.k_blocks) ksplit = g.k_blocks;
     if (ksplit < 1) ksplit = 1;
     g.ksplit = ksplit;
     g.grp_n_tiles = 1 << 30; g.a_koff = 0;
-    g.grp_m_tiles = grp_m_rows > 0 ? grp_m_rows / BLOCK_M : (1 << 30); g.b_coff = b_coff;
+    g.grp_m_tiles = grp_m_rows > 0 ? grp_m_rows / tile_m : (1 << 30); g.b_coff = b_coff;
     g.out = out; g.ldc = (int)ldc;
+    if (two_cta) return launch_gemm2_mn(ta, tb, g, (cudaStream_t)stream);
     return launch_gemm<256, MODE_MN, EPI_ATOMIC>(ta, tb, g, (cudaStream_t)stream);
 }
 

@@ -30,13 +30,13 @@ def cfg(mods, precision):
                      activation="softmax", n_heads=4, b200_precision=precision)
 
 
-def config3(precision, steps, warmup, skip=True):
+def config3(precision, steps, warmup, skip=True, bs=32, tag="BASELINE configs[2]: batch=32"):
     dev = torch.device("cuda")
     mods = ["HE", "HER2", "PGR", "KI67", "ER"]
     model = MADELEINE(cfg(mods, precision), stain_encoding=True)
     model.load_state_dict(make_state_dict(3, n_mod=5, stain_encoding=True))
     model.to(dev).train()
-    bs, T = 32, 2048
+    T = 2048
     g = torch.Generator().manual_seed(0)
     labels = (torch.rand(bs, 5, generator=g) < torch.tensor([1.0, 0.46, 0.73, 0.73, 0.73])).float()
     labels[:, 0] = 1
@@ -67,7 +67,7 @@ def config3(precision, steps, warmup, skip=True):
     ms = e0.elapsed_time(e1) / steps
     kt = {k: sum(a.elapsed_time(b) for a, b in v) / steps for k, v in _lib.kernel_events.items()}
     bags = bs * 5
-    print(json.dumps({"config": "BASELINE configs[2]: batch=32, 5 stains, T=2048, stain encodings, InfoNCE + GOT, fwd+bwd, train mode",
+    print(json.dumps({"config": tag + ", 5 stains, T=2048, stain encodings, InfoNCE + GOT, fwd+bwd, train mode",
                       "missing_bags_encoded_from_one_token": skip, "missing_bag_fraction": float(1 - labels.mean()),
                       "precision": precision, "ms_per_step": ms, "slides_per_s": bags / (ms * 1e-3), "cases_per_s": bs / (ms * 1e-3),
                       "loss": float(loss), "cases_per_stain": labels[:, 1:].sum(0).tolist(), "loss_kernel_ms_per_step": kt,
@@ -118,5 +118,8 @@ if __name__ == "__main__":
     if "3" in a.which:
         config3(a.precision, a.steps, 2, skip=True)
         config3(a.precision, a.steps, 2, skip=False)
+    if "canon" in a.which:
+        # the reference's shipped pre-training configuration (scripts/launch_pretrain_withStainEncodings.sh): batch 65
+        config3(a.precision, a.steps, 2, skip=True, bs=65, tag="reference canonical config: batch=65")
     if "5" in a.which:
         config5(a.precision, a.slides, 4000)

@@ -97,17 +97,18 @@ struct Vecs {
 };
 
 // IPOT forward (loss.py:179-193) on L = -C/beta.  On exit T holds the plan T_K, lu/lw[t] the cumulative log scalings.
-__device__ void ipot_forward(const float* L, float* T, int K, int n, int ld, const Vecs& v) {
+// `A` is scratch for exp(L) (computed once instead of once per iteration).
+__device__ void ipot_forward(const float* L, float* T, float* A, int K, int n, int ld, const Vecs& v) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float inv_n = 1.f / n;
-    for (int idx = tid; idx < n * ld; idx += GOT_THREADS) T[idx] = 1.f;
+    for (int idx = tid; idx < n * ld; idx += GOT_THREADS) { T[idx] = 1.f; A[idx] = expf(L[idx]); }
     for (int j = tid; j < n; j += GOT_THREADS) { v.sigma[j] = inv_n; v.lu[j] = 0.f; v.lw[j] = 0.f; }
     __syncthreads();
     for (int t = 1; t <= K; ++t) {
         for (int i = warp; i < n; i += GOT_WARPS) {          // Q = A * T (in place), delta = 1 / (n Q sigma)
             float rs = 0.f;
             for (int j = lane; j < n; j += 32) {
-                const float qv = expf(L[i * ld + j]) * T[i * ld + j];
+                const float qv = A[i * ld + j] * T[i * ld + j];
                 T[i * ld + j] = qv;
                 rs = fmaf(qv, v.sigma[j], rs);
             }
@@ -307,7 +308,9 @@ __global__ void got_extrema_kernel(GotLayout lay, float* __restrict__ ws, float*
 // ---------------------------------------------------------------------------------------------------
 // kernel C: forward + reverse sweep of one problem, down to gradients w.r.t. the thresholded costs
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GOT_THREADS, 1)
+// two CTAs per SM when shared memory allows (n <= ~70): the four per-stain problem sets of a step (<= 65 CTAs each, issued on
+// side streams) then fit in one wave
+__global__ void __launch_bounds__(GOT_THREADS, 2)
 got_main_kernel(GotLayout lay, float* __restrict__ ws, const float* __restrict__ extrema, float* __restrict__ wd_out, float* __restrict__ gwd_out) {
     extern __shared__ float sm[];
     const int n = lay.n, ld = n | 1;
@@ -332,7 +335,7 @@ got_main_kernel(GotLayout lay, float* __restrict__ ws, const float* __restrict__
     // S1 = L = -C/beta (C = relu(C0 - thr0));  S0 = T
     load_mat(S1, slab + lay.raw0, n, ld, -1.f / WD_BETA, thr0, true);
     __syncthreads();
-    ipot_forward(S1, S0, WD_ITERS, n, ld, v);
+    ipot_forward(S1, S0, S2, WD_ITERS, n, ld, v);
     {   // wd = <C, T>;  dT_K = C (into S2);  direct dC = T kept in S0;  dL accumulator S3 = 0
         float acc = 0.f;
         for (int idx = tid; idx < n * n; idx += GOT_THREADS) {
@@ -397,7 +400,7 @@ got_main_kernel(GotLayout lay, float* __restrict__ ws, const float* __restrict__
             S4[i * ld + j] *= -1.f / GW_BETA;
         }
         __syncthreads();
-        ipot_forward(S4, S0, GW_INNER, n, ld, v);
+        ipot_forward(S4, S0, S2, GW_INNER, n, ld, v);
         store_mat(S0, slab + lay.gamma + (size_t)k * lay.nn, n, ld);
         float* lulw = slab + lay.lulw + (size_t)k * 2 * (GW_INNER + 1) * n;
         for (int idx = tid; idx < (GW_INNER + 1) * n; idx += GOT_THREADS) {

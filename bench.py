@@ -49,7 +49,61 @@ def read_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock and throttle reasons sampled every ~10 ms through NVML (nvidia_ml_py) while the timed region runs;
+    falls back to `nvidia-smi -lms` when NVML is not importable."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self._smi = None
+
+    def _visible_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.index])
+            except (ValueError, IndexError):
+                return self.index
+        return self.index
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._visible_index())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        for bit, name in self.REASONS.items():
+                            if mask & bit:
+                                self.reasons.add(name)
+                    except Exception:  # noqa: BLE001
+                        pass
+                    time.sleep(0.01)
+
+            self._thread = threading.Thread(target=poll, daemon=True)
+            self._thread.start()
+        except Exception:  # noqa: BLE001
+            self._smi = _SmiSampler(self.index)
+            self._smi.start()
+
+    def stop(self):
+        if self._smi is not None:
+            return self._smi.stop()
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=1.0)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples), "source": "nvml, 10 ms period"}
+
+
+class _SmiSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -59,7 +113,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
@@ -71,7 +125,7 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        time.sleep(0.1)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -87,7 +141,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 50"}
 
 
 def model_cfg(precision):

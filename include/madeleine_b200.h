@@ -144,6 +144,15 @@ int mdl_got_max_tokens(void);
 int mdl_got_extrema(const float* v, const float* q, int m, int n, int D, void* workspace, float* extrema, void* stream);
 int mdl_got_fwd_bwd(const float* v, const float* q, int m, int n, int D, void* workspace, const float* extrema,
                     float* loss, float* wd, float* gwd, float* dv, float* dq, void* stream);
+/* The same in two steps for case-sharded runs (quirk Q5 couples all problems of a stain through the batch-wide min/max):
+ *   mdl_got_extrema -> all-reduce MIN/MAX of `extrema` across ranks -> mdl_got_main (also writes the 3 local
+ *   threshold-gradient sums to dthr_local) -> all-reduce SUM of dthr -> mdl_got_finish(dthr_global).
+ * A rank adds the threshold gradient to its arg-min/max element only if its local extremum equals the global one. */
+int mdl_got_main(int m, int n, int D, void* workspace, const float* extrema, float* wd, float* gwd, float* dthr_local,
+                 void* stream);
+int mdl_got_finish(const float* v, const float* q, int m, int n, int D, void* workspace, const float* extrema,
+                   const float* dthr_global, const float* wd, const float* gwd, float* loss, float* dv, float* dq,
+                   void* stream);
 
 /* ---- optimiser (train-step caller) -------------------------------------------------------------- */
 /* Fused multi-tensor AdamW, one launch for all parameters (torch.optim.AdamW semantics; reference:

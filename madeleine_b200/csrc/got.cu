@@ -501,6 +501,7 @@ got_main_kernel(GotLayout lay, float* __restrict__ ws, const float* __restrict__
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GOT_THREADS)
 got_grad_kernel(const float* __restrict__ v, const float* __restrict__ q, GotLayout lay, float* __restrict__ ws,
+                const float* __restrict__ extrema, const float* __restrict__ dthr_ext,
                 const float* __restrict__ wd, const float* __restrict__ gwd, float* __restrict__ loss,
                 float* __restrict__ dv, float* __restrict__ dq) {
     extern __shared__ float sm[];
@@ -522,7 +523,11 @@ got_grad_kernel(const float* __restrict__ v, const float* __restrict__ q, GotLay
     }
     if (tid < 3) {
         float s = 0.f;
-        for (int i = 0; i < lay.m; ++i) s += ws[lay.header + lay.per_item * (size_t)i + lay.ext + 12 + tid];
+        if (dthr_ext != nullptr) {
+            s = dthr_ext[tid];                   // sharded run: sums over ALL ranks' problems (all-reduced by the host side)
+        } else {
+            for (int i = 0; i < lay.m; ++i) s += ws[lay.header + lay.per_item * (size_t)i + lay.ext + 12 + tid];
+        }
         dthr[tid] = s;
     }
     for (int r = warp; r < 2 * n; r += GOT_WARPS) {
@@ -542,7 +547,9 @@ got_grad_kernel(const float* __restrict__ v, const float* __restrict__ q, GotLay
     if (tid < 6) {
         const int* h = reinterpret_cast<const int*>(ws);
         const int which = tid >> 1, is_max = tid & 1;
-        if (h[tid * 2] == b) {
+        // the local candidate owns the extremum only if it equals the (possibly all-reduced) batch extremum
+        const float local_best = ws[lay.header + lay.per_item * (size_t)h[tid * 2] + lay.ext + tid];
+        if (h[tid * 2] == b && local_best == extrema[tid]) {
             float* g = slab + (which == 0 ? lay.g0 : (which == 1 ? lay.gs : lay.gt));
             atomicAdd(g + h[tid * 2 + 1], (is_max ? THR_BETA : 1.f - THR_BETA) * dthr[which]);
         }
@@ -585,6 +592,15 @@ got_grad_kernel(const float* __restrict__ v, const float* __restrict__ q, GotLay
     }
 }
 
+// local sums of the three threshold-gradient partials (one launch, 3 threads) for the sharded path
+__global__ void got_dthr_kernel(GotLayout lay, const float* __restrict__ ws, float* __restrict__ dthr_out) {
+    const int k = threadIdx.x;
+    if (k >= 3) return;
+    float s = 0.f;
+    for (int i = 0; i < lay.m; ++i) s += ws[lay.header + lay.per_item * (size_t)i + lay.ext + 12 + k];
+    dthr_out[k] = s;
+}
+
 static size_t main_smem_bytes(int n) {
     const int ld = n | 1;
     return sizeof(float) * ((size_t)5 * n * ld + (size_t)13 * n + (size_t)2 * (MAX_ITERS + 1) * n);
@@ -622,24 +638,49 @@ int mdl_got_extrema(const float* v, const float* q, int m, int n, int D, void* w
     return 0;
 }
 
-int mdl_got_fwd_bwd(const float* v, const float* q, int m, int n, int D, void* workspace, const float* extrema,
-                    float* loss, float* wd, float* gwd, float* dv, float* dq, void* stream) {
-    MDL_REQUIRE(m > 0 && n > 0 && n <= GOT_NMAX, "GOT: n must be in [1, %d] (got %d)", GOT_NMAX, n);
-    MDL_REQUIRE(D > 0 && D <= 128, "GOT: token dim must be <= 128 (got %d)", D);
-    cudaStream_t st = (cudaStream_t)stream;
-    GotLayout lay(m, n, D);
+static int got_set_attrs() {
     static bool attr = false;
     if (!attr) {
         MDL_CHECK_CUDA(cudaFuncSetAttribute(got_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)main_smem_bytes(GOT_NMAX)));
         MDL_CHECK_CUDA(cudaFuncSetAttribute(got_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * (2 * GOT_NMAX * 129 + 2 * GOT_NMAX))));
         attr = true;
     }
+    return 0;
+}
+
+int mdl_got_main(int m, int n, int D, void* workspace, const float* extrema, float* wd, float* gwd, float* dthr_local, void* stream) {
+    MDL_REQUIRE(m > 0 && n > 0 && n <= GOT_NMAX, "GOT: n must be in [1, %d] (got %d)", GOT_NMAX, n);
+    cudaStream_t st = (cudaStream_t)stream;
+    GotLayout lay(m, n, D);
+    if (int rc = got_set_attrs()) return rc;
     got_main_kernel<<<m, GOT_THREADS, main_smem_bytes(n), st>>>(lay, (float*)workspace, extrema, wd, gwd);
     MDL_CHECK_LAUNCH();
+    if (dthr_local != nullptr) {
+        got_dthr_kernel<<<1, 32, 0, st>>>(lay, (const float*)workspace, dthr_local);
+        MDL_CHECK_LAUNCH();
+    }
+    return 0;
+}
+
+int mdl_got_finish(const float* v, const float* q, int m, int n, int D, void* workspace, const float* extrema, const float* dthr_global,
+                   const float* wd, const float* gwd, float* loss, float* dv, float* dq, void* stream) {
+    MDL_REQUIRE(m > 0 && n > 0 && n <= GOT_NMAX, "GOT: n must be in [1, %d] (got %d)", GOT_NMAX, n);
+    MDL_REQUIRE(D > 0 && D <= 128, "GOT: token dim must be <= 128 (got %d)", D);
+    cudaStream_t st = (cudaStream_t)stream;
+    GotLayout lay(m, n, D);
+    if (int rc = got_set_attrs()) return rc;
     const size_t smem = sizeof(float) * ((size_t)2 * n * (D + 1) + 2 * n);
-    got_grad_kernel<<<m, GOT_THREADS, smem, st>>>(v, q, lay, (float*)workspace, wd, gwd, loss, dv, dq);
+    got_grad_kernel<<<m, GOT_THREADS, smem, st>>>(v, q, lay, (float*)workspace, extrema, dthr_global, wd, gwd, loss, dv, dq);
     MDL_CHECK_LAUNCH();
     return 0;
+}
+
+int mdl_got_fwd_bwd(const float* v, const float* q, int m, int n, int D, void* workspace, const float* extrema,
+                    float* loss, float* wd, float* gwd, float* dv, float* dq, void* stream) {
+    MDL_REQUIRE(D > 0 && D <= 128, "GOT: token dim must be <= 128 (got %d)", D);
+    int rc = mdl_got_main(m, n, D, workspace, extrema, wd, gwd, nullptr, stream);
+    if (rc) return rc;
+    return mdl_got_finish(v, q, m, n, D, workspace, extrema, nullptr, wd, gwd, loss, dv, dq, stream);
 }
 
 }  // extern "C"

@@ -625,6 +625,58 @@ class GOTFn(torch.autograd.Function):
         return dv * go, dq * go, None
 
 
+class GOTShardedFn(torch.autograd.Function):
+    """GOT over this rank's share of the (case, stain) problems when cases are sharded across ranks.
+
+    The batch-wide min/max of the three cost tensors (quirk Q5) are all-reduced between the cost kernel and the main
+    kernel, and the three threshold-gradient sums between the main kernel and the gradient kernel; token embeddings
+    never leave their rank.  Every rank must call this for every stain, even with zero local problems.  Returns the sum
+    of the LOCAL problems' losses (the global loss is the sum over ranks)."""
+
+    @staticmethod
+    def forward(ctx, v, q):
+        import torch.distributed as dist
+        m, n, D = v.shape
+        dev = v.device
+        st = stream_ptr(dev)
+        neg = torch.tensor([-1.0, 1.0, -1.0, 1.0, -1.0, 1.0], device=dev)
+        if m > 0:
+            v = v.contiguous().float()
+            q = q.contiguous().float()
+            max_n = call("mdl_got_max_tokens")
+            if n > max_n:
+                raise RuntimeError(f"madeleine_b200 GOT kernel supports at most {max_n} tokens per problem (got {n})")
+            ws = torch.empty(call("mdl_got_workspace_bytes", m, n, D), dtype=torch.uint8, device=dev)
+            extrema = torch.empty(6, dtype=torch.float32, device=dev)
+            call("mdl_got_extrema", v, q, m, n, D, ws, extrema, st)
+            packed = extrema * neg                       # (-min, max) pairs -> one MAX all-reduce
+        else:
+            packed = torch.full((6,), float("-inf"), device=dev)
+        dist.all_reduce(packed, op=dist.ReduceOp.MAX)
+        extrema_g = (packed * neg).contiguous()
+        dthr = torch.zeros(3, dtype=torch.float32, device=dev)
+        if m > 0:
+            wd = torch.empty(m, dtype=torch.float32, device=dev)
+            gwd = torch.empty(m, dtype=torch.float32, device=dev)
+            call("mdl_got_main", m, n, D, ws, extrema_g, wd, gwd, dthr, st)
+        dist.all_reduce(dthr, op=dist.ReduceOp.SUM)
+        loss = torch.zeros((), dtype=torch.float32, device=dev)
+        if m > 0:
+            dv = torch.empty_like(v)
+            dq = torch.empty_like(q)
+            call("mdl_got_finish", v, q, m, n, D, ws, extrema_g, dthr, wd, gwd, loss, dv, dq, st)
+            ctx.save_for_backward(dv, dq)
+        ctx.has_local = m > 0
+        return loss
+
+    @staticmethod
+    def backward(ctx, go):
+        if not ctx.has_local:
+            return None, None
+        dv, dq = ctx.saved_tensors
+        return dv * go, dq * go
+
+
 def got_loss(v, q, slot: int = -1):
     _lib.require_cuda(v, "GOT tokens")
     return GOTFn.apply(v, q, slot)

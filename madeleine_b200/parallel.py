@@ -106,3 +106,53 @@ def allreduce_gradients(module: torch.nn.Module):
         n = g.numel()
         g.copy_(flat[o:o + n].view_as(g))
         o += n
+
+
+def got_sharded(v_local: torch.Tensor, q_local: torch.Tensor, m_global: int, subsample: int = 256) -> torch.Tensor:
+    """Local Graph-OT loss with cases sharded across ranks.  v_local / q_local: [m_local, T, 128] token embeddings of this
+    rank's cases that have the stain (m_local may be 0); m_global: number of such cases over all ranks.
+
+    Reproduces the reference's subsampling quirk (Q3, loss.py:281-284) on the GLOBAL batch: one permutation of
+    range(m_global) — rank 0's draw from torch's CPU generator, broadcast — indexes the token axis on every rank.
+    Returns the sum of the local problems' losses; summing over ranks gives the reference's value for the whole batch."""
+    from . import ops
+    dev = v_local.device
+    perm = torch.randperm(m_global)[:subsample].to(dev)
+    dist.broadcast(perm, src=0)
+    return ops.GOTShardedFn.apply(v_local[:, perm, :], q_local[:, perm, :])
+
+
+def calculate_losses_sharded(STAINS, loss_fn_interMod, use_local, wsi_embs_global, token_embs_local, labels_global_withoutHE,
+                             args, rank: int, b_local: int):
+    """Sharded counterpart of utils.trainer.calculate_losses (reference trainer.py:20-77): slide embeddings are the
+    all-gathered ones (global batch), token embeddings and the local-loss problems stay on their rank.
+
+    Returns (loss, flag, parts).  ``loss`` = InfoNCE(global batch) + local_loss_weight * GOT(this rank's problems) is the
+    tensor to call ``backward()`` on: the all-gather's backward hands every rank only its own rows of dInfoNCE/dE, so
+    the parameter gradients SUMMED over ranks (encoder gradient sync) are exactly those of
+    InfoNCE + GOT(all problems).  The value of that global objective is  parts['global'] + all_reduce(parts['local'])."""
+    dev = wsi_embs_global["HE"].device
+    labels = labels_global_withoutHE.detach().to("cpu").bool()
+    counts = labels.sum(dim=0).tolist()
+    lo, hi = rank * b_local, (rank + 1) * b_local
+    g_terms, l_terms, flag = [], [], False
+    for s_idx, stain in enumerate(STAINS):
+        if counts[s_idx] <= 1:
+            continue
+        rows = labels[:, s_idx].nonzero(as_tuple=True)[0]
+        if loss_fn_interMod:
+            idx = rows.to(dev, non_blocking=True)
+            he = wsi_embs_global["HE"][:, 0, :, s_idx][idx]
+            ihc = wsi_embs_global[stain][:, 0, :][idx]
+            g_terms.append(loss_fn_interMod(query=he, positive_key=ihc, symmetric=args.symmetric_cl))
+        if use_local:
+            mine = (rows[(rows >= lo) & (rows < hi)] - lo).to(dev, non_blocking=True)
+            he_t = token_embs_local["HE"][:, :, :, s_idx][mine]
+            ihc_t = token_embs_local[stain][mine]
+            l_terms.append(got_sharded(he_t, ihc_t, counts[s_idx]) * args.local_loss_weight)
+        flag = True
+    zero = torch.zeros((), device=dev)
+    parts = {"global": sum(g_terms) if g_terms else zero, "local": sum(l_terms) if l_terms else zero}
+    if not (g_terms or l_terms):
+        return -1, flag, parts
+    return parts["global"] + parts["local"], flag, parts

@@ -339,3 +339,27 @@ def test_infonce_reductions():
     torch.testing.assert_close(none, ref, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(q.grad, q2.grad, rtol=1e-3, atol=1e-5)
     torch.testing.assert_close(k.grad, k2.grad, rtol=1e-3, atol=1e-5)
+
+
+def test_pool_empty_and_single_token_bags():
+    """Edge cases of the packed layout: an empty bag pools to zeros, a one-token bag returns that token."""
+    H, E = 4, 512
+    C = H * E
+    lens = [0, 1, 5, 0, 3]
+    cu, M = _ragged(lens)
+    x = torch.randn(M, C, device=DEV)
+    xp = ops.split_planes(x, 2)
+    logits = torch.randn(M, H, device=DEV)
+    out = torch.full((len(lens), C), 7.0, device=DEV)
+    attn = torch.zeros(M, H, device=DEV)
+    ops.pool_fwd(xp, 2, logits, cu, None, len(lens), M, H, E, out, attn, 0)
+    xr = planes_f32(xp)
+    assert float(out[0].abs().max()) == 0.0 and float(out[3].abs().max()) == 0.0
+    torch.testing.assert_close(out[1], xr[0], rtol=1e-6, atol=1e-7)
+    p = torch.softmax(logits[1:6], dim=0)
+    torch.testing.assert_close(out[2], (xr[1:6].view(5, H, E) * p[:, :, None]).sum(0).reshape(C), rtol=1e-5, atol=1e-6)
+    dS = torch.randn(len(lens), C, device=DEV)
+    dlogit = torch.zeros(M, H, device=DEV)
+    call("mdl_pool_bwd_dlogit", xp, M * C, 2, dS, out, attn, cu, None, len(lens), M, H, E, dlogit, 0, logits, 0, 1, _st())
+    assert torch.isfinite(dlogit).all()
+    assert float(dlogit[0].abs().max()) < 1e-6          # a one-token bag has a constant softmax: zero logit gradient

@@ -91,18 +91,21 @@ int mdl_gate_bwd(const void* gate_a, const void* gate_b, const float* dlogit, co
                  float* dba, float* dbb, float* dwc, float* dbc, void* stream);
 
 /* ---- attention pooling (the HBM-bound kernel) ---------------------------------------------------------------- */
-/* softmax over tokens + weighted sum (abmil.py:55, Model.py:416-417); activation 0 softmax, 1 leaky_relu, 2 relu,
- * 3 sigmoid (abmil.py:54-63).  out [n_bags, n_heads*head_dim] head-major; attn_p [tokens, n_heads] receives the
- * attention weights (required; rows outside every segment are left untouched).
- * tok_idx (optional) gathers rows: segment r pools rows tok_idx[cu[r] .. cu[r+1]) (n_views=3, Model.py:427-437).
- * Each bag is split over `tsplit` CTAs along tokens (mdl_pool_tsplit suggests a value that fills the 148 SMs); the
- * partial sums go through `workspace` (mdl_pool_workspace_bytes; may be NULL when tsplit == 1) and are combined in a
- * fixed order, so results are bit-reproducible. */
+/* softmax over tokens + weighted sum (abmil.py:55, Model.py:416-417) in two launches:
+ *   mdl_pool_weights: attn_p[t, h] = act(logits) per (bag, head); activation 0 softmax over the bag's tokens, 1 leaky_relu,
+ *                     2 relu, 3 sigmoid (abmil.py:54-63).  Also clears the split tickets in `workspace`.
+ *   mdl_pool_fwd:     out[r, h, :] = sum_t attn_p[t, h] * X[t, h, :]   (the HBM-bound streaming kernel), head-major out.
+ * tok_idx (optional) gathers rows: segment r pools rows tok_idx[cu[r] .. cu[r+1]) (n_views=3, Model.py:427-437); rows
+ * outside every segment are left untouched in attn_p.  Each bag is split over `tsplit` CTAs along tokens (mdl_pool_tsplit
+ * suggests ~192 tokens per CTA); partial sums go through `workspace` (mdl_pool_workspace_bytes; may be NULL when
+ * tsplit == 1) and are combined in a fixed order, so results are bit-reproducible. */
 int mdl_pool_tsplit(int n_bags, long long total_tokens, int n_heads, int head_dim);
 long long mdl_pool_workspace_bytes(int n_bags, int n_heads, int head_dim, int tsplit);
-int mdl_pool_fwd(const void* x_planes, long long plane_stride, int nplanes, const float* logits, const int* cu_seqlens,
+int mdl_pool_weights(const float* logits, const int* cu_seqlens, const int* tok_idx, int n_bags, int n_heads, int head_dim,
+                     float* attn_p, int activation, int tsplit, void* workspace, void* stream);
+int mdl_pool_fwd(const void* x_planes, long long plane_stride, int nplanes, const float* attn_p, const int* cu_seqlens,
                  const int* tok_idx, int n_bags, long long total_tokens, int n_heads, int head_dim,
-                 float* out, float* attn_p, int activation, int tsplit, void* workspace, void* stream);
+                 float* out, int tsplit, void* workspace, void* stream);
 int mdl_pool_bwd_dlogit(const void* x_planes, long long plane_stride, int nplanes, const float* dS, const float* S,
                         const float* attn_p, const int* cu_seqlens, const int* tok_idx, int n_bags,
                         long long total_tokens, int n_heads, int head_dim, float* dlogit, int accumulate,

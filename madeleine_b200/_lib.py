@@ -47,7 +47,8 @@ SIGNATURES = {
     "mdl_gate_bwd": [c_p, c_p, c_p, c_p, c_ll, c_i, c_f, c_ull, c_p, c_ll, c_i, c_p, c_p, c_p, c_p, c_p],
     "mdl_pool_tsplit": [c_i, c_ll, c_i, c_i],
     "mdl_pool_workspace_bytes": [c_i, c_i, c_i, c_i],
-    "mdl_pool_fwd": [c_p, c_ll, c_i, c_p, c_p, c_p, c_i, c_ll, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_p],
+    "mdl_pool_weights": [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_p],
+    "mdl_pool_fwd": [c_p, c_ll, c_i, c_p, c_p, c_p, c_i, c_ll, c_i, c_i, c_p, c_i, c_p, c_p],
     "mdl_pool_bwd_dlogit": [c_p, c_ll, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_ll, c_i, c_i, c_p, c_i, c_p, c_i, c_i, c_p],
     "mdl_planes_to_ref_order": [c_p, c_ll, c_i, c_ll, c_i, c_i, c_p, c_p],
     "mdl_skinny_linear_fwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p],
@@ -112,7 +113,7 @@ def load():
 LAUNCHES = {
     "mdl_split_planes": 1, "mdl_gather_split": 1, "mdl_gather_f32": 1, "mdl_scatter_f32": 1, "mdl_row2bag": 1,
     "mdl_gemm_nt": 1, "mdl_gemm_gated": 1, "mdl_gemm_tn_accum": 1, "mdl_gemm_nt_simt": 1, "mdl_gemm_tn_simt": 1,
-    "mdl_ln_gelu_fwd": 1, "mdl_ln_gelu_bwd": 1, "mdl_gate_bwd": 1, "mdl_pool_fwd": 2, "mdl_pool_bwd_dlogit": 1,
+    "mdl_ln_gelu_fwd": 1, "mdl_ln_gelu_bwd": 1, "mdl_gate_bwd": 1, "mdl_pool_weights": 1, "mdl_pool_fwd": 1, "mdl_pool_bwd_dlogit": 1,
     "mdl_planes_to_ref_order": 1, "mdl_skinny_linear_fwd": 1, "mdl_skinny_linear_bwd": 2, "mdl_stain_rowbias": 1,
     "mdl_bag_colsum_planes": 1, "mdl_stain_rowbias_bwd": 1, "mdl_colsum_f32": 1, "mdl_infonce_fwd": 4, "mdl_infonce_bwd": 2,
     "mdl_got_extrema": 2, "mdl_got_fwd_bwd": 2, "mdl_got_main": 2, "mdl_got_finish": 1, "mdl_adamw_step": 1,

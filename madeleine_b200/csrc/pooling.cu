@@ -64,9 +64,10 @@ __device__ __forceinline__ float attn_weight_grad(float l, float w, int act) {  
 // attention weights of one (bag, head): p[t, h] = act(logit) (softmax over the bag's tokens, or a pointwise activation).
 __global__ void __launch_bounds__(POOL_THREADS)
 pool_weights_kernel(const float* __restrict__ logits, const int* __restrict__ cu, const int* __restrict__ tok_idx, int H,
-                    float* __restrict__ attn_p, int act) {
+                    float* __restrict__ attn_p, int act, int* __restrict__ tickets, int halves) {
     __shared__ float scratch[33];
     const int r = blockIdx.x;
+    if (tickets != nullptr && threadIdx.x < halves) tickets[(r * H + blockIdx.y) * halves + threadIdx.x] = 0;
     const int t0 = cu[r], n = cu[r + 1] - t0;
     {
         const int h = blockIdx.y;
@@ -265,26 +266,39 @@ using namespace mdl;
 
 extern "C" {
 
-int mdl_pool_fwd(const void* x_planes, long long plane_stride, int nplanes, const float* logits, const int* cu_seqlens,
+static int* pool_tickets(void* workspace, int tsplit, int n_bags, int n_heads, int head_dim) {
+    if (tsplit <= 1 || workspace == nullptr) return nullptr;
+    return reinterpret_cast<int*>(reinterpret_cast<float*>(workspace) + (size_t)tsplit * n_bags * n_heads * head_dim);
+}
+
+int mdl_pool_weights(const float* logits, const int* cu_seqlens, const int* tok_idx, int n_bags, int n_heads, int head_dim,
+                     float* attn_p, int activation, int tsplit, void* workspace, void* stream) {
+    MDL_REQUIRE(activation >= 0 && activation <= 3, "pool_weights: unknown activation %d", activation);
+    MDL_REQUIRE(attn_p != nullptr, "pool_weights: attn_p ([tokens, n_heads] fp32) is required");
+    MDL_REQUIRE(tsplit >= 1 && tsplit <= 64, "pool_weights: tsplit must be in [1, 64]");
+    MDL_REQUIRE(tsplit == 1 || workspace != nullptr, "pool_weights: tsplit > 1 needs the pooling workspace (its tickets are cleared here)");
+    if (n_bags == 0) return 0;
+    const int halves = head_dim / 256 > 0 ? head_dim / 256 : 1;
+    pool_weights_kernel<<<dim3(n_bags, n_heads), POOL_THREADS, 0, (cudaStream_t)stream>>>(
+        logits, cu_seqlens, tok_idx, n_heads, attn_p, activation, pool_tickets(workspace, tsplit, n_bags, n_heads, head_dim), halves);
+    MDL_CHECK_LAUNCH();
+    return 0;
+}
+
+int mdl_pool_fwd(const void* x_planes, long long plane_stride, int nplanes, const float* attn_p, const int* cu_seqlens,
                  const int* tok_idx, int n_bags, long long total_tokens, int n_heads, int head_dim,
-                 float* out, float* attn_p, int activation, int tsplit, void* workspace, void* stream) {
-    MDL_REQUIRE(activation >= 0 && activation <= 3, "pool_fwd: unknown activation %d", activation);
+                 float* out, int tsplit, void* workspace, void* stream) {
     MDL_REQUIRE(head_dim % 256 == 0, "pool_fwd: head_dim must be a multiple of 256 (got %d)", head_dim);
     MDL_REQUIRE(nplanes == 1 || nplanes == 2, "pool_fwd: nplanes must be 1 or 2");
-    MDL_REQUIRE(attn_p != nullptr, "pool_fwd: attn_p ([tokens, n_heads] fp32) is required");
+    MDL_REQUIRE(attn_p != nullptr, "pool_fwd: attn_p (from mdl_pool_weights) is required");
+    (void)total_tokens;
     if (n_bags == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     const int halves = head_dim / 256;
     MDL_REQUIRE(tsplit >= 1 && tsplit <= 64, "pool_fwd: tsplit must be in [1, 64] (use mdl_pool_tsplit), got %d", tsplit);
     MDL_REQUIRE(tsplit == 1 || workspace != nullptr, "pool_fwd: tsplit > 1 needs a workspace (mdl_pool_workspace_bytes)");
     float* partial = reinterpret_cast<float*>(workspace);
-    int* tickets = nullptr;
-    if (tsplit > 1) {
-        tickets = reinterpret_cast<int*>(partial + (size_t)tsplit * n_bags * n_heads * head_dim);
-        MDL_CHECK_CUDA(cudaMemsetAsync(tickets, 0, sizeof(int) * (size_t)n_bags * n_heads * halves, st));
-    }
-    pool_weights_kernel<<<dim3(n_bags, n_heads), POOL_THREADS, 0, st>>>(logits, cu_seqlens, tok_idx, n_heads, attn_p, activation);
-    MDL_CHECK_LAUNCH();
+    int* tickets = pool_tickets(workspace, tsplit, n_bags, n_heads, head_dim);
     dim3 grid(halves * tsplit, n_heads, n_bags);
     if (nplanes == 2)
         pool_fwd_kernel<2><<<grid, POOL_THREADS, 0, st>>>((const __nv_bfloat16*)x_planes, plane_stride, attn_p, cu_seqlens, tok_idx, n_heads, head_dim, tsplit, out, partial, tickets);

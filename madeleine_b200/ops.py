@@ -241,7 +241,9 @@ def pool_fwd(h3, npl, logits, cu, tok_idx, R, total_tokens, H, E, out, attn_p, a
     ws = None
     if tsplit > 1:
         ws = torch.empty(call("mdl_pool_workspace_bytes", R, H, E, tsplit), dtype=torch.uint8, device=h3.device)
-    call("mdl_pool_fwd", h3, M * C, npl, logits, cu, tok_idx, R, total_tokens, H, E, out, attn_p, act, tsplit, ws, stream_ptr(h3.device))
+    st = stream_ptr(h3.device)
+    call("mdl_pool_weights", logits, cu, tok_idx, R, H, E, attn_p, act, tsplit, ws, st)
+    call("mdl_pool_fwd", h3, M * C, npl, attn_p, cu, tok_idx, R, total_tokens, H, E, out, tsplit, ws, st)
     return out
 
 

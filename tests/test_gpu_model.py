@@ -264,3 +264,17 @@ def test_fused_adamw_matches_torch():
         ref.step(); ours.step(); sched.step(); sched_ref.step()
     for a, b in zip(ref_p, our_p):
         torch.testing.assert_close(b, a, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("scale,offset", [(10.0, 0.0), (0.01, 0.0), (1.0, 3.0), (30.0, -5.0)])
+def test_encode_he_input_scale_robustness(scale, offset):
+    """CONCH features are un-normalised ViT outputs: parity must not depend on the input scale / mean.
+    Checked against the CPU oracle on the same weights and inputs."""
+    import oracle
+    sd = make_state_dict(0)
+    model = build(["HE"], False, 0)
+    x = make_feats(77, 2, 300, 512) * scale + offset
+    with torch.no_grad():
+        out = model.encode_he(x, DEV)
+    ref = oracle.encode_he(sd, x)
+    close(out, ref)

@@ -77,14 +77,18 @@ int mdl_ln_gelu_fwd(const float* z, long long M, int C, const float* gamma, cons
                     float drop_p, unsigned long long seed, unsigned stream_id,
                     void* planes, long long plane_stride, int nplanes, float* mean, float* rstd, void* stream);
 /* Backward of the above; dh = dh_a + dh_b + sum_v pool_p_v[m, head] * pool_dS_v[pool_seg_v[m], c] (any may be NULL).
- * Accumulates dgamma, dbeta and the preceding Linear's bias grad dbias (all [C], caller zero-fills). */
+ * dh_b_rows == NULL: dh_b is dense [M, C]; otherwise dh_b is compact [n_sel, C] and dh_b_rows[m] is token m's compact row
+ * or -1 (the token_projector gradient of the token window, Model.py:138-146 + loss.py:281-284).
+ * Accumulates dgamma, dbeta and the preceding Linear's bias grad dbias (all [C], caller zero-fills).
+ * bag_dz != NULL (C == 512, no dh_b / pooling term): also accumulates per-bag column sums of dz into bag_dz[row2bag[m], c]
+ * ([n_bags, C], caller zero-fills) — the stain-encoding backward of Model.py:126-133. */
 int mdl_ln_gelu_bwd(const float* z, long long M, int C, const float* gamma, const float* beta, const float* mean,
-                    const float* rstd, const float* dh_a, const float* dh_b,
+                    const float* rstd, const float* dh_a, const float* dh_b, const int* dh_b_rows,
                     const float* pool_p0, const float* pool_dS0, const int* pool_seg0,
                     const float* pool_p1, const float* pool_dS1, const int* pool_seg1, int n_heads,
                     float drop_p, unsigned long long seed, unsigned stream_id,
                     void* dz_planes, long long plane_stride, int nplanes,
-                    float* dgamma, float* dbeta, float* dbias, void* stream);
+                    float* dgamma, float* dbeta, float* dbias, const int* row2bag, float* bag_dz, void* stream);
 /* Backward of the gate nonlinearities of mdl_gemm_gated; dpre planes [M, n_heads*1024] in packed gate order. */
 int mdl_gate_bwd(const void* gate_a, const void* gate_b, const float* dlogit, const float* wc, long long M, int n_heads,
                  float drop_p, unsigned long long seed, void* dpre_planes, long long plane_stride, int nplanes,
@@ -122,6 +126,10 @@ int mdl_skinny_linear_bwd(const float* dY, const float* X, const float* W, int R
 /* Stain encodings (Model.py:125-132) folded into a per-bag bias: rowbias[r,:] = W1[:, d_in:] emb[code[r]]. */
 int mdl_stain_rowbias(const float* emb, const int* code, const float* w1, int ldw, int d_in, int se_dim, int n_out,
                       int R, float* rowbias, void* stream);
+/* out[p][s, :] = planes[p][rows[s], :]: the token rows that token_projector (Model.py:80-83,138-146) has to see when only
+ * a window of every bag's tokens can reach the local loss (GOT's permutation is over the batch size, loss.py:281-284). */
+int mdl_gather_rows_planes(const void* planes, long long plane_stride_in, int nplanes, int C, const int* rows,
+                           long long n_sel, void* out, long long plane_stride_out, void* stream);
 int mdl_bag_colsum_planes(const void* planes, long long plane_stride, int nplanes, int C, const int* cu_seqlens,
                           int n_bags, float* out, void* stream);
 int mdl_stain_rowbias_bwd(const float* G, const float* emb, const int* code, const float* w1, int ldw, int d_in,

@@ -42,8 +42,8 @@ SIGNATURES = {
     "mdl_gemm_nt_simt": [c_p, c_ll, c_ll, c_p, c_ll, c_ll, c_p, c_ll, c_i, c_i, c_i, c_i, c_p],
     "mdl_gemm_tn_simt": [c_p, c_ll, c_ll, c_p, c_ll, c_ll, c_ll, c_p, c_ll, c_i, c_i, c_i, c_p],
     "mdl_ln_gelu_fwd": [c_p, c_ll, c_i, c_p, c_p, c_f, c_f, c_ull, c_u, c_p, c_ll, c_i, c_p, c_p, c_p],
-    "mdl_ln_gelu_bwd": [c_p, c_ll, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_f, c_ull, c_u,
-                        c_p, c_ll, c_i, c_p, c_p, c_p, c_p],
+    "mdl_ln_gelu_bwd": [c_p, c_ll, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_f, c_ull, c_u,
+                        c_p, c_ll, c_i, c_p, c_p, c_p, c_p, c_p, c_p],
     "mdl_gate_bwd": [c_p, c_p, c_p, c_p, c_ll, c_i, c_f, c_ull, c_p, c_ll, c_i, c_p, c_p, c_p, c_p, c_p],
     "mdl_pool_tsplit": [c_i, c_ll, c_i, c_i],
     "mdl_pool_workspace_bytes": [c_i, c_i, c_i, c_i],
@@ -54,6 +54,7 @@ SIGNATURES = {
     "mdl_skinny_linear_fwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p],
     "mdl_skinny_linear_bwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p],
     "mdl_stain_rowbias": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p],
+    "mdl_gather_rows_planes": [c_p, c_ll, c_i, c_i, c_p, c_ll, c_p, c_ll, c_p],
     "mdl_bag_colsum_planes": [c_p, c_ll, c_i, c_i, c_p, c_i, c_p, c_p],
     "mdl_stain_rowbias_bwd": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p],
     "mdl_colsum_f32": [c_p, c_ll, c_i, c_p, c_p],
@@ -115,11 +116,12 @@ LAUNCHES = {
     "mdl_gemm_nt": 1, "mdl_gemm_gated": 1, "mdl_gemm_tn_accum": 1, "mdl_gemm_nt_simt": 1, "mdl_gemm_tn_simt": 1,
     "mdl_ln_gelu_fwd": 1, "mdl_ln_gelu_bwd": 1, "mdl_gate_bwd": 1, "mdl_pool_weights": 1, "mdl_pool_fwd": 1, "mdl_pool_bwd_dlogit": 1,
     "mdl_planes_to_ref_order": 1, "mdl_skinny_linear_fwd": 1, "mdl_skinny_linear_bwd": 2, "mdl_stain_rowbias": 1,
-    "mdl_bag_colsum_planes": 1, "mdl_stain_rowbias_bwd": 1, "mdl_colsum_f32": 1, "mdl_infonce_fwd": 4, "mdl_infonce_bwd": 2,
+    "mdl_bag_colsum_planes": 1, "mdl_gather_rows_planes": 1, "mdl_stain_rowbias_bwd": 1, "mdl_colsum_f32": 1, "mdl_infonce_fwd": 4, "mdl_infonce_bwd": 2,
     "mdl_got_extrema": 2, "mdl_got_fwd_bwd": 2, "mdl_got_main": 2, "mdl_got_finish": 1, "mdl_adamw_step": 1,
 }
 launch_count = [0]
 # optional per-kernel device timing: {name: [(start_event, end_event), ...]} filled when `timed_kernels` is a set of names
+# (or the string "all")
 timed_kernels = None
 kernel_events = {}
 
@@ -138,7 +140,7 @@ def call(name, *args):
     if name in _VALUE_FUNCS:
         return getattr(lib, name)(*[_conv(a) for a in args])
     launch_count[0] += LAUNCHES.get(name, 0)
-    if timed_kernels is not None and name in timed_kernels:
+    if timed_kernels is not None and (timed_kernels == "all" or name in timed_kernels):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         rc = getattr(lib, name)(*[_conv(a) for a in args])

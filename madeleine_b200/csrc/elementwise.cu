@@ -155,14 +155,20 @@ struct PoolTerm {
     const int* row2seg;    // [M]
 };
 
-template <int C, int U, bool HAS_B, int NPOOL>
+// HAS_B: 0 = no second dense gradient, 1 = dh_b is [M, C], 2 = dh_b is COMPACT [n_sel, C] and dh_b_rows[m] gives the compact
+// row of token m (or -1): the token-projector gradient exists only for the token window the local loss can read.
+// BAGSUM: additionally accumulate per-bag column sums of dz into bag_dz[row2bag[m], c] (the stain-encoding backward needs
+// them); a block owns a CONTIGUOUS run of rows, so a thread flushes its bag accumulator only when the bag id changes.
+template <int C, int U, int HAS_B, int NPOOL, bool BAGSUM>
 __global__ void __launch_bounds__(512, 2)
 ln_gelu_bwd_kernel(const float* __restrict__ z, int M, const float* __restrict__ gamma, const float* __restrict__ beta,
                    const float* __restrict__ mean, const float* __restrict__ rstd_in,
-                   const float* __restrict__ dh_a, const float* __restrict__ dh_b, PoolTerm pt0, PoolTerm pt1, int n_heads,
+                   const float* __restrict__ dh_a, const float* __restrict__ dh_b, const int* __restrict__ dh_b_rows,
+                   PoolTerm pt0, PoolTerm pt1, int n_heads,
                    float drop_p, unsigned long long seed, unsigned stream_id,
                    __nv_bfloat16* __restrict__ dz_planes, long long plane_stride, int nplanes,
-                   float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias) {
+                   float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
+                   const int* __restrict__ row2bag, float* __restrict__ bag_dz) {
     constexpr int TPR = C / 4;            // threads per row
     constexpr int SLOTS = 512 / TPR;      // row slots per block
     constexpr int WPS = TPR / 32;         // warps per slot
@@ -176,11 +182,14 @@ ln_gelu_bwd_kernel(const float* __restrict__ z, int M, const float* __restrict__
     const float gg[4] = {g.x, g.y, g.z, g.w};
     const float bb[4] = {be.x, be.y, be.z, be.w};
     float accg[4] = {0.f, 0.f, 0.f, 0.f}, accb[4] = {0.f, 0.f, 0.f, 0.f}, accz[4] = {0.f, 0.f, 0.f, 0.f};
+    float accbag[4] = {0.f, 0.f, 0.f, 0.f};
+    int cur_bag = -1;
     const bool drop = drop_p > 0.f;
     const int rows_per_iter = gridDim.x * SLOTS * U;
     const int iters = (M + rows_per_iter - 1) / rows_per_iter;
     for (int it = 0; it < iters; ++it) {
-        const int mbase = (it * gridDim.x + blockIdx.x) * (SLOTS * U) + slot * U;
+        // block b sweeps rows [b * iters * SLOTS*U, (b+1) * iters * SLOTS*U): contiguous, so it meets few bag boundaries
+        const int mbase = (blockIdx.x * iters + it) * (SLOTS * U) + slot * U;
         float xh[U][4], dy[U][4], rs[U];
         float s1[U], s2[U];
 #pragma unroll
@@ -191,9 +200,16 @@ ln_gelu_bwd_kernel(const float* __restrict__ z, int M, const float* __restrict__
             const size_t off = (size_t)mr * C + c;
             const float4 zv = __ldg(reinterpret_cast<const float4*>(z + off));
             float4 d = __ldg(reinterpret_cast<const float4*>(dh_a + off));
-            if (HAS_B) {
+            if (HAS_B == 1) {
                 const float4 t = __ldg(reinterpret_cast<const float4*>(dh_b + off));
                 d.x += t.x; d.y += t.y; d.z += t.z; d.w += t.w;
+            }
+            if (HAS_B == 2) {
+                const int sel = __ldg(dh_b_rows + mr);
+                if (sel >= 0) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(dh_b + (size_t)sel * C + c));
+                    d.x += t.x; d.y += t.y; d.z += t.z; d.w += t.w;
+                }
             }
             if (NPOOL >= 1) {
                 const float pw = __ldg(pt0.p + (size_t)mr * n_heads + head);
@@ -262,8 +278,24 @@ ln_gelu_bwd_kernel(const float* __restrict__ z, int M, const float* __restrict__
                 __nv_bfloat16* o = dz_planes + (size_t)m * C + c;
                 *reinterpret_cast<uint2*>(o) = make_uint2(h01, h23);
                 if (nplanes > 1) *reinterpret_cast<uint2*>(o + plane_stride) = make_uint2(l01, l23);
+                if (BAGSUM) {
+                    const int bag = __ldg(row2bag + m);
+                    if (bag != cur_bag) {
+                        if (cur_bag >= 0) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) { atomicAdd(bag_dz + (size_t)cur_bag * C + c + i, accbag[i]); accbag[i] = 0.f; }
+                        }
+                        cur_bag = bag;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) accbag[i] += dzv[i];
+                }
             }
         }
+    }
+    if (BAGSUM && cur_bag >= 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) atomicAdd(bag_dz + (size_t)cur_bag * C + c + i, accbag[i]);
     }
     // column sums: one atomic per column per slot per block (slots own the same columns)
 #pragma unroll
@@ -361,6 +393,22 @@ gate_bwd_kernel(const __half* __restrict__ gate_a, const __half* __restrict__ ga
         atomicAdd(dwc + j0 + i, s_w[i]);
     }
     if (threadIdx.x % 64 == 0) atomicAdd(dbc + head, s_c);
+}
+
+// out[p][s, :] = planes[p][rows[s], :]  — row gather of a bf16 planes tensor (token window of the local loss: only the
+// first few tokens of every bag go through token_projector).  One warp per selected row, 16-byte vectors.
+__global__ void __launch_bounds__(256)
+gather_rows_planes_kernel(const __nv_bfloat16* __restrict__ planes, long long plane_stride_in, int nplanes, int C,
+                          const int* __restrict__ rows, long long n_sel, __nv_bfloat16* __restrict__ out, long long plane_stride_out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int vec = C >> 3;                                   // uint4 per row
+    for (long long s = (long long)blockIdx.x * 8 + warp; s < n_sel * nplanes; s += (long long)gridDim.x * 8) {
+        const int p = (int)(s / n_sel);
+        const long long r = s - (long long)p * n_sel;
+        const uint4* src = reinterpret_cast<const uint4*>(planes + p * plane_stride_in + (long long)__ldg(rows + r) * C);
+        uint4* dst = reinterpret_cast<uint4*>(out + p * plane_stride_out + r * C);
+        for (int v = lane; v < vec; v += 32) dst[v] = __ldg(src + v);
+    }
 }
 
 // G[bag, c] = sum_{t in bag} (hi + lo)[t, c]  — per-bag column sums of a planes tensor (stain-encoding backward).
@@ -488,47 +536,59 @@ int mdl_ln_gelu_fwd(const float* z, long long M, int C, const float* gamma, cons
 }  // extern "C"
 
 template <int C>
-static void launch_ln_bwd(bool has_b, int npool, int grid, cudaStream_t st, const float* z, int M, const float* gamma, const float* beta,
-                          const float* mean, const float* rstd, const float* dh_a, const float* dh_b, PoolTerm t0, PoolTerm t1, int n_heads,
+static void launch_ln_bwd(int has_b, int npool, int grid, cudaStream_t st, const float* z, int M, const float* gamma, const float* beta,
+                          const float* mean, const float* rstd, const float* dh_a, const float* dh_b, const int* dh_b_rows,
+                          PoolTerm t0, PoolTerm t1, int n_heads,
                           float drop_p, unsigned long long seed, unsigned stream_id, __nv_bfloat16* dz, long long ps, int npl,
-                          float* dgamma, float* dbeta, float* dbias) {
-#define MDL_LN_BWD(HB, NP) ln_gelu_bwd_kernel<C, 2, HB, NP><<<grid, 512, 0, st>>>(z, M, gamma, beta, mean, rstd, dh_a, dh_b, t0, t1, n_heads, drop_p, seed, stream_id, dz, ps, npl, dgamma, dbeta, dbias)
-    if (!has_b && npool == 0) MDL_LN_BWD(false, 0);
-    else if (!has_b && npool == 1) MDL_LN_BWD(false, 1);
-    else if (!has_b) MDL_LN_BWD(false, 2);
-    else if (npool == 0) MDL_LN_BWD(true, 0);
-    else if (npool == 1) MDL_LN_BWD(true, 1);
-    else MDL_LN_BWD(true, 2);
+                          float* dgamma, float* dbeta, float* dbias, const int* row2bag, float* bag_dz) {
+#define MDL_LN_BWD(HB, NP, BS) ln_gelu_bwd_kernel<C, 2, HB, NP, BS><<<grid, 512, 0, st>>>(z, M, gamma, beta, mean, rstd, dh_a, dh_b, dh_b_rows, t0, t1, n_heads, drop_p, seed, stream_id, dz, ps, npl, dgamma, dbeta, dbias, row2bag, bag_dz)
+    if constexpr (C == 512) {
+        if (bag_dz != nullptr) { MDL_LN_BWD(0, 0, true); return; }   // only the first layer (no second gradient, no pooling term)
+    }
+    if (has_b == 0 && npool == 0) MDL_LN_BWD(0, 0, false);
+    else if (has_b == 0 && npool == 1) MDL_LN_BWD(0, 1, false);
+    else if (has_b == 0) MDL_LN_BWD(0, 2, false);
+    else if (has_b == 1 && npool == 0) MDL_LN_BWD(1, 0, false);
+    else if (has_b == 1 && npool == 1) MDL_LN_BWD(1, 1, false);
+    else if (has_b == 1) MDL_LN_BWD(1, 2, false);
+    else if (npool == 0) MDL_LN_BWD(2, 0, false);
+    else if (npool == 1) MDL_LN_BWD(2, 1, false);
+    else MDL_LN_BWD(2, 2, false);
 #undef MDL_LN_BWD
 }
 
 extern "C" {
 
 int mdl_ln_gelu_bwd(const float* z, long long M, int C, const float* gamma, const float* beta, const float* mean, const float* rstd,
-                    const float* dh_a, const float* dh_b,
+                    const float* dh_a, const float* dh_b, const int* dh_b_rows,
                     const float* pool_p0, const float* pool_dS0, const int* pool_seg0,
                     const float* pool_p1, const float* pool_dS1, const int* pool_seg1, int n_heads,
                     float drop_p, unsigned long long seed, unsigned stream_id,
                     void* dz_planes, long long plane_stride, int nplanes,
-                    float* dgamma, float* dbeta, float* dbias, void* stream) {
+                    float* dgamma, float* dbeta, float* dbias, const int* row2bag, float* bag_dz, void* stream) {
     MDL_REQUIRE(C == 512 || C == 2048, "ln_gelu_bwd: C must be 512 or 2048 (got %d)", C);
     MDL_REQUIRE(n_heads > 0 && C % n_heads == 0 && (C / n_heads) % 4 == 0, "ln_gelu_bwd: bad n_heads");
     MDL_REQUIRE(M < (1LL << 31), "ln_gelu_bwd: too many rows");
     MDL_REQUIRE(dh_a != nullptr || dh_b != nullptr, "ln_gelu_bwd: at least one dense upstream gradient is required");
     MDL_REQUIRE(pool_p0 != nullptr || pool_p1 == nullptr, "ln_gelu_bwd: pool term 1 given without pool term 0");
+    MDL_REQUIRE(dh_b_rows == nullptr || (dh_a != nullptr && dh_b != nullptr), "ln_gelu_bwd: a row-indexed dh_b needs a dense dh_a");
+    MDL_REQUIRE(bag_dz == nullptr || (row2bag != nullptr && dh_b == nullptr && pool_p0 == nullptr),
+                "ln_gelu_bwd: per-bag sums are built for the first layer only (no dh_b, no pooling term) and need row2bag");
     if (M == 0) return 0;
     if (dh_a == nullptr) { dh_a = dh_b; dh_b = nullptr; }
+    const int has_b = dh_b == nullptr ? 0 : (dh_b_rows == nullptr ? 1 : 2);
     PoolTerm t0{pool_p0, pool_dS0, pool_seg0}, t1{pool_p1, pool_dS1, pool_seg1};
     const int npool = pool_p0 == nullptr ? 0 : (pool_p1 == nullptr ? 1 : 2);
     cudaStream_t st = (cudaStream_t)stream;
     if (C == 512) {
         const int grid = grid_for(M, 4 * 2 * 4, 2);   // several iterations per block so the column atomics amortise
-        launch_ln_bwd<512>(dh_b != nullptr, npool, grid, st, z, (int)M, gamma, beta, mean, rstd, dh_a, dh_b, t0, t1, n_heads, drop_p, seed, stream_id,
-                           (__nv_bfloat16*)dz_planes, plane_stride, nplanes, dgamma, dbeta, dbias);
+        launch_ln_bwd<512>(has_b, npool, grid, st, z, (int)M, gamma, beta, mean, rstd, dh_a, dh_b, dh_b_rows, t0, t1, n_heads, drop_p, seed, stream_id,
+                           (__nv_bfloat16*)dz_planes, plane_stride, nplanes, dgamma, dbeta, dbias, row2bag, bag_dz);
     } else {
         const int grid = grid_for(M, 1 * 2 * 8, 2);
-        launch_ln_bwd<2048>(dh_b != nullptr, npool, grid, st, z, (int)M, gamma, beta, mean, rstd, dh_a, dh_b, t0, t1, n_heads, drop_p, seed, stream_id,
-                            (__nv_bfloat16*)dz_planes, plane_stride, nplanes, dgamma, dbeta, dbias);
+        MDL_REQUIRE(bag_dz == nullptr, "ln_gelu_bwd: per-bag sums are only built for C == 512");
+        launch_ln_bwd<2048>(has_b, npool, grid, st, z, (int)M, gamma, beta, mean, rstd, dh_a, dh_b, dh_b_rows, t0, t1, n_heads, drop_p, seed, stream_id,
+                            (__nv_bfloat16*)dz_planes, plane_stride, nplanes, dgamma, dbeta, dbias, nullptr, nullptr);
     }
     MDL_CHECK_LAUNCH();
     return 0;
@@ -542,6 +602,16 @@ int mdl_gate_bwd(const void* gate_a, const void* gate_b, const float* dlogit, co
     const int grid = grid_for(M, 32, 3);
     gate_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)gate_a, (const __half*)gate_b, dlogit, wc, M, n_heads, drop_p, seed,
                                                            (__nv_bfloat16*)dpre_planes, plane_stride, nplanes, dba, dbb, dwc, dbc);
+    MDL_CHECK_LAUNCH();
+    return 0;
+}
+
+int mdl_gather_rows_planes(const void* planes, long long plane_stride_in, int nplanes, int C, const int* rows, long long n_sel,
+                           void* out, long long plane_stride_out, void* stream) {
+    MDL_REQUIRE(C % 8 == 0, "gather_rows_planes: C must be a multiple of 8 (got %d)", C);
+    if (n_sel == 0) return 0;
+    gather_rows_planes_kernel<<<grid_for(n_sel * nplanes, 8, 8), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)planes, plane_stride_in, nplanes, C, rows, n_sel, (__nv_bfloat16*)out, plane_stride_out);
     MDL_CHECK_LAUNCH();
     return 0;
 }
@@ -571,7 +641,8 @@ int mdl_stain_rowbias_bwd(const float* G, const float* emb, const int* code, con
 
 int mdl_colsum_f32(const float* x, long long M, int C, float* out, void* stream) {
     if (M == 0) return 0;
-    dim3 grid((C + 127) / 128, (unsigned)((M + 63) / 64 > 64 ? 64 : (M + 63) / 64));
+    const long long want = (M + 63) / 64, cap = 4LL * kNumSMs / ((C + 127) / 128) + 1;   // ~4 blocks per SM in total
+    dim3 grid((C + 127) / 128, (unsigned)(want > cap ? cap : want));
     colsum_f32_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x, M, C, out);
     MDL_CHECK_LAUNCH();
     return 0;

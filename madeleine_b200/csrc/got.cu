@@ -21,7 +21,7 @@
 namespace mdl {
 
 constexpr int GOT_NMAX = 96;
-constexpr int GOT_THREADS = 256;
+constexpr int GOT_THREADS = 512;
 constexpr int GOT_WARPS = GOT_THREADS / 32;
 constexpr int WD_ITERS = 30;
 constexpr int GW_OUTER = 5;

@@ -9,10 +9,16 @@ own ``forward`` is never called.  There is no CPU path: tensors must be on a CUD
 Extensions over the reference API (all optional):
   * ``MADELEINE.encode_packed(feats[M, D], cu_seqlens)`` / ``forward_packed`` — variable-length, bag-packed input
     (the reference can only batch equal-length bags, SURVEY.md §0);
-  * ``config.b200_precision`` ∈ {'auto', 'fp32', 'bf16'} (default 'auto': follow torch autocast like the reference).
+  * ``config.b200_precision`` ∈ {'auto', 'fp32', 'bf16'} (default 'auto': follow torch autocast like the reference);
+  * ``config.b200_token_window`` ∈ {'off' (default), 'batch', int} or env ``MADELEINE_B200_TOKEN_WINDOW``: the training
+    forward returns token embeddings for the first W tokens of every bag only ([bs, W, 128] instead of [bs, T, 128]).
+    ``GOT(..., subsample=256)`` draws its permutation over the number of CASES and uses it to index the TOKEN axis
+    (loss.py:281-284, quirk Q3), so tokens past the batch size can never reach the loss: with W = batch size the losses
+    and gradients of ``calculate_losses`` are unchanged while token_projector and its backward touch ~3 % of the rows.
 """
 from __future__ import annotations
 
+import os
 from collections import OrderedDict
 from typing import Dict, Optional, Union
 
@@ -97,7 +103,7 @@ class ABMILEmbedder(nn.Module):
         return self._placeholders
 
     def run_kernels(self, x, cu, codes, head_params, embedding_weight, *, se_dim, want_tokens, want_projector, want_ref_feats,
-                    views=None, precision=None):
+                    views=None, precision=None, token_rows=None, token_sel_of_row=None):
         """x [M, d_in] fp32 bag-packed → dict(slide, logits, tokens?, ref_feats?). Differentiable w.r.t. parameters."""
         self._check_supported()
         require_cuda(x, "patch features")
@@ -133,7 +139,7 @@ class ABMILEmbedder(nn.Module):
         opt = ops.EncodeOptions(n_heads=self.n_heads, activation=self.attention_params["params"]["activation"],
                                 precision=precision, training=self.training, want_tokens=want_tokens,
                                 want_projector=want_projector, want_ref_feats=want_ref_feats, d_in=d_in, se_dim=se_dim,
-                                views=views, seed=seed)
+                                views=views, seed=seed, token_rows=token_rows, token_sel_of_row=token_sel_of_row)
         if opt.activation not in ops.ACT_CODES:
             raise NotImplementedError("Activation not implemented.")
         holder = {"opt": opt, "cu": cu, "codes": codes, "pw": pw, "need_grad": need_grad}
@@ -198,6 +204,7 @@ class MADELEINE(nn.Module):
         # masks out of every loss.  When the batch carries `modality_labels`, such bags are encoded from ONE token (all of
         # their tokens are identical, so slide and token embeddings are unchanged) — ~27 % less work on ACROBAT.
         self.b200_skip_missing_bags = bool(getattr(config, "b200_skip_missing_bags", True))
+        self.b200_token_window = getattr(config, "b200_token_window", None)
         if self.stain_encoding:
             self.stain_encoding_dim = 32
             self.embedding = nn.Embedding(len(self.modalities), self.stain_encoding_dim)
@@ -220,14 +227,57 @@ class MADELEINE(nn.Module):
     def _heads(self):
         return [self.token_projector.weight, self.token_projector.bias, self.projector.weight, self.projector.bias]
 
-    def _encode(self, x, cu, codes, *, want_tokens, views=None):
+    def _encode(self, x, cu, codes, *, want_tokens, views=None, token_rows=None, token_sel_of_row=None):
         se = self.stain_encoding_dim if codes is not None else 0
         return self.wsi_embedders.run_kernels(x, cu, codes, self._heads(), self.embedding.weight if se else None, se_dim=se,
                                               want_tokens=want_tokens, want_projector=True, want_ref_feats=False, views=views,
-                                              precision=self.b200_precision)
+                                              precision=self.b200_precision, token_rows=token_rows,
+                                              token_sel_of_row=token_sel_of_row)
+
+    def _token_window(self, bs, n_tokens, data):
+        """Resolved window W (0 = off → full [bs, T, 128] token embeddings, the reference's return shape)."""
+        req = data.get("b200_token_window") if isinstance(data, dict) else None
+        if req is None:
+            req = self.b200_token_window
+        if req is None:
+            req = os.environ.get("MADELEINE_B200_TOKEN_WINDOW")
+        if req is None or req is False or str(req).lower() in ("off", "0", "none", "false", ""):
+            return 0
+        if str(req).lower() in ("batch", "on", "true", "auto"):
+            world = 1
+            if torch.distributed.is_available() and torch.distributed.is_initialized():
+                world = torch.distributed.get_world_size()      # cases are sharded: the permutation spans the GLOBAL batch
+            w = bs * world
+        else:
+            w = int(req)
+            if w <= 0:
+                raise ValueError(f"b200_token_window must be 'off', 'batch' or a positive integer (got {req!r})")
+        return min(w, n_tokens)
 
     @staticmethod
-    def _compact_plan(present, n_tokens, device):
+    def _window_plan(lens, cu_host, window, device):
+        """Token rows that token_projector must see.  lens [R] CPU int64: packed length of every bag (T, or 1 for a missing
+        bag encoded from one token); cu_host [R+1].  Returns (token_rows [n_sel] int32, sel_of_row [M] int32 with -1 for
+        rows outside the window, dense_idx [R*window] int64 or None when the compact order already is [R, window])."""
+        R = lens.numel()
+        k = lens.clamp(max=window)
+        base = torch.zeros(R + 1, dtype=torch.int64)
+        base[1:] = k.cumsum(0)
+        n_sel, M = int(base[-1]), int(cu_host[-1])
+        rows_host = torch.repeat_interleave(cu_host[:-1] - base[:-1], k) + torch.arange(n_sel)
+        token_rows = rows_host.to(torch.int32).to(device, non_blocking=True)
+        sel_of_row = torch.full((M,), -1, dtype=torch.int32, device=device)
+        sel_of_row[token_rows.long()] = torch.arange(n_sel, dtype=torch.int32, device=device)
+        dense_idx = None
+        if n_sel != R * window:
+            # a bag shorter than the window is a missing bag (one token, all of its T tokens are identical): repeat its row
+            t = torch.arange(R * window) % window
+            full = torch.repeat_interleave(k == window, window)
+            dense_idx = (torch.repeat_interleave(base[:-1], window) + t * full).to(device, non_blocking=True)
+        return token_rows, sel_of_row, dense_idx
+
+    @staticmethod
+    def _compact_plan(present, n_tokens, device, want_inv=True):
         """Row maps for encoding missing (all-zero) bags from a single token.  present: CPU bool [R].
         Returns (rows [M_c] gather index into the dense [R*T] rows, cu_seqlens [R+1], inv [R*T] map back to packed rows);
         built from two [R]-sized host tensors, no device sync."""
@@ -239,10 +289,13 @@ class MADELEINE(nn.Module):
         lens_d = lens.to(device, non_blocking=True)
         starts = (torch.arange(R) * n_tokens - cu_host[:-1]).to(device, non_blocking=True)
         rows = torch.arange(m_c, device=device) + torch.repeat_interleave(starts, lens_d, output_size=m_c)
+        cu_dev = cu_host.to(torch.int32).to(device, non_blocking=True)
+        if not want_inv:
+            return rows, cu_dev, None
         t_in_bag = torch.arange(R * n_tokens, device=device) % n_tokens
         pres_rep = torch.repeat_interleave(present.to(device, non_blocking=True).long(), n_tokens, output_size=R * n_tokens)
         inv = torch.repeat_interleave(cu_host[:-1].to(device, non_blocking=True), n_tokens, output_size=R * n_tokens) + t_in_bag * pres_rep
-        return rows, cu_host.to(torch.int32).to(device, non_blocking=True), inv
+        return rows, cu_dev, inv
 
     # -- reference API --------------------------------------------------------------------------------------------------
     def encode_he(self, feats, device):
@@ -292,12 +345,32 @@ class MADELEINE(nn.Module):
             flat = all_wsi_feats.reshape(R * n_tokens, d_in)
             labels = data.get("modality_labels") if isinstance(data, dict) else None
             compact = None
+            window = self._token_window(bs, n_tokens, data) if n_views == 1 else 0
             if (self.b200_skip_missing_bags and labels is not None and n_views == 1 and n_tokens > 1
                     and tuple(labels.shape) == (bs, n_mod)):
                 present = labels.detach().to("cpu").reshape(R) != 0
                 if not bool(present.all()):
-                    compact = self._compact_plan(present, n_tokens, all_wsi_feats.device)
-            if compact is None:
+                    compact = self._compact_plan(present, n_tokens, all_wsi_feats.device, want_inv=not window)
+            if window:
+                # token window (quirk Q3): token_projector sees the first `window` tokens of every bag only
+                if compact is None:
+                    lens = torch.full((R,), n_tokens, dtype=torch.int64)
+                else:
+                    lens = torch.where(present, torch.tensor(n_tokens), torch.tensor(1))
+                cu_host = torch.zeros(R + 1, dtype=torch.int64)
+                cu_host[1:] = lens.cumsum(0)
+                token_rows, sel_of_row, dense_idx = self._window_plan(lens, cu_host, window, all_wsi_feats.device)
+                if compact is None:
+                    out = self._encode(flat, cu, codes, want_tokens=True, token_rows=token_rows, token_sel_of_row=sel_of_row)
+                else:
+                    rows, cu_c, _ = compact
+                    out = self._encode(flat.index_select(0, rows), cu_c, codes, want_tokens=True, token_rows=token_rows,
+                                       token_sel_of_row=sel_of_row)
+                out = dict(out)
+                if dense_idx is not None:
+                    out["tokens"] = out["tokens"].index_select(0, dense_idx)
+                n_tokens = window
+            elif compact is None:
                 out = self._encode(flat, cu, codes, want_tokens=True, views=views)
             else:
                 rows, cu_c, inv = compact

@@ -256,12 +256,15 @@ def ln_gelu_fwd(z, gamma, beta, nplanes, drop_p, seed, stream_id):
     return planes, mean, rstd
 
 
-def ln_gelu_bwd(z, gamma, beta, mean, rstd, dh_a, dh_b, pool_terms, n_heads, nplanes, drop_p, seed, stream_id, dgamma, dbeta, dbias):
+def ln_gelu_bwd(z, gamma, beta, mean, rstd, dh_a, dh_b, pool_terms, n_heads, nplanes, drop_p, seed, stream_id, dgamma, dbeta, dbias,
+                dh_b_rows=None, row2bag=None, bag_dz=None):
+    """dh_b_rows: dh_b is compact [n_sel, C] and dh_b_rows [M] int32 maps token → compact row (-1: none).
+    bag_dz [n_bags, C] (zero-filled) + row2bag: also accumulate per-bag column sums of dz (first layer only)."""
     M, C = z.shape
     dz = _planes_empty(nplanes, M, C, z.device)
     t = list(pool_terms) + [(None, None, None)] * (2 - len(pool_terms))
-    call("mdl_ln_gelu_bwd", z, M, C, gamma, beta, mean, rstd, dh_a, dh_b, t[0][0], t[0][1], t[0][2], t[1][0], t[1][1], t[1][2],
-         n_heads, drop_p, seed, stream_id, dz, M * C, nplanes, dgamma, dbeta, dbias, stream_ptr(z.device))
+    call("mdl_ln_gelu_bwd", z, M, C, gamma, beta, mean, rstd, dh_a, dh_b, dh_b_rows, t[0][0], t[0][1], t[0][2], t[1][0], t[1][1], t[1][2],
+         n_heads, drop_p, seed, stream_id, dz, M * C, nplanes, dgamma, dbeta, dbias, row2bag, bag_dz, stream_ptr(z.device))
     return dz
 
 
@@ -281,6 +284,10 @@ class EncodeOptions:
     se_dim: int = 0
     views: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None  # n_views=3: (tok_idx, cu2, row2seg2)
     seed: int = 0
+    # token window: token_projector only sees the packed rows `token_rows` [n_sel] (unique, int32); `token_sel_of_row` [M]
+    # maps a packed row to its position in that list or -1.  tokens are then returned compact, [n_sel, 128].
+    token_rows: Optional[torch.Tensor] = None
+    token_sel_of_row: Optional[torch.Tensor] = None
 
 
 def _nsplit(precision):
@@ -360,8 +367,15 @@ def encoder_forward(x: torch.Tensor, cu: torch.Tensor, codes: Optional[torch.Ten
     else:
         # reference layout [*, E, H] (c = e*H + h) from head-major [*, H, E]
         outs["slide"] = slide_hm.view(-1, H, HID).transpose(1, 2).contiguous()
+    h3_sel = None
     if opt.want_tokens:
-        outs["tokens"] = gemm_nt(h3, C, pw.planes("tp"), TOK, nsplit, bias=pw.vec("btp"))
+        if opt.token_rows is not None:
+            n_sel = opt.token_rows.numel()
+            h3_sel = _planes_empty(npl, n_sel, C, dev)
+            call("mdl_gather_rows_planes", h3, M * C, npl, C, opt.token_rows, n_sel, h3_sel, n_sel * C, st)
+            outs["tokens"] = gemm_nt(h3_sel, C, pw.planes("tp"), TOK, nsplit, bias=pw.vec("btp"))
+        else:
+            outs["tokens"] = gemm_nt(h3, C, pw.planes("tp"), TOK, nsplit, bias=pw.vec("btp"))
     if opt.want_ref_feats:
         ref = torch.empty(M, HID, H, dtype=torch.float32, device=dev)
         call("mdl_planes_to_ref_order", h3, M * C, npl, M, H, HID, ref, st)
@@ -372,6 +386,7 @@ def encoder_forward(x: torch.Tensor, cu: torch.Tensor, codes: Optional[torch.Ten
         sv.z3, sv.mean3, sv.rstd3, sv.h3 = z3, mean3, rstd3, h3
         sv.logits, sv.gate_a, sv.gate_b, sv.attn_p, sv.pooled, sv.slide_hm = logits, gate_a, gate_b, attn_p, pooled, slide_hm
         sv.p_pre, sv.p_gate = p_pre, p_gate
+        sv.h3_sel = h3_sel
     return outs, sv
 
 
@@ -433,20 +448,27 @@ def encoder_backward(sv, d_slide: Optional[torch.Tensor], d_logits: Optional[tor
 
     # ---- token projector backward ----
     dh3_tok = None
+    dh3_tok_rows = None
     if d_tokens is not None:
-        d_tokens = d_tokens.reshape(M, TOK).contiguous().float()
+        tok_src = sv.h3 if sv.h3_sel is None else sv.h3_sel           # the rows token_projector saw in forward
+        n_tok = tok_src.shape[1]
+        d_tokens = d_tokens.reshape(n_tok, TOK).contiguous().float()
         dtp = split_planes(d_tokens, npl)
-        dh3_tok = gemm_nt(dtp, TOK, pw.planes("tpT"), C, nsplit)
-        gemm_tn_accum(dtp, sv.h3, g("tp"), nsplit)
-        call("mdl_colsum_f32", d_tokens, M, TOK, g("btp"), st)
+        dh3_tok = gemm_nt(dtp, TOK, pw.planes("tpT"), C, nsplit)      # [n_tok, C]; compact when a token window is active
+        gemm_tn_accum(dtp, tok_src, g("tp"), nsplit)
+        call("mdl_colsum_f32", d_tokens, n_tok, TOK, g("btp"), st)
+        if sv.h3_sel is not None:
+            dh3_tok_rows = opt.token_sel_of_row
     if d_ref_feats is not None:
         # gradient w.r.t. the reference-order features → head-major, added as a second dh source
         extra = d_ref_feats.float().reshape(M, HID, H).transpose(1, 2).contiguous().view(M, C)
+        if dh3_tok_rows is not None:
+            raise RuntimeError("madeleine_b200: a token window cannot be combined with gradients through the pre-attention features")
         dh3_tok = extra if dh3_tok is None else dh3_tok.add_(extra)
 
     # ---- layer 3 → 2 → 1 ----
     dz3 = ln_gelu_bwd(sv.z3, pw.vec("g3"), pw.vec("be3"), sv.mean3, sv.rstd3, dh3_attn, dh3_tok, pool_terms, H, npl,
-                      sv.p_pre, opt.seed, 3, g("g3"), g("be3"), g("b3"))
+                      sv.p_pre, opt.seed, 3, g("g3"), g("be3"), g("b3"), dh_b_rows=dh3_tok_rows)
     del dh3_attn, dh3_tok
     dh2 = gemm_nt(dz3, C, pw.planes("w3T"), HID, nsplit)
     gemm_tn_accum(dz3, sv.h2, g("w3"), nsplit)
@@ -455,8 +477,9 @@ def encoder_backward(sv, d_slide: Optional[torch.Tensor], d_logits: Optional[tor
                       g("g2"), g("be2"), g("b2"))
     dh1 = gemm_nt(dz2, HID, pw.planes("w2T"), HID, nsplit)
     gemm_tn_accum(dz2, sv.h1, g("w2"), nsplit)
+    G = torch.zeros(R, HID, dtype=torch.float32, device=dev) if opt.se_dim > 0 else None   # per-bag column sums of dz1
     dz1 = ln_gelu_bwd(sv.z1, pw.vec("g1"), pw.vec("be1"), sv.mean1, sv.rstd1, dh1, None, [], 1, npl, sv.p_pre, opt.seed, 1,
-                      g("g1"), g("be1"), g("b1"))
+                      g("g1"), g("be1"), g("b1"), row2bag=sv.row2bag if G is not None else None, bag_dz=G)
     gemm_tn_accum(dz1, sv.xp, g("w1"), nsplit)
 
     gmaster = torch.zeros(spec.master_numel, dtype=torch.float32, device=dev)
@@ -465,8 +488,6 @@ def encoder_backward(sv, d_slide: Optional[torch.Tensor], d_logits: Optional[tor
     call("mdl_gather_f32", gp, spec.gr_pos, spec.gr_pos.numel(), compact, st)
     call("mdl_scatter_f32", compact, spec.gr_dst, spec.gr_dst.numel(), gmaster, 0, st)
     if opt.se_dim > 0:
-        G = torch.empty(R, HID, dtype=torch.float32, device=dev)
-        call("mdl_bag_colsum_planes", dz1, M * HID, npl, HID, sv.cu, R, G, st)
         w1 = pw.master[spec.off("pre0.w"):]
         emb = pw.master[spec.off("emb.w"):]
         call("mdl_stain_rowbias_bwd", G, emb, sv.codes, w1, spec.d_in_total, opt.d_in, opt.se_dim, HID, R,

@@ -66,7 +66,12 @@ def GOT(v_, q_, subsample=None, _slot=-1):
     Quirk Q3 is reproduced: the permutation is drawn over the *batch* size with torch's global CPU generator and
     indexes the token axis, so n = min(m, subsample) of the first m tokens are used."""
     if subsample is not None:
-        patch_indices = torch.randperm(v_.shape[0])[:subsample].to(v_.device)
+        patch_indices = torch.randperm(v_.shape[0])[:subsample]
+        if patch_indices.numel() and int(patch_indices.max()) >= v_.shape[1]:
+            # same failure as the reference (index out of range), but with the reason: e.g. a token window smaller than the batch
+            raise IndexError(f"GOT indexes the token axis with a permutation of the {v_.shape[0]} cases (loss.py:281-284) but only "
+                             f"{v_.shape[1]} tokens per bag are available (b200_token_window must be >= the batch size)")
+        patch_indices = patch_indices.to(v_.device)
         v_ = v_[:, patch_indices, :]
         q_ = q_[:, patch_indices, :]
     # _slot >= 0 (used by calculate_losses): run on a side stream; the caller joins with ops.got_join before using the value

@@ -99,6 +99,67 @@ def test_ln_gelu_bwd(C, H):
     torch.testing.assert_close(dbias, z.grad.sum(0), rtol=1e-3, atol=1e-3 * float(z.grad.sum(0).abs().max()) + 1e-4)
 
 
+def test_ln_gelu_bwd_row_indexed_second_gradient():
+    """dh_b given compactly for a subset of rows (token window) == dense dh_b that is zero elsewhere."""
+    M, C, H, R = 2500, 2048, 4, 5
+    z = torch.randn(M, C, device=DEV) * 2
+    g = 1 + 0.1 * torch.randn(C, device=DEV)
+    b = 0.1 * torch.randn(C, device=DEV)
+    dh_a = torch.randn(M, C, device=DEV)
+    rows = torch.randperm(M, device=DEV)[:300].sort().values.to(torch.int32)
+    dh_sel = torch.randn(rows.numel(), C, device=DEV)
+    dense = torch.zeros(M, C, device=DEV)
+    dense[rows.long()] = dh_sel
+    sel_of_row = torch.full((M,), -1, dtype=torch.int32, device=DEV)
+    sel_of_row[rows.long()] = torch.arange(rows.numel(), dtype=torch.int32, device=DEV)
+    p = torch.rand(M, H, device=DEV)
+    dS = torch.randn(R, C, device=DEV)
+    seg = torch.randint(0, R, (M,), device=DEV, dtype=torch.int32)
+    _, mean, rstd = ops.ln_gelu_fwd(z, g, b, 2, 0.0, 0, 1)
+    res = []
+    for kw, dh_b in (({"dh_b_rows": sel_of_row}, dh_sel), ({}, dense)):
+        acc = [torch.zeros(C, device=DEV) for _ in range(3)]
+        dz = ops.ln_gelu_bwd(z, g, b, mean, rstd, dh_a, dh_b, [(p, dS, seg)], H, 2, 0.1, 99, 3, *acc, **kw)
+        res.append((planes_f32(dz), acc))
+    assert torch.equal(res[0][0], res[1][0])
+    for a0, a1 in zip(res[0][1], res[1][1]):
+        torch.testing.assert_close(a0, a1, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("lens", [[3, 10, 1, 20, 5, 8, 2], [2048, 1, 1, 2048, 700, 1], [5000]])
+def test_ln_gelu_bwd_per_bag_sums(lens):
+    """Per-bag column sums of dz accumulated inside the first layer's backward (stain-encoding gradient)."""
+    R = len(lens)
+    cu, M = _ragged(lens)
+    C = 512
+    z = torch.randn(M, C, device=DEV) * 2
+    g = 1 + 0.1 * torch.randn(C, device=DEV)
+    b = 0.1 * torch.randn(C, device=DEV)
+    dh = torch.randn(M, C, device=DEV)
+    _, mean, rstd = ops.ln_gelu_fwd(z, g, b, 2, 0.0, 0, 1)
+    row2bag = torch.empty(M, dtype=torch.int32, device=DEV)
+    call("mdl_row2bag", cu, R, row2bag, M, _st())
+    acc = [torch.zeros(C, device=DEV) for _ in range(3)]
+    G = torch.zeros(R, C, device=DEV)
+    dz = planes_f32(ops.ln_gelu_bwd(z, g, b, mean, rstd, dh, None, [], 1, 2, 0.0, 0, 1, *acc, row2bag=row2bag, bag_dz=G))
+    acc2 = [torch.zeros(C, device=DEV) for _ in range(3)]
+    dz2 = planes_f32(ops.ln_gelu_bwd(z, g, b, mean, rstd, dh, None, [], 1, 2, 0.0, 0, 1, *acc2))
+    assert torch.equal(dz, dz2)
+    ref = torch.stack([dz[int(cu[i]):int(cu[i + 1])].sum(0) for i in range(R)])
+    torch.testing.assert_close(G, ref, rtol=1e-4, atol=1e-4 * float(ref.abs().max()) + 1e-5)
+    torch.testing.assert_close(acc[2], G.sum(0), rtol=1e-4, atol=1e-3)
+
+
+def test_gather_rows_planes():
+    M, C = 777, 2048
+    x = torch.randn(M, C, device=DEV)
+    xp = ops.split_planes(x, 2)
+    rows = torch.tensor([0, 5, 5, 776, 13, 400], dtype=torch.int32, device=DEV)
+    out = torch.empty(2, rows.numel(), C, dtype=torch.bfloat16, device=DEV)
+    call("mdl_gather_rows_planes", xp, M * C, 2, C, rows, rows.numel(), out, rows.numel() * C, _st())
+    assert torch.equal(out, xp[:, rows.long()])
+
+
 def test_ln_gelu_dropout_consistency():
     """Dropout masks are regenerated in backward from (seed, stream, index): kept fraction ~ 1-p and fwd/bwd agree."""
     M, C, p = 256, 512, 0.1

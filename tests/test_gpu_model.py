@@ -246,6 +246,57 @@ def test_skip_missing_bags_matches_full_encoding(golden):
         assert float((g1[n] - g0[n]).norm()) / denom < 2e-2 or denom < 1e-4, n
 
 
+@pytest.mark.parametrize("with_labels", [True, False])
+def test_token_window_matches_full_tokens(golden, with_labels):
+    """GOT's permutation runs over the number of cases, so with b200_token_window='batch' (token
+    embeddings of the first `bs` tokens of every bag only) calculate_losses returns the reference's loss and the same
+    parameter gradients as with all T token embeddings; the windowed tokens equal the leading slice of the full ones."""
+    g = golden("losses_grads")["global_local_se"]
+    mods = g["modalities"]
+    x = make_feats(g["seed_x"], *g["shape"]) * g["labels"][:, :, None, None]
+    bs, T = g["shape"][0], g["shape"][2]
+    args = Namespace(global_loss="info-nce", symmetric_cl=True, local_loss_weight=1.0)
+    outs = []
+    for window in ("batch", "off"):
+        c = cfg(mods)
+        c.b200_token_window = window
+        model = MADELEINE(c, stain_encoding=True)
+        model.load_state_dict(make_state_dict(g["seed_w"], n_mod=len(mods), stain_encoding=True))
+        model.to(DEV).eval()
+        data = {"feats": x, "modality_labels": g["labels"]} if with_labels else {"feats": x}
+        embs, toks = model(data, DEV, train=True, n_views=1)
+        torch.manual_seed(g["torch_seed"])
+        loss, _ = calculate_losses(mods[1:], InfoNCE(temperature=0.001), GOT, None, embs, toks, g["labels"][:, 1:], args)
+        loss.backward()
+        outs.append((embs, toks, loss.detach(), {n: p.grad.clone() for n, p in model.named_parameters()}))
+    (e1, t1, l1, g1), (e0, t0, l0, g0) = outs
+    W = min(bs, T)
+    for m in mods:
+        assert t1[m].shape[:2] == (bs, W) and t0[m].shape[:2] == (bs, T)
+        torch.testing.assert_close(e1[m], e0[m], rtol=1e-6, atol=1e-7)
+        torch.testing.assert_close(t1[m], t0[m][:, :W], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(l1, l0, rtol=1e-5, atol=1e-5)
+    close(l1, g["loss"], rtol=1e-3, atol=1e-3)
+    for n in g1:
+        denom = float(g0[n].norm()) + 1e-12
+        assert float((g1[n] - g0[n]).norm()) / denom < 2e-2 or denom < 1e-4, n
+
+
+def test_token_window_too_small_raises(golden):
+    g = golden("losses_grads")["global_local_se"]
+    mods = g["modalities"]
+    c = cfg(mods)
+    c.b200_token_window = 1
+    model = MADELEINE(c, stain_encoding=True).to(DEV).eval()
+    x = make_feats(g["seed_x"], *g["shape"])
+    embs, toks = model({"feats": x}, DEV, train=True, n_views=1)
+    assert toks[mods[1]].shape[1] == 1
+    with pytest.raises(IndexError, match="b200_token_window"):
+        torch.manual_seed(0)
+        for _ in range(8):           # any permutation of >= 2 cases contains an index >= 1
+            GOT(toks["HE"][:, :, :, 0], toks[mods[1]], subsample=256)
+
+
 def test_fused_adamw_matches_torch():
     from madeleine_b200.optim import FusedAdamW
     torch.manual_seed(0)

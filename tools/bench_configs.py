@@ -25,15 +25,15 @@ from madeleine_b200.utils.inference import extract_slide_embeddings  # noqa: E40
 from weights import make_state_dict  # noqa: E402
 
 
-def cfg(mods, precision):
+def cfg(mods, precision, token_window="off"):
     return Namespace(MODALITIES=mods, wsi_encoder="abmil", patch_embedding_dim=512, wsi_encoder_hidden_dim=512,
-                     activation="softmax", n_heads=4, b200_precision=precision)
+                     activation="softmax", n_heads=4, b200_precision=precision, b200_token_window=token_window)
 
 
-def config3(precision, steps, warmup, skip=True, bs=32, tag="BASELINE configs[2]: batch=32"):
+def config3(precision, steps, warmup, skip=True, bs=32, tag="BASELINE configs[2]: batch=32", breakdown=False, token_window="off"):
     dev = torch.device("cuda")
     mods = ["HE", "HER2", "PGR", "KI67", "ER"]
-    model = MADELEINE(cfg(mods, precision), stain_encoding=True)
+    model = MADELEINE(cfg(mods, precision, token_window), stain_encoding=True)
     model.load_state_dict(make_state_dict(3, n_mod=5, stain_encoding=True))
     model.to(dev).train()
     T = 2048
@@ -56,7 +56,7 @@ def config3(precision, steps, warmup, skip=True, bs=32, tag="BASELINE configs[2]
         step()
     torch.cuda.synchronize()
     _lib.kernel_events.clear()
-    _lib.timed_kernels = {"mdl_got_fwd_bwd", "mdl_got_extrema", "mdl_infonce_fwd", "mdl_infonce_bwd"}
+    _lib.timed_kernels = "all" if breakdown else {"mdl_got_fwd_bwd", "mdl_got_extrema", "mdl_infonce_fwd", "mdl_infonce_bwd"}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
@@ -65,10 +65,10 @@ def config3(precision, steps, warmup, skip=True, bs=32, tag="BASELINE configs[2]
     torch.cuda.synchronize()
     _lib.timed_kernels = None
     ms = e0.elapsed_time(e1) / steps
-    kt = {k: sum(a.elapsed_time(b) for a, b in v) / steps for k, v in _lib.kernel_events.items()}
+    kt = {k: round(sum(a.elapsed_time(b) for a, b in v) / steps, 4) for k, v in _lib.kernel_events.items()}
     bags = bs * 5
     print(json.dumps({"config": tag + ", 5 stains, T=2048, stain encodings, InfoNCE + GOT, fwd+bwd, train mode",
-                      "missing_bags_encoded_from_one_token": skip, "missing_bag_fraction": float(1 - labels.mean()),
+                      "missing_bags_encoded_from_one_token": skip, "token_window": token_window, "missing_bag_fraction": float(1 - labels.mean()),
                       "precision": precision, "ms_per_step": ms, "slides_per_s": bags / (ms * 1e-3), "cases_per_s": bs / (ms * 1e-3),
                       "loss": float(loss), "cases_per_stain": labels[:, 1:].sum(0).tolist(), "loss_kernel_ms_per_step": kt,
                       "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}))
@@ -114,12 +114,15 @@ if __name__ == "__main__":
     ap.add_argument("--precision", default="fp32")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--slides", type=int, default=500)
+    ap.add_argument("--token-window", default="off", help="'off' | 'batch' | int (config.b200_token_window)")
+    ap.add_argument("--breakdown", action="store_true", help="time every C-ABI entry point (events around each call)")
     a = ap.parse_args()
     if "3" in a.which:
-        config3(a.precision, a.steps, 2, skip=True)
-        config3(a.precision, a.steps, 2, skip=False)
+        config3(a.precision, a.steps, 2, skip=True, token_window=a.token_window, breakdown=a.breakdown)
+        config3(a.precision, a.steps, 2, skip=False, token_window=a.token_window)
     if "canon" in a.which:
         # the reference's shipped pre-training configuration (scripts/launch_pretrain_withStainEncodings.sh): batch 65
-        config3(a.precision, a.steps, 2, skip=True, bs=65, tag="reference canonical config: batch=65")
+        config3(a.precision, a.steps, 2, skip=True, bs=65, tag="reference canonical config: batch=65", breakdown=a.breakdown,
+                token_window=a.token_window)
     if "5" in a.which:
         config5(a.precision, a.slides, 4000)

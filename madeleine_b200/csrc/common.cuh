@@ -107,33 +107,41 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uin
 __device__ __forceinline__ float bf16_lo_of(uint32_t packed) { return __uint_as_float(packed << 16); }
 __device__ __forceinline__ float bf16_hi_of(uint32_t packed) { return __uint_as_float(packed & 0xffff0000u); }
 
+// Raw SFU instructions (one MUFU each).  __fdividef / exp2f / __expf wrap the same instructions in denormal-range guards
+// (FSETP + two predicated FMUL + FSEL per call) that the arguments here never need: denominators are >= 1, and an
+// exponential that underflows should flush to zero.
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 // GELU(x) = x Phi(x) and its derivative Phi(x) + x phi(x) from ONE exponential: erfc(|x|/sqrt2) by Abramowitz-Stegun
 // 7.1.26 (|abs err| <= 1.5e-7, far inside the 1e-4 parity budget) uses exp(-x^2/2), which is also the Gaussian pdf.
-//   w = poly(t) * exp(-x^2/2) = erfc(|x|/sqrt2),  t = 1 / (1 + p |x| / sqrt2)
-//   gelu(x) = x - x w / 2 (x >= 0),  x w / 2 (x < 0);   Phi(x) = 1 - w/2 (x >= 0),  w/2 (x < 0)
-__device__ __forceinline__ float erfc_core(float x, float& e) {
-    const float up = fabsf(x) * 0.84932180028801907f;           // |x| / sqrt2 * sqrt(log2 e)  -> exp2(-up^2) = exp(-x^2/2)
-    const float t = __fdividef(1.f, fmaf(0.27273617448364717f, up, 1.f));   // 0.3275911 / sqrt(log2 e)
-    e = exp2f(-up * up);
-    const float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
-    return poly * e;
-}
+//   u = |x| sqrt(log2 e) / sqrt2  (so that exp2(-u^2) = exp(-x^2/2)),  t = 1 / (1 + p |x| / sqrt2),  e = exp2(-u^2)
+//   erfc(|x|/sqrt2) = poly(t) e
+//   gelu(x) = max(x, 0) - (|x|/2) erfc(|x|/sqrt2) = max(x, 0) - u (poly_g(t) e),   poly_g = poly / (2 sqrt(log2 e)/sqrt2)
+//   Phi(x)  = 1/2 + copysign(1/2 - erfc/2, x)
+// Branch-free: 13 instructions (2 MUFU) for the value, 15 for the derivative.
+#define MDL_GELU_K 0.84932180028801907f               /* sqrt(log2 e) / sqrt2 */
+#define MDL_GELU_P 0.27273617448364717f               /* 0.3275911 / sqrt(log2 e): p |x| / sqrt2 = MDL_GELU_P * u */
 __device__ __forceinline__ float gelu_erf(float x) {
-    float e;
-    const float h = 0.5f * x * erfc_core(x, e);
-    return x >= 0.f ? x - h : h;
+    const float u = fabsf(x) * MDL_GELU_K;
+    const float t = rcp_approx(fmaf(MDL_GELU_P, u, 1.f));
+    const float e = ex2_approx(-u * u);
+    // A-S coefficients times 1 / (2 K)
+    const float poly = t * (0.1500194578f + t * (-0.1674846542f + t * (0.8367933924f + t * (-0.8554778804f + t * 0.624854695f))));
+    return fmaf(-u, poly * e, fmaxf(x, 0.f));
 }
-__device__ __forceinline__ void gelu_and_grad(float x, float& g, float& dg) {
-    float e;
-    const float hw = 0.5f * erfc_core(x, e);
-    const float h = x * hw;
-    const bool pos = x >= 0.f;
-    g = pos ? x - h : h;
-    dg = fmaf(x * e, 0.39894228040143268f, pos ? 1.f - hw : hw);
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+    const float u = fabsf(x) * MDL_GELU_K;
+    const float t = rcp_approx(fmaf(MDL_GELU_P, u, 1.f));
+    const float e = ex2_approx(-u * u);
+    // A-S coefficients times 1/2: hw = erfc(|x|/sqrt2) / 2
+    const float hw = (t * (0.127414796f + t * (-0.142248368f + t * (0.7107068705f + t * (-0.7265760135f + t * 0.5307027145f))))) * e;
+    const float phi_cdf = 0.5f + copysignf(0.5f - hw, x);
+    return fmaf(x * e, 0.39894228040143268f, phi_cdf);
 }
-__device__ __forceinline__ float gelu_erf_grad(float x) { float g, dg; gelu_and_grad(x, g, dg); return dg; }
+__device__ __forceinline__ void gelu_and_grad(float x, float& g, float& dg) { g = gelu_erf(x); dg = gelu_erf_grad(x); }
 // sigmoid / tanh from one ex2 + one rcp each; abs error ~1e-7, saturate correctly at +-inf.
-__device__ __forceinline__ float sigmoid_acc(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float sigmoid_acc(float x) { return rcp_approx(1.f + ex2_approx(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float tanh_acc(float x) { return fmaf(2.f, sigmoid_acc(2.f * x), -1.f); }
 
 // Stateless counter-based RNG for dropout masks: the same (seed, stream, index) gives the same bit in fwd and bwd.
@@ -153,13 +161,31 @@ __device__ __forceinline__ uint64_t hash_u64(uint64_t seed, uint32_t stream, uin
     return ((uint64_t)c0 << 32) | c1;
 }
 // multiplicative masks for elements 4*idx4 .. 4*idx4+3: 0 (dropped) or 1/(1-p) (kept); p == 0 -> all 1.
-__device__ __forceinline__ void dropout_scale4(float p, uint64_t seed, uint32_t stream, uint64_t idx4, float (&m)[4]) {
-    if (p <= 0.f) { m[0] = m[1] = m[2] = m[3] = 1.f; return; }
-    const uint32_t thresh = (uint32_t)(p * 65536.f);
-    const float keep = __fdividef(1.f, 1.f - p);
+// Element i is kept when the i-th 16-bit field of the hash is >= p * 65536.  The fields are compared in place: a field in
+// the top half of a 32-bit word compares as (word >= thresh << 16), one in the bottom half after a 16-bit left shift.
+struct DropCfg {
+    uint32_t thresh_hi;      // (uint32_t)(p * 65536) << 16
+    float keep;              // 1 / (1 - p)
+    bool on;
+};
+__device__ __forceinline__ DropCfg make_drop_cfg(float p) {
+    DropCfg c;
+    c.on = p > 0.f;
+    c.thresh_hi = ((uint32_t)(p * 65536.f)) << 16;
+    c.keep = c.on ? __fdividef(1.f, 1.f - p) : 1.f;
+    return c;
+}
+__device__ __forceinline__ void dropout_scale4(const DropCfg& c, uint64_t seed, uint32_t stream, uint64_t idx4, float (&m)[4]) {
+    if (!c.on) { m[0] = m[1] = m[2] = m[3] = 1.f; return; }
     const uint64_t h = hash_u64(seed, stream, idx4);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) m[i] = ((uint32_t)(h >> (16 * i)) & 0xffffu) >= thresh ? keep : 0.f;
+    const uint32_t lo = (uint32_t)h, hi = (uint32_t)(h >> 32);
+    m[0] = (lo << 16) >= c.thresh_hi ? c.keep : 0.f;
+    m[1] = lo >= c.thresh_hi ? c.keep : 0.f;
+    m[2] = (hi << 16) >= c.thresh_hi ? c.keep : 0.f;
+    m[3] = hi >= c.thresh_hi ? c.keep : 0.f;
+}
+__device__ __forceinline__ void dropout_scale4(float p, uint64_t seed, uint32_t stream, uint64_t idx4, float (&m)[4]) {
+    dropout_scale4(make_drop_cfg(p), seed, stream, idx4, m);
 }
 
 // ---------------------------------------------------------------------------------------------------

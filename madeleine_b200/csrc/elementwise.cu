@@ -82,7 +82,8 @@ ln_gelu_fwd_kernel(const float* __restrict__ z, int M, const float* __restrict__
     constexpr int V = C / 128;            // float4 per lane per row
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int warps_total = gridDim.x * 8;
-    const bool drop = drop_p > 0.f;
+    const DropCfg dcfg = make_drop_cfg(drop_p);
+    const bool drop = dcfg.on;
     for (int m0 = (blockIdx.x * 8 + warp) * RPW; m0 < M; m0 += warps_total * RPW) {
         float4 v[RPW][V];
 #pragma unroll
@@ -122,7 +123,7 @@ ln_gelu_fwd_kernel(const float* __restrict__ z, int M, const float* __restrict__
                 float y3 = gelu_erf(fmaf(fmaf(v[r][j].w, rstd, nmr), g.w, be.w));
                 if (drop) {
                     float msk[4];
-                    dropout_scale4(drop_p, seed, stream_id, (row_off + j * 128) >> 2, msk);
+                    dropout_scale4(dcfg, seed, stream_id, (row_off + j * 128) >> 2, msk);
                     y0 *= msk[0]; y1 *= msk[1]; y2 *= msk[2]; y3 *= msk[3];
                 }
                 uint32_t h01, l01, h23, l23;
@@ -184,7 +185,8 @@ ln_gelu_bwd_kernel(const float* __restrict__ z, int M, const float* __restrict__
     float accg[4] = {0.f, 0.f, 0.f, 0.f}, accb[4] = {0.f, 0.f, 0.f, 0.f}, accz[4] = {0.f, 0.f, 0.f, 0.f};
     float accbag[4] = {0.f, 0.f, 0.f, 0.f};
     int cur_bag = -1;
-    const bool drop = drop_p > 0.f;
+    const DropCfg dcfg = make_drop_cfg(drop_p);
+    const bool drop = dcfg.on;
     const int rows_per_iter = gridDim.x * SLOTS * U;
     const int iters = (M + rows_per_iter - 1) / rows_per_iter;
     for (int it = 0; it < iters; ++it) {
@@ -225,7 +227,7 @@ ln_gelu_bwd_kernel(const float* __restrict__ z, int M, const float* __restrict__
             const float nmr = -__ldg(mean + mr) * r_;
             rs[u] = r_;
             float msk[4] = {1.f, 1.f, 1.f, 1.f};
-            if (drop) dropout_scale4(drop_p, seed, stream_id, off >> 2, msk);
+            if (drop) dropout_scale4(dcfg, seed, stream_id, off >> 2, msk);
             const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
             const float dd[4] = {d.x, d.y, d.z, d.w};
             const float okf = ok ? 1.f : 0.f;
@@ -326,6 +328,7 @@ gate_bwd_kernel(const __half* __restrict__ gate_a, const __half* __restrict__ ga
     for (int i = 0; i < 8; ++i) { w[i] = __ldg(wc + j0 + i); s_a[i] = 0.f; s_b[i] = 0.f; s_w[i] = 0.f; }
     float s_c = 0.f;
     const float keep_inv = drop_p > 0.f ? (1.f - drop_p) : 1.f;
+    const DropCfg dcfg = make_drop_cfg(drop_p);
     constexpr int R = 2;
     for (long long m0 = (long long)blockIdx.x * R; m0 < M; m0 += (long long)gridDim.x * R) {
         uint4 ua[R], ub[R];
@@ -347,10 +350,10 @@ gate_bwd_kernel(const __half* __restrict__ gate_a, const __half* __restrict__ ga
             {
                 float t[4];
                 const uint64_t idx4 = ((uint64_t)m * (uint64_t)HC + (uint64_t)j0) >> 2;
-                dropout_scale4(drop_p, seed, 10u, idx4, t); sa[0] = t[0]; sa[1] = t[1]; sa[2] = t[2]; sa[3] = t[3];
-                dropout_scale4(drop_p, seed, 10u, idx4 + 1, t); sa[4] = t[0]; sa[5] = t[1]; sa[6] = t[2]; sa[7] = t[3];
-                dropout_scale4(drop_p, seed, 11u, idx4, t); sb[0] = t[0]; sb[1] = t[1]; sb[2] = t[2]; sb[3] = t[3];
-                dropout_scale4(drop_p, seed, 11u, idx4 + 1, t); sb[4] = t[0]; sb[5] = t[1]; sb[6] = t[2]; sb[7] = t[3];
+                dropout_scale4(dcfg, seed, 10u, idx4, t); sa[0] = t[0]; sa[1] = t[1]; sa[2] = t[2]; sa[3] = t[3];
+                dropout_scale4(dcfg, seed, 10u, idx4 + 1, t); sa[4] = t[0]; sa[5] = t[1]; sa[6] = t[2]; sa[7] = t[3];
+                dropout_scale4(dcfg, seed, 11u, idx4, t); sb[0] = t[0]; sb[1] = t[1]; sb[2] = t[2]; sb[3] = t[3];
+                dropout_scale4(dcfg, seed, 11u, idx4 + 1, t); sb[4] = t[0]; sb[5] = t[1]; sb[6] = t[2]; sb[7] = t[3];
             }
             float dpa[8], dpb[8];
 #pragma unroll
@@ -361,9 +364,9 @@ gate_bwd_kernel(const __half* __restrict__ gate_a, const __half* __restrict__ ga
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                     const int i = 2 * i2 + k;
-                    const float ad = adv[k], bd = bdv[k];               // dropout-scaled gates
-                    const float a = ad * (sa[i] != 0.f ? keep_inv : 0.f);  // undo the 1/(1-p) scaling where kept
-                    const float b = bd * (sb[i] != 0.f ? keep_inv : 0.f);
+                    const float ad = adv[k], bd = bdv[k];               // dropout-scaled gates (0 where dropped)
+                    const float a = ad * keep_inv;                      // undo the 1/(1-p) scaling; dropped gates stay 0 and
+                    const float b = bd * keep_inv;                      // their gradients are zeroed by sa / sb below
                     const float dA = dl[r] * w[i];
                     dpa[i] = dA * bd * sa[i] * (1.f - a * a);
                     dpb[i] = dA * ad * sb[i] * b * (1.f - b);

@@ -118,6 +118,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, float* aux, uin
         const int head = n_group;          // one work unit = (m_tile, head); inner = 128-wide gate group
         const int j_base = head * 512 + inner * 128;
         const int HC = p.n_heads * 512;
+        const DropCfg dcfg = make_drop_cfg(p.drop_p);
 #pragma unroll 1
         for (int cc = 0; cc < 2; ++cc) {
             const int c = half * 2 + cc;
@@ -136,8 +137,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, float* aux, uin
                 const float fwc[4] = {vwc.x, vwc.y, vwc.z, vwc.w};
                 float ma[4], mb[4];
                 const uint64_t idx4 = ((uint64_t)m * (uint64_t)HC + (uint64_t)(j0 + 4 * i4)) >> 2;
-                dropout_scale4(p.drop_p, p.seed, 10u, idx4, ma);
-                dropout_scale4(p.drop_p, p.seed, 11u, idx4, mb);
+                dropout_scale4(dcfg, p.seed, 10u, idx4, ma);
+                dropout_scale4(dcfg, p.seed, 11u, idx4, mb);
                 float av[4], bv[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {

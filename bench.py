@@ -262,7 +262,13 @@ def main():
     B = CASES_PER_GPU
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     feats_dev = torch.randn(B, N_STAINS, N_TOKENS, D_IN, generator=g, device=dev)          # 131 MB > 126 MB L2
-    feats_host = [torch.randn(B, N_STAINS, N_TOKENS, D_IN).pin_memory() for _ in range(2)]  # e2e: pinned host buffers
+    from madeleine_b200.utils import hostmem
+    hostmem.bind_to_gpu(local_rank)     # pinned pages on the GPU's NUMA node (no-op on single-node hosts)
+    feats_host = []                     # e2e: pinned host buffers
+    for _ in range(2):
+        buf = hostmem.pinned_empty((B, N_STAINS, N_TOKENS, D_IN))
+        buf.normal_()
+        feats_host.append(buf)
     labels = torch.ones(B, N_STAINS)
     labels_dev = labels.to(dev)
     labels_global = torch.ones(B * world, N_STAINS)      # the loader knows the whole batch's availability mask (case list)
@@ -333,7 +339,7 @@ def main():
 
         def run_e2e(n_steps):
             batches = ({"feats": feats_host[i % 2]} for i in range(n_steps))
-            LAG = 2                                    # the host reads the loss of step i-2 while step i is being queued
+            LAG = 4                                    # the host reads the loss of step i-4 while step i is being queued
             host_loss = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(LAG + 1)]
             events = [torch.cuda.Event() for _ in range(LAG + 1)]
             seen = []
@@ -361,11 +367,25 @@ def main():
                 dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             return float(ms) / n_steps
 
-        run_e2e(3)
+        run_e2e(5)
         ms_e2e = run_e2e(args.steps)
+        # what the link alone gives on this box (the e2e number is bounded by it on hosts with slow pinned copies)
+        scratch = torch.empty_like(feats_dev)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        c0.record()
+        for _ in range(4):
+            scratch.copy_(feats_host[0], non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        h2d_gbs = 4 * feats_host[0].numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        del scratch
         e2e = {"value": bags_per_step / (ms_e2e * 1e-3), "unit": "slides/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": feats_host[0].numel() * 4, "d2h_bytes_per_step": 4,
-               "note": "pinned host features staged one batch ahead on a copy stream; every step's loss is read back, two steps deferred"}
+               "h2d_gbs_alone": h2d_gbs,
+               "note": "pinned host features staged one batch ahead on a copy stream; every step's loss is read back inside the "
+                       "timed region, four steps deferred so the host stays ahead of the device (tools/e2e_probe.py); "
+                       "h2d_gbs_alone = this box's pinned H2D rate for one batch with the GPU otherwise idle"}
 
     if rank != 0:
         if world > 1:

@@ -263,12 +263,14 @@ def main():
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     feats_dev = torch.randn(B, N_STAINS, N_TOKENS, D_IN, generator=g, device=dev)          # 131 MB > 126 MB L2
     from madeleine_b200.utils import hostmem
-    hostmem.bind_to_gpu(local_rank)     # pinned pages on the GPU's NUMA node (no-op on single-node hosts)
+    saved_affinity = os.sched_getaffinity(0)
+    hostmem.bind_to_gpu(local_rank)     # first-touch the pinned pages from the GPU's NUMA node (no-op on single-node hosts)
     feats_host = []                     # e2e: pinned host buffers
     for _ in range(2):
         buf = hostmem.pinned_empty((B, N_STAINS, N_TOKENS, D_IN))
         buf.normal_()
         feats_host.append(buf)
+    os.sched_setaffinity(0, saved_affinity)
     labels = torch.ones(B, N_STAINS)
     labels_dev = labels.to(dev)
     labels_global = torch.ones(B * world, N_STAINS)      # the loader knows the whole batch's availability mask (case list)

@@ -152,6 +152,9 @@ int mdl_infonce_bwd(const float* q, const float* k, int m, int D, float temperat
  * use_external_extrema != 0 the thresholds use these instead of the local batch extrema (quirk Q5 under sharding). */
 long long mdl_got_workspace_bytes(int m, int n, int D);
 int mdl_got_max_tokens(void);
+/* Test hook: send problems of any size to the global-memory kernels used for 96 < n <= 256 (got_big.cu), so that both
+ * implementations can be compared on the same inputs.  Also settable with MDL_GOT_FORCE_BIG=1. */
+int mdl_got_force_big(int on);
 int mdl_got_extrema(const float* v, const float* q, int m, int n, int D, void* workspace, float* extrema, void* stream);
 int mdl_got_fwd_bwd(const float* v, const float* q, int m, int n, int D, void* workspace, const float* extrema,
                     float* loss, float* wd, float* gwd, float* dv, float* dq, void* stream);

@@ -64,6 +64,7 @@ SIGNATURES = {
     "mdl_adamw_step": [c_i, c_p, c_p, c_p, c_p, c_p, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_p],
     "mdl_got_workspace_bytes": [c_i, c_i, c_i],
     "mdl_got_max_tokens": [],
+    "mdl_got_force_big": [c_i],
     "mdl_got_extrema": [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p],
     "mdl_got_fwd_bwd": [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "mdl_got_main": [c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p],

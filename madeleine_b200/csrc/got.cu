@@ -15,48 +15,11 @@
 // One CTA per (case, stain) problem; n <= 96 tokens, all n x n work in shared memory (5 matrices + vectors),
 // GW-level state (Cg_k, gamma_k, lu/lw per outer iteration, gradient accumulators) in a per-problem global workspace.
 // Three launches: costs + extrema, main forward/backward, gradient w.r.t. the token embeddings.
-#include "common.cuh"
+#include "got_common.cuh"
 #include "madeleine_b200.h"
+#include <stdlib.h>
 
 namespace mdl {
-
-constexpr int GOT_NMAX = 96;
-constexpr int GOT_THREADS = 512;
-constexpr int GOT_WARPS = GOT_THREADS / 32;
-constexpr int WD_ITERS = 30;
-constexpr int GW_OUTER = 5;
-constexpr int GW_INNER = 20;
-constexpr float WD_BETA = 0.5f;
-constexpr float GW_BETA = 0.1f;
-constexpr float THR_BETA = 0.1f;
-constexpr int MAX_ITERS = WD_ITERS;  // lu/lw capacity (>= GW_INNER)
-
-struct GotLayout {
-    int m, n, D;
-    size_t nn;
-    // float offsets inside one problem's slab
-    size_t raw0, raws, rawt;          // raw costs
-    size_t g0, gs, gt;                // gradient accumulators (w.r.t. thresholded costs, then raw costs)
-    size_t cg;                        // 6 x nn
-    size_t gamma;                     // 5 x nn (gamma_1..gamma_5)
-    size_t lulw;                      // GW_OUTER x 2 x (GW_INNER+1) x n
-    size_t ext;                       // 6 floats extrema + 6 ints argidx + 3 floats dthr + pad
-    size_t per_item;
-    size_t header;                    // global header floats (6 extrema + 12 ints)
-    __host__ __device__ GotLayout(int m_, int n_, int D_) : m(m_), n(n_), D(D_) {
-        nn = (size_t)n * n;
-        size_t o = 0;
-        raw0 = o; o += nn; raws = o; o += nn; rawt = o; o += nn;
-        g0 = o; o += nn; gs = o; o += nn; gt = o; o += nn;
-        cg = o; o += 6 * nn;
-        gamma = o; o += 5 * nn;
-        lulw = o; o += (size_t)GW_OUTER * 2 * (GW_INNER + 1) * n;
-        ext = o; o += 16;
-        per_item = (o + 31) / 32 * 32;
-        header = 32;
-    }
-    __host__ __device__ size_t total_floats() const { return header + per_item * (size_t)m; }
-};
 
 // ---------------------------------------------------------------------------------------------------
 // shared-memory helpers (n x n matrices with odd leading dimension ld)
@@ -601,6 +564,17 @@ __global__ void got_dthr_kernel(GotLayout lay, const float* __restrict__ ws, flo
     dthr_out[k] = s;
 }
 
+int got_launch_extrema(const GotLayout& lay, float* ws, float* extrema, cudaStream_t st) {
+    got_extrema_kernel<<<1, 32, 0, st>>>(lay, ws, extrema);
+    MDL_CHECK_LAUNCH();
+    return 0;
+}
+int got_launch_dthr(const GotLayout& lay, const float* ws, float* dthr_out, cudaStream_t st) {
+    got_dthr_kernel<<<1, 32, 0, st>>>(lay, ws, dthr_out);
+    MDL_CHECK_LAUNCH();
+    return 0;
+}
+
 static size_t main_smem_bytes(int n) {
     const int ld = n | 1;
     return sizeof(float) * ((size_t)5 * n * ld + (size_t)13 * n + (size_t)2 * (MAX_ITERS + 1) * n);
@@ -610,21 +584,35 @@ static size_t main_smem_bytes(int n) {
 
 using namespace mdl;
 
+// Problems above GOT_NMAX tokens go to the global-memory kernels; MDL_GOT_FORCE_BIG=1 (or mdl_got_force_big) sends every
+// problem there so the two implementations can be compared on the same inputs.
+static int g_force_big = -1;
+static bool got_use_big(int n) {
+    if (g_force_big < 0) {
+        const char* e = getenv("MDL_GOT_FORCE_BIG");
+        g_force_big = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return n > GOT_NMAX || g_force_big == 1;
+}
+
 extern "C" {
 
-int mdl_got_max_tokens(void) { return GOT_NMAX; }
+int mdl_got_force_big(int on) { g_force_big = on ? 1 : 0; return 0; }
+
+int mdl_got_max_tokens(void) { return GOT_BIG_NMAX; }
 
 long long mdl_got_workspace_bytes(int m, int n, int D) {
     if (m <= 0 || n <= 0) return 0;
-    GotLayout lay(m, n, D);
+    GotLayout lay(m, n, D, got_use_big(n));
     return (long long)(lay.total_floats() * sizeof(float));
 }
 
 int mdl_got_extrema(const float* v, const float* q, int m, int n, int D, void* workspace, float* extrema, void* stream) {
-    MDL_REQUIRE(m > 0 && n > 0 && n <= GOT_NMAX, "GOT: n must be in [1, %d] (got %d)", GOT_NMAX, n);
+    MDL_REQUIRE(m > 0 && n > 0 && n <= GOT_BIG_NMAX, "GOT: n must be in [1, %d] (got %d)", GOT_BIG_NMAX, n);
     MDL_REQUIRE(D > 0 && D <= 128, "GOT: token dim must be <= 128 (got %d)", D);
     cudaStream_t st = (cudaStream_t)stream;
-    GotLayout lay(m, n, D);
+    if (got_use_big(n)) return got_big_extrema(v, q, m, n, D, workspace, extrema, st);
+    GotLayout lay(m, n, D, got_use_big(n));
     const size_t smem = sizeof(float) * (size_t)2 * n * (D + 1);
     static bool attr = false;
     if (!attr) {
@@ -633,9 +621,7 @@ int mdl_got_extrema(const float* v, const float* q, int m, int n, int D, void* w
     }
     got_cost_kernel<<<m, GOT_THREADS, smem, st>>>(v, q, lay, (float*)workspace);
     MDL_CHECK_LAUNCH();
-    got_extrema_kernel<<<1, 32, 0, st>>>(lay, (float*)workspace, extrema);
-    MDL_CHECK_LAUNCH();
-    return 0;
+    return got_launch_extrema(lay, (float*)workspace, extrema, st);
 }
 
 static int got_set_attrs() {
@@ -649,9 +635,10 @@ static int got_set_attrs() {
 }
 
 int mdl_got_main(int m, int n, int D, void* workspace, const float* extrema, float* wd, float* gwd, float* dthr_local, void* stream) {
-    MDL_REQUIRE(m > 0 && n > 0 && n <= GOT_NMAX, "GOT: n must be in [1, %d] (got %d)", GOT_NMAX, n);
+    MDL_REQUIRE(m > 0 && n > 0 && n <= GOT_BIG_NMAX, "GOT: n must be in [1, %d] (got %d)", GOT_BIG_NMAX, n);
     cudaStream_t st = (cudaStream_t)stream;
-    GotLayout lay(m, n, D);
+    if (got_use_big(n)) return got_big_main(m, n, D, workspace, extrema, wd, gwd, dthr_local, st);
+    GotLayout lay(m, n, D, got_use_big(n));
     if (int rc = got_set_attrs()) return rc;
     got_main_kernel<<<m, GOT_THREADS, main_smem_bytes(n), st>>>(lay, (float*)workspace, extrema, wd, gwd);
     MDL_CHECK_LAUNCH();
@@ -664,10 +651,11 @@ int mdl_got_main(int m, int n, int D, void* workspace, const float* extrema, flo
 
 int mdl_got_finish(const float* v, const float* q, int m, int n, int D, void* workspace, const float* extrema, const float* dthr_global,
                    const float* wd, const float* gwd, float* loss, float* dv, float* dq, void* stream) {
-    MDL_REQUIRE(m > 0 && n > 0 && n <= GOT_NMAX, "GOT: n must be in [1, %d] (got %d)", GOT_NMAX, n);
+    MDL_REQUIRE(m > 0 && n > 0 && n <= GOT_BIG_NMAX, "GOT: n must be in [1, %d] (got %d)", GOT_BIG_NMAX, n);
     MDL_REQUIRE(D > 0 && D <= 128, "GOT: token dim must be <= 128 (got %d)", D);
     cudaStream_t st = (cudaStream_t)stream;
-    GotLayout lay(m, n, D);
+    if (got_use_big(n)) return got_big_finish(v, q, m, n, D, workspace, extrema, dthr_global, wd, gwd, loss, dv, dq, st);
+    GotLayout lay(m, n, D, got_use_big(n));
     if (int rc = got_set_attrs()) return rc;
     const size_t smem = sizeof(float) * ((size_t)2 * n * (D + 1) + 2 * n);
     got_grad_kernel<<<m, GOT_THREADS, smem, st>>>(v, q, lay, (float*)workspace, extrema, dthr_global, wd, gwd, loss, dv, dq);

@@ -108,6 +108,28 @@ def config5(precision, n_slides, n_tokens):
                       "embedding_checksum": float(abs(emb).sum())}))
 
 
+def got_sizes():
+    """Graph-OT loss alone (forward + token gradients) for a range of problem counts / sizes, incl. the n > 96 path."""
+    from madeleine_b200 import ops
+    dev = torch.device("cuda")
+    for m, n in ((53, 53), (65, 65), (96, 96), (128, 128), (192, 192), (256, 256)):
+        g = torch.Generator().manual_seed(n)
+        v = torch.randn(m, n, 128, generator=g).to(dev)
+        q = (v + 0.5 * torch.randn(m, n, 128, device=dev))
+        for _ in range(2):
+            ops.got_loss(v, q)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            loss = ops.got_loss(v, q)
+        e1.record()
+        torch.cuda.synchronize()
+        print(json.dumps({"config": "GOT alone (one stain): m problems of n tokens, forward + gradients w.r.t. the tokens",
+                          "m": m, "n": n, "ms": round(e0.elapsed_time(e1) / 3, 3), "loss": float(loss),
+                          "kernels": "got.cu (shared memory)" if n <= 96 else "got_big.cu (global memory)"}))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--which", default="3,5")
@@ -124,5 +146,7 @@ if __name__ == "__main__":
         # the reference's shipped pre-training configuration (scripts/launch_pretrain_withStainEncodings.sh): batch 65
         config3(a.precision, a.steps, 2, skip=True, bs=65, tag="reference canonical config: batch=65", breakdown=a.breakdown,
                 token_window=a.token_window)
+    if "got" in a.which:
+        got_sizes()
     if "5" in a.which:
         config5(a.precision, a.slides, 4000)

@@ -85,6 +85,17 @@ ln_gelu_fwd_kernel(const float* __restrict__ z, int M, const float* __restrict__
     const DropCfg dcfg = make_drop_cfg(drop_p);
     const bool drop = dcfg.on;
     for (int m0 = (blockIdx.x * 8 + warp) * RPW; m0 < M; m0 += warps_total * RPW) {
+        {   // next rows of this warp -> L2 (16 warps per SM do not cover the HBM round trip on their own)
+            const int mp = m0 + warps_total * RPW;
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) {
+                if (mp + r < M) {
+                    const float* zp = z + (size_t)(mp + r) * C + lane * 4;
+#pragma unroll
+                    for (int j = 0; j < V; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(zp + j * 128));
+                }
+            }
+        }
         float4 v[RPW][V];
 #pragma unroll
         for (int r = 0; r < RPW; ++r) {
@@ -145,9 +156,12 @@ ln_gelu_fwd_kernel(const float* __restrict__ z, int M, const float* __restrict__
 // Writes dz as bf16 planes (operand of the following dgrad / wgrad GEMMs) and accumulates the column sums
 // dgamma += dy*xhat, dbeta += dy, dbias += dz.
 //
-// "Column-owner" layout: a thread owns 4 fixed columns for the whole kernel (gamma/beta and the 12 column-sum
-// accumulators live in registers); C/4 threads form a row slot, 512/(C/4) slots per block, U rows per slot per iteration.
-// The two per-row means need one cross-warp exchange per iteration (double-buffered smem, one __syncthreads).
+// Layout: a warp owns a 512-column slab of a row — lane l holds 16 FIXED columns (float4 at slab + 128 j + 4 l, j < 4)
+// for the whole kernel, so the 48 column-sum accumulators live in registers and every per-row cost (the two shuffle
+// reductions, mean / rstd / attention-weight loads, address arithmetic) is spread over 16 elements per thread.  C = 512:
+// one warp per row, no shared memory and no barrier in the row loop.  C = 2048: the four warps of a row exchange their two
+// partial sums through shared memory behind a 128-thread named barrier (double-buffered, one barrier per row).
+// A block sweeps a CONTIGUOUS run of rows (few bag boundaries per thread for the per-bag sums).
 // Optional inputs are template flags so the inner loop carries no pointer tests.
 // ---------------------------------------------------------------------------------------------------
 struct PoolTerm {
@@ -159,9 +173,9 @@ struct PoolTerm {
 // HAS_B: 0 = no second dense gradient, 1 = dh_b is [M, C], 2 = dh_b is COMPACT [n_sel, C] and dh_b_rows[m] gives the compact
 // row of token m (or -1): the token-projector gradient exists only for the token window the local loss can read.
 // BAGSUM: additionally accumulate per-bag column sums of dz into bag_dz[row2bag[m], c] (the stain-encoding backward needs
-// them); a block owns a CONTIGUOUS run of rows, so a thread flushes its bag accumulator only when the bag id changes.
-template <int C, int U, int HAS_B, int NPOOL, bool BAGSUM>
-__global__ void __launch_bounds__(512, 2)
+// them); a thread flushes its bag accumulator only when the bag id changes.
+template <int C, int HAS_B, int NPOOL, bool BAGSUM>
+__global__ void __launch_bounds__(256, 2)
 ln_gelu_bwd_kernel(const float* __restrict__ z, int M, const float* __restrict__ gamma, const float* __restrict__ beta,
                    const float* __restrict__ mean, const float* __restrict__ rstd_in,
                    const float* __restrict__ dh_a, const float* __restrict__ dh_b, const int* __restrict__ dh_b_rows,
@@ -170,141 +184,190 @@ ln_gelu_bwd_kernel(const float* __restrict__ z, int M, const float* __restrict__
                    __nv_bfloat16* __restrict__ dz_planes, long long plane_stride, int nplanes,
                    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
                    const int* __restrict__ row2bag, float* __restrict__ bag_dz) {
-    constexpr int TPR = C / 4;            // threads per row
-    constexpr int SLOTS = 512 / TPR;      // row slots per block
-    constexpr int WPS = TPR / 32;         // warps per slot
-    __shared__ float red[2][SLOTS][2 * U][WPS];
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int slot = tid / TPR, tin = tid % TPR, wslot = tin >> 5;
-    const int c = tin * 4;
-    const int head = c / (C / n_heads);
-    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
-    const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
-    const float gg[4] = {g.x, g.y, g.z, g.w};
-    const float bb[4] = {be.x, be.y, be.z, be.w};
-    float accg[4] = {0.f, 0.f, 0.f, 0.f}, accb[4] = {0.f, 0.f, 0.f, 0.f}, accz[4] = {0.f, 0.f, 0.f, 0.f};
-    float accbag[4] = {0.f, 0.f, 0.f, 0.f};
+    constexpr int WPR = C / 512;          // warps per row
+    constexpr int GROUPS = 8 / WPR;       // rows in flight per block
+    __shared__ float red[2][GROUPS][2][WPR];
+    __shared__ float colacc[3 * C];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = warp / WPR, wq = warp % WPR;
+    const int c0 = wq * 512 + lane * 4;                       // this lane's columns: c0 + 128 j + i
+    const int cols_per_head = C / n_heads;
+    for (int i = tid; i < 3 * C; i += 256) colacc[i] = 0.f;
+    float accg[16], accb[16], accz[16], accbag[BAGSUM ? 16 : 1];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { accg[i] = 0.f; accb[i] = 0.f; accz[i] = 0.f; }
+    if (BAGSUM) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) accbag[BAGSUM ? i : 0] = 0.f;
+    }
     int cur_bag = -1;
     const DropCfg dcfg = make_drop_cfg(drop_p);
-    const bool drop = dcfg.on;
-    const int rows_per_iter = gridDim.x * SLOTS * U;
-    const int iters = (M + rows_per_iter - 1) / rows_per_iter;
+    const int rows_per_block = (M + gridDim.x - 1) / gridDim.x;
+    const int row_begin = blockIdx.x * rows_per_block;
+    const int row_end = min(M, row_begin + rows_per_block);
+    const int iters = (rows_per_block + GROUPS - 1) / GROUPS;
     for (int it = 0; it < iters; ++it) {
-        // block b sweeps rows [b * iters * SLOTS*U, (b+1) * iters * SLOTS*U): contiguous, so it meets few bag boundaries
-        const int mbase = (blockIdx.x * iters + it) * (SLOTS * U) + slot * U;
-        float xh[U][4], dy[U][4], rs[U];
-        float s1[U], s2[U];
+        const int m = row_begin + it * GROUPS + grp;
+        const bool ok = m < row_end;
+        const int mr = ok ? m : 0;                             // clamp; contributions of padded rows are zeroed below
+        const size_t row_off = (size_t)mr * C + c0;
+        {   // pull the rows this warp will need two iterations from now into L2 (the kernel is latency-bound otherwise:
+            // 128 registers per thread leave 16 warps per SM to cover the HBM round trip)
+            const int mp = m + 2 * GROUPS;
+            if (mp < row_end) {
+                const size_t po = (size_t)mp * C + c0;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int m = mbase + u;
-            const bool ok = m < M;
-            const int mr = ok ? m : 0;                                  // clamp; contributions of padded rows are zeroed below
-            const size_t off = (size_t)mr * C + c;
-            const float4 zv = __ldg(reinterpret_cast<const float4*>(z + off));
-            float4 d = __ldg(reinterpret_cast<const float4*>(dh_a + off));
+                for (int j = 0; j < 4; ++j) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(z + po + 128 * j));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(dh_a + po + 128 * j));
+                    if (HAS_B == 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(dh_b + po + 128 * j));
+                }
+            }
+        }
+        float x[16], dx[16];                                    // xhat, then dy*gamma
+        {
+            float4 zv[4], dv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                zv[j] = __ldg(reinterpret_cast<const float4*>(z + row_off + 128 * j));
+                dv[j] = __ldg(reinterpret_cast<const float4*>(dh_a + row_off + 128 * j));
+            }
             if (HAS_B == 1) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(dh_b + off));
-                d.x += t.x; d.y += t.y; d.z += t.z; d.w += t.w;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(dh_b + row_off + 128 * j));
+                    dv[j].x += t.x; dv[j].y += t.y; dv[j].z += t.z; dv[j].w += t.w;
+                }
             }
             if (HAS_B == 2) {
                 const int sel = __ldg(dh_b_rows + mr);
                 if (sel >= 0) {
-                    const float4 t = __ldg(reinterpret_cast<const float4*>(dh_b + (size_t)sel * C + c));
-                    d.x += t.x; d.y += t.y; d.z += t.z; d.w += t.w;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(dh_b + (size_t)sel * C + c0 + 128 * j));
+                        dv[j].x += t.x; dv[j].y += t.y; dv[j].z += t.z; dv[j].w += t.w;
+                    }
                 }
             }
             if (NPOOL >= 1) {
-                const float pw = __ldg(pt0.p + (size_t)mr * n_heads + head);
-                const float4 t = __ldg(reinterpret_cast<const float4*>(pt0.dS + (size_t)__ldg(pt0.row2seg + mr) * C + c));
-                d.x = fmaf(pw, t.x, d.x); d.y = fmaf(pw, t.y, d.y); d.z = fmaf(pw, t.z, d.z); d.w = fmaf(pw, t.w, d.w);
+                const float* dS = pt0.dS + (size_t)__ldg(pt0.row2seg + mr) * C + c0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float pw = __ldg(pt0.p + (size_t)mr * n_heads + (c0 + 128 * j) / cols_per_head);
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(dS + 128 * j));
+                    dv[j].x = fmaf(pw, t.x, dv[j].x); dv[j].y = fmaf(pw, t.y, dv[j].y);
+                    dv[j].z = fmaf(pw, t.z, dv[j].z); dv[j].w = fmaf(pw, t.w, dv[j].w);
+                }
             }
             if (NPOOL >= 2) {
-                const float pw = __ldg(pt1.p + (size_t)mr * n_heads + head);
-                const float4 t = __ldg(reinterpret_cast<const float4*>(pt1.dS + (size_t)__ldg(pt1.row2seg + mr) * C + c));
-                d.x = fmaf(pw, t.x, d.x); d.y = fmaf(pw, t.y, d.y); d.z = fmaf(pw, t.z, d.z); d.w = fmaf(pw, t.w, d.w);
+                const float* dS = pt1.dS + (size_t)__ldg(pt1.row2seg + mr) * C + c0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float pw = __ldg(pt1.p + (size_t)mr * n_heads + (c0 + 128 * j) / cols_per_head);
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(dS + 128 * j));
+                    dv[j].x = fmaf(pw, t.x, dv[j].x); dv[j].y = fmaf(pw, t.y, dv[j].y);
+                    dv[j].z = fmaf(pw, t.z, dv[j].z); dv[j].w = fmaf(pw, t.w, dv[j].w);
+                }
             }
             const float r_ = ok ? __ldg(rstd_in + mr) : 0.f;
             const float nmr = -__ldg(mean + mr) * r_;
-            rs[u] = r_;
-            float msk[4] = {1.f, 1.f, 1.f, 1.f};
-            if (drop) dropout_scale4(dcfg, seed, stream_id, off >> 2, msk);
-            const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
-            const float dd[4] = {d.x, d.y, d.z, d.w};
             const float okf = ok ? 1.f : 0.f;
-            s1[u] = 0.f; s2[u] = 0.f;
+            float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float x = fmaf(zz[i], r_, nmr);
-                const float t = dd[i] * (msk[i] * okf) * gelu_erf_grad(fmaf(x, gg[i], bb[i]));
-                xh[u][i] = x; dy[u][i] = t;
-                const float dx = t * gg[i];
-                s1[u] += dx;
-                s2[u] = fmaf(dx, x, s2[u]);
-                accg[i] = fmaf(t, x, accg[i]);
-                accb[i] += t;
+            for (int j = 0; j < 4; ++j) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 128 * j));
+                const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c0 + 128 * j));
+                float msk[4] = {okf, okf, okf, okf};
+                if (dcfg.on) {
+                    dropout_scale4(dcfg, seed, stream_id, (row_off + 128 * j) >> 2, msk);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) msk[i] *= okf;
+                }
+                const float zz[4] = {zv[j].x, zv[j].y, zv[j].z, zv[j].w};
+                const float dd[4] = {dv[j].x, dv[j].y, dv[j].z, dv[j].w};
+                const float gg[4] = {g.x, g.y, g.z, g.w};
+                const float bb[4] = {be.x, be.y, be.z, be.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int k = 4 * j + i;
+                    const float xh = fmaf(zz[i], r_, nmr);
+                    const float t = dd[i] * msk[i] * gelu_erf_grad(fmaf(xh, gg[i], bb[i]));
+                    const float dxg = t * gg[i];
+                    x[k] = xh; dx[k] = dxg;
+                    s1 += dxg;
+                    s2 = fmaf(dxg, xh, s2);
+                    accg[k] = fmaf(t, xh, accg[k]);
+                    accb[k] += t;
+                }
+            }
+            s1 = warp_sum(s1);
+            s2 = warp_sum(s2);
+            if (WPR > 1) {
+                const int buf = it & 1;
+                if (lane == 0) { red[buf][grp][0][wq] = s1; red[buf][grp][1][wq] = s2; }
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(WPR * 32) : "memory");
+                s1 = 0.f; s2 = 0.f;
+#pragma unroll
+                for (int w = 0; w < WPR; ++w) { s1 += red[buf][grp][0][w]; s2 += red[buf][grp][1][w]; }
+            }
+            const float m1 = s1 * (1.f / C), m2 = s2 * (1.f / C);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                dx[k] = r_ * (dx[k] - m1 - x[k] * m2);             // dz; r_ = 0 for rows past the end
+                accz[k] += dx[k];
             }
         }
-        // row sums across the slot's WPS warps
+        if (ok) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) { s1[u] = warp_sum(s1[u]); s2[u] = warp_sum(s2[u]); }
-        const int buf = it & 1;
-        if (lane == 0) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) { red[buf][slot][2 * u][wslot] = s1[u]; red[buf][slot][2 * u + 1][wslot] = s2[u]; }
-        }
-        __syncthreads();
-        // lane l fetches the partials of warp (l % WPS) and a WPS-wide xor-shuffle tree adds them: 2U LDS + a few SHFL per
-        // thread instead of WPS * 2U broadcast loads, and a fixed summation order (deterministic).
-        float tot[2 * U];
-#pragma unroll
-        for (int k = 0; k < 2 * U; ++k) {
-            float t = red[buf][slot][k][lane % WPS];
-#pragma unroll
-            for (int o = WPS / 2; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-            tot[k] = t;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const float m1 = tot[2 * u] * (1.f / C), m2 = tot[2 * u + 1] * (1.f / C);
-            const int m = mbase + u;
-            float dzv[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                dzv[i] = rs[u] * (fmaf(dy[u][i], gg[i], -m1) - xh[u][i] * m2);   // rs = 0 for rows past M
-                accz[i] += dzv[i];
-            }
-            if (m < M) {
+            for (int j = 0; j < 4; ++j) {
                 uint32_t h01, l01, h23, l23;
-                split_bf16x2(dzv[0], dzv[1], h01, l01);
-                split_bf16x2(dzv[2], dzv[3], h23, l23);
-                __nv_bfloat16* o = dz_planes + (size_t)m * C + c;
+                split_bf16x2(dx[4 * j], dx[4 * j + 1], h01, l01);
+                split_bf16x2(dx[4 * j + 2], dx[4 * j + 3], h23, l23);
+                __nv_bfloat16* o = dz_planes + row_off + 128 * j;
                 *reinterpret_cast<uint2*>(o) = make_uint2(h01, h23);
                 if (nplanes > 1) *reinterpret_cast<uint2*>(o + plane_stride) = make_uint2(l01, l23);
-                if (BAGSUM) {
-                    const int bag = __ldg(row2bag + m);
-                    if (bag != cur_bag) {
-                        if (cur_bag >= 0) {
+            }
+            if (BAGSUM) {
+                const int bag = __ldg(row2bag + m);
+                if (bag != cur_bag) {
+                    if (cur_bag >= 0) {
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) { atomicAdd(bag_dz + (size_t)cur_bag * C + c + i, accbag[i]); accbag[i] = 0.f; }
-                        }
-                        cur_bag = bag;
+                        for (int j = 0; j < 4; ++j)
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                atomicAdd(bag_dz + (size_t)cur_bag * C + c0 + 128 * j + i, accbag[BAGSUM ? 4 * j + i : 0]);
+                                accbag[BAGSUM ? 4 * j + i : 0] = 0.f;
+                            }
                     }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) accbag[i] += dzv[i];
+                    cur_bag = bag;
                 }
+#pragma unroll
+                for (int k = 0; k < 16; ++k) accbag[BAGSUM ? k : 0] += dx[k];
             }
         }
     }
     if (BAGSUM && cur_bag >= 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) atomicAdd(bag_dz + (size_t)cur_bag * C + c + i, accbag[i]);
-    }
-    // column sums: one atomic per column per slot per block (slots own the same columns)
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        atomicAdd(dgamma + c + i, accg[i]);
-        atomicAdd(dbeta + c + i, accb[i]);
-        atomicAdd(dbias + c + i, accz[i]);
+            for (int i = 0; i < 4; ++i) atomicAdd(bag_dz + (size_t)cur_bag * C + c0 + 128 * j + i, accbag[BAGSUM ? 4 * j + i : 0]);
+    }
+    // column sums: the GROUPS warps that own the same columns combine in shared memory, then one atomic per column per block
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = c0 + 128 * j + i, k = 4 * j + i;
+            atomicAdd(colacc + c, accg[k]);
+            atomicAdd(colacc + C + c, accb[k]);
+            atomicAdd(colacc + 2 * C + c, accz[k]);
+        }
+    __syncthreads();
+    for (int c = tid; c < C; c += 256) {
+        atomicAdd(dgamma + c, colacc[c]);
+        atomicAdd(dbeta + c, colacc[C + c]);
+        atomicAdd(dbias + c, colacc[2 * C + c]);
     }
 }
 
@@ -544,7 +607,7 @@ static void launch_ln_bwd(int has_b, int npool, int grid, cudaStream_t st, const
                           PoolTerm t0, PoolTerm t1, int n_heads,
                           float drop_p, unsigned long long seed, unsigned stream_id, __nv_bfloat16* dz, long long ps, int npl,
                           float* dgamma, float* dbeta, float* dbias, const int* row2bag, float* bag_dz) {
-#define MDL_LN_BWD(HB, NP, BS) ln_gelu_bwd_kernel<C, 2, HB, NP, BS><<<grid, 512, 0, st>>>(z, M, gamma, beta, mean, rstd, dh_a, dh_b, dh_b_rows, t0, t1, n_heads, drop_p, seed, stream_id, dz, ps, npl, dgamma, dbeta, dbias, row2bag, bag_dz)
+#define MDL_LN_BWD(HB, NP, BS) ln_gelu_bwd_kernel<C, HB, NP, BS><<<grid, 256, 0, st>>>(z, M, gamma, beta, mean, rstd, dh_a, dh_b, dh_b_rows, t0, t1, n_heads, drop_p, seed, stream_id, dz, ps, npl, dgamma, dbeta, dbias, row2bag, bag_dz)
     if constexpr (C == 512) {
         if (bag_dz != nullptr) { MDL_LN_BWD(0, 0, true); return; }   // only the first layer (no second gradient, no pooling term)
     }
@@ -584,11 +647,11 @@ int mdl_ln_gelu_bwd(const float* z, long long M, int C, const float* gamma, cons
     const int npool = pool_p0 == nullptr ? 0 : (pool_p1 == nullptr ? 1 : 2);
     cudaStream_t st = (cudaStream_t)stream;
     if (C == 512) {
-        const int grid = grid_for(M, 4 * 2 * 4, 2);   // several iterations per block so the column atomics amortise
+        const int grid = grid_for(M, 8 * 4, 2);       // two blocks per SM, several rows per warp so the column atomics amortise
         launch_ln_bwd<512>(has_b, npool, grid, st, z, (int)M, gamma, beta, mean, rstd, dh_a, dh_b, dh_b_rows, t0, t1, n_heads, drop_p, seed, stream_id,
                            (__nv_bfloat16*)dz_planes, plane_stride, nplanes, dgamma, dbeta, dbias, row2bag, bag_dz);
     } else {
-        const int grid = grid_for(M, 1 * 2 * 8, 2);
+        const int grid = grid_for(M, 2 * 8, 2);
         MDL_REQUIRE(bag_dz == nullptr, "ln_gelu_bwd: per-bag sums are only built for C == 512");
         launch_ln_bwd<2048>(has_b, npool, grid, st, z, (int)M, gamma, beta, mean, rstd, dh_a, dh_b, dh_b_rows, t0, t1, n_heads, drop_p, seed, stream_id,
                             (__nv_bfloat16*)dz_planes, plane_stride, nplanes, dgamma, dbeta, dbias, nullptr, nullptr);

@@ -4,7 +4,8 @@ import importlib
 import sys
 
 _TARGET = "madeleine_b200"
-_SUBMODULES = ["models", "models.Model", "models.abmil", "models.factory", "utils", "utils.loss", "utils.trainer", "utils.utils"]
+_SUBMODULES = ["models", "models.Model", "models.abmil", "models.factory", "utils", "utils.loss", "utils.trainer", "utils.utils",
+               "datasets", "datasets.wsi_dataset"]
 
 _pkg = importlib.import_module(_TARGET)
 for _name in _SUBMODULES:
@@ -12,3 +13,4 @@ for _name in _SUBMODULES:
     sys.modules[f"{__name__}.{_name}"] = _mod
 models = sys.modules[f"{__name__}.models"]
 utils = sys.modules[f"{__name__}.utils"]
+datasets = sys.modules[f"{__name__}.datasets"]

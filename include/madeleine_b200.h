@@ -177,6 +177,15 @@ int mdl_adamw_step(int n_tensors, void* const* host_params, void* const* host_gr
                    void* const* host_exp_avg_sq, const long long* host_numels, float lr, float beta1, float beta2,
                    float eps, float weight_decay, int step, float grad_scale, void* stream);
 
+/* ---- on-device patch resampling from an HBM-resident feature store --------------------------------------------- */
+/* SlideDataset.sample_n + collate (madeleine/datasets/wsi_dataset.py:42-50, 85-99) + the H2D copy of Model.py:113 in one
+ * kernel: store [sum N, D] fp32 holds every bag; bag b = rows [bag_offset[b], bag_offset[b] + bag_len[b]).  For each of the
+ * n_bags bags writes n_sample rows to out [n_bags, n_sample, D]: a random subset without replacement when
+ * bag_len >= n_sample (keyed Feistel permutation, evaluated pointwise), draws with replacement when shorter, zero rows when
+ * bag_len == 0 (missing stain).  idx_out (optional, [n_bags, n_sample]) receives the chosen row of each slot (-1: zero row). */
+int mdl_sample_gather_f32(const float* store, const long long* bag_offset, const int* bag_len, int n_bags, int n_sample,
+                          int D, unsigned long long seed, float* out, int* idx_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,6 +62,7 @@ SIGNATURES = {
     "mdl_infonce_bwd": [c_p, c_p, c_i, c_i, c_f, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "mdl_adamw_max_tensors": [],
     "mdl_adamw_step": [c_i, c_p, c_p, c_p, c_p, c_p, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_p],
+    "mdl_sample_gather_f32": [c_p, c_p, c_p, c_i, c_i, c_i, c_ull, c_p, c_p, c_p],
     "mdl_got_workspace_bytes": [c_i, c_i, c_i],
     "mdl_got_max_tokens": [],
     "mdl_got_force_big": [c_i],
@@ -118,7 +119,7 @@ LAUNCHES = {
     "mdl_ln_gelu_fwd": 1, "mdl_ln_gelu_bwd": 1, "mdl_gate_bwd": 1, "mdl_pool_weights": 1, "mdl_pool_fwd": 1, "mdl_pool_bwd_dlogit": 1,
     "mdl_planes_to_ref_order": 1, "mdl_skinny_linear_fwd": 1, "mdl_skinny_linear_bwd": 2, "mdl_stain_rowbias": 1,
     "mdl_bag_colsum_planes": 1, "mdl_gather_rows_planes": 1, "mdl_stain_rowbias_bwd": 1, "mdl_colsum_f32": 1, "mdl_infonce_fwd": 4, "mdl_infonce_bwd": 2,
-    "mdl_got_extrema": 2, "mdl_got_fwd_bwd": 2, "mdl_got_main": 2, "mdl_got_finish": 1, "mdl_adamw_step": 1,
+    "mdl_got_extrema": 2, "mdl_got_fwd_bwd": 2, "mdl_got_main": 2, "mdl_got_finish": 1, "mdl_adamw_step": 1, "mdl_sample_gather_f32": 1,
 }
 launch_count = [0]
 # optional per-kernel device timing: {name: [(start_event, end_event), ...]} filled when `timed_kernels` is a set of names

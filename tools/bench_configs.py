@@ -108,6 +108,90 @@ def config5(precision, n_slides, n_tokens):
                       "embedding_checksum": float(abs(emb).sum())}))
 
 
+def resident_loader(precision, steps, bs=65, n_cases=130, token_window="batch"):
+    """The reference's canonical step fed three ways: features already in HBM (static batch), the HBM-resident store with
+    on-device resampling (a NEW sample of every bag every step), and the reference's way — a pinned host batch copied in
+    every step (prefetched one batch ahead)."""
+    from madeleine.datasets.wsi_dataset import ResidentSlideStore, ResidentLoader
+    from madeleine_b200.utils.prefetch import DevicePrefetcher
+    dev = torch.device("cuda")
+    mods = ["HE", "HER2", "PGR", "KI67", "ER"]
+    T = 2048
+    g = torch.Generator().manual_seed(0)
+    avail = torch.rand(n_cases, 5, generator=g) < torch.tensor([1.0, 0.46, 0.73, 0.73, 0.73])
+    avail[:, 0] = True
+    base = torch.randn(9000, 512, generator=g)
+    cases = []
+    for c in range(n_cases):
+        row = []
+        for k in range(5):
+            if not avail[c, k]:
+                row.append(None)
+                continue
+            n = int(torch.randint(1500, 8000, (1,), generator=g))          # slides have a few thousand patches
+            o = int(torch.randint(0, 9000 - n, (1,), generator=g))
+            row.append(base[o:o + n])
+        cases.append(row)
+    store = ResidentSlideStore(cases, mods, device=dev)
+    model = MADELEINE(cfg(mods, precision, token_window), stain_encoding=True)
+    model.load_state_dict(make_state_dict(3, n_mod=5, stain_encoding=True))
+    model.to(dev).train()
+    args = Namespace(global_loss="info-nce", symmetric_cl=True, local_loss_weight=1.0)
+    loss_fn = InfoNCE(temperature=0.001)
+
+    def step(batch):
+        model.zero_grad(set_to_none=True)
+        embs, toks = model(batch, device=dev, n_views=1)
+        loss, ok = calculate_losses(mods[1:], loss_fn, GOT, None, embs, toks, batch["modality_labels"][:, 1:], args)
+        loss.backward()
+        return loss
+
+    def timed(batches, n):
+        it = iter(batches)
+        for _ in range(2):
+            step(next(it))
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            step(next(it))
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    def cycle(make):
+        while True:
+            yield from make()
+
+    static = store.sample_batch(list(range(bs)), T, seed=1)
+    ms_static = timed(cycle(lambda: [static]), steps)
+    counter = [0]
+
+    def resampled():                      # the SAME cases as the static batch (same work), a new sample of every bag every step
+        counter[0] += 1
+        return [store.sample_batch(list(range(bs)), T, seed=1000 + counter[0])]
+    ms_resident = timed(cycle(resampled), steps)
+    loader = ResidentLoader(store, batch_size=bs, sample=T, shuffle=True, drop_last=True, seed=0)
+    ms_loader = timed(cycle(lambda: loader), steps)
+    host = [{"feats": static["feats"].cpu().pin_memory(), "modality_labels": static["modality_labels"]} for _ in range(2)]
+    ms_host = timed(DevicePrefetcher(cycle(lambda: host), dev), steps)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(5):
+        store.sample_batch(list(range(bs)), T, seed=100 + i)
+    e1.record()
+    torch.cuda.synchronize()
+    print(json.dumps({"config": f"reference canonical config fed from an HBM-resident store: {n_cases} cases x 5 stains, "
+                                f"{store.nbytes / 1e9:.1f} GB of features resident, batch {bs}, sample {T}, token window {token_window}",
+                      "precision": precision, "ms_per_step_static_device_batch": round(ms_static, 3),
+                      "ms_per_step_resident_store_resampled_every_step": round(ms_resident, 3),
+                      "ms_per_step_resident_loader_shuffled_cases": round(ms_loader, 3),
+                      "ms_per_step_pinned_host_batch_prefetched": round(ms_host, 3),
+                      "sample_gather_kernel_ms": round(e0.elapsed_time(e1) / 5, 3),
+                      "h2d_bytes_per_step_host_path": static["feats"].numel() * 4, "h2d_bytes_per_step_resident": 0,
+                      "cases_per_s_resident": round(bs / (ms_resident * 1e-3), 1)}))
+
+
 def got_sizes():
     """Graph-OT loss alone (forward + token gradients) for a range of problem counts / sizes, incl. the n > 96 path."""
     from madeleine_b200 import ops
@@ -148,5 +232,7 @@ if __name__ == "__main__":
                 token_window=a.token_window)
     if "got" in a.which:
         got_sizes()
+    if "resident" in a.which:
+        resident_loader(a.precision, a.steps, token_window=a.token_window if a.token_window != "off" else "batch")
     if "5" in a.which:
         config5(a.precision, a.slides, 4000)

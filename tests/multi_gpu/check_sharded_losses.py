@@ -36,8 +36,10 @@ def main():
     args = Namespace(global_loss="info-nce", symmetric_cl=True, local_loss_weight=1.0)
     sd = make_state_dict(4, n_mod=3, stain_encoding=False)
 
-    def fresh():
-        m = MADELEINE(cfg, stain_encoding=False)
+    def fresh(token_window="off"):
+        c = Namespace(**vars(cfg))
+        c.b200_token_window = token_window
+        m = MADELEINE(c, stain_encoding=False)
         m.load_state_dict(sd)
         return m.to(dev).eval()
 
@@ -50,35 +52,37 @@ def main():
     loss_ref.backward()
     g_ref = {n: p.grad.clone() for n, p in ref.named_parameters()}
 
-    # ---- sharded: rank r owns cases [r*4, r*4+4)
-    model = fresh()
-    parallel.enable_gradient_sync(True)
-    bl = B // world
-    local = feats[rank * bl:(rank + 1) * bl]
-    embs_l, toks_l = model({"feats": local}, dev, train=True)
-    embs_g, _ = parallel.gather_slide_embeddings(embs_l, labels[rank * bl:(rank + 1) * bl].to(dev), global_labels_host=labels)
-    torch.manual_seed(99)
-    loss_sh, flag, parts = parallel.calculate_losses_sharded(mods[1:], InfoNCE(temperature=0.1), True, embs_g, toks_l, labels[:, 1:],
-                                                             args, rank, bl)
-    loss_sh.backward()                      # encoder backward all-reduces (SUM) the flat gradient buffer
-    local = parts["local"].detach().clone()
-    dist.all_reduce(local)
-    total = parts["global"].detach() + local
     ok = True
-    err = abs(float(total) - float(loss_ref)) / max(1.0, abs(float(loss_ref)))
-    ok &= err < 1e-4
-    if rank == 0:
-        print(f"[{'PASS' if err < 1e-4 else 'FAIL'}] loss sharded(sum over ranks)={float(total):.6f} single={float(loss_ref):.6f}")
-    worst = 0.0
-    for n, p in model.named_parameters():
-        if p.grad is None:
-            continue
-        d = float((p.grad - g_ref[n]).norm() / (g_ref[n].norm() + 1e-12))
-        if float(g_ref[n].norm()) > 1e-5:
-            worst = max(worst, d)
-    ok &= worst < 2e-2
-    if rank == 0:
-        print(f"[{'PASS' if worst < 2e-2 else 'FAIL'}] worst relative gradient difference over parameters = {worst:.3e}")
+    # the token window 'batch' spans the GLOBAL batch (local batch x world size): GOT's permutation is over all cases
+    for token_window in ("off", "batch"):
+        # ---- sharded: rank r owns cases [r*4, r*4+4)
+        model = fresh(token_window)
+        parallel.enable_gradient_sync(True)
+        bl = B // world
+        local = feats[rank * bl:(rank + 1) * bl]
+        embs_l, toks_l = model({"feats": local}, dev, train=True)
+        embs_g, _ = parallel.gather_slide_embeddings(embs_l, labels[rank * bl:(rank + 1) * bl].to(dev), global_labels_host=labels)
+        torch.manual_seed(99)
+        loss_sh, flag, parts = parallel.calculate_losses_sharded(mods[1:], InfoNCE(temperature=0.1), True, embs_g, toks_l, labels[:, 1:],
+                                                                 args, rank, bl)
+        loss_sh.backward()                      # encoder backward all-reduces (SUM) the flat gradient buffer
+        local = parts["local"].detach().clone()
+        dist.all_reduce(local)
+        total = parts["global"].detach() + local
+        err = abs(float(total) - float(loss_ref)) / max(1.0, abs(float(loss_ref)))
+        ok &= err < 1e-4
+        if rank == 0:
+            print(f"[{'PASS' if err < 1e-4 else 'FAIL'}] (token window {token_window}) loss sharded(sum over ranks)={float(total):.6f} single={float(loss_ref):.6f}")
+        worst = 0.0
+        for n, p in model.named_parameters():
+            if p.grad is None:
+                continue
+            d = float((p.grad - g_ref[n]).norm() / (g_ref[n].norm() + 1e-12))
+            if float(g_ref[n].norm()) > 1e-5:
+                worst = max(worst, d)
+        ok &= worst < 2e-2
+        if rank == 0:
+            print(f"[{'PASS' if worst < 2e-2 else 'FAIL'}] (token window {token_window}) worst relative gradient difference over parameters = {worst:.3e}")
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 

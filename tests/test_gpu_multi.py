@@ -16,4 +16,4 @@ def test_sharded_losses_match_single_process():
            "--master-port", "29541", os.path.join(REPO, "tests", "multi_gpu", "check_sharded_losses.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert out.stdout.count("[PASS]") == 2
+    assert out.stdout.count("[PASS]") == 4

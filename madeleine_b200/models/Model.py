@@ -129,7 +129,7 @@ class ABMILEmbedder(nn.Module):
         versions = tuple((p.data_ptr(), p._version) for p in params)
         cached = self._pack_cache.get(key)
         if cached is None or cached[0] != versions:
-            pw = ops.PackedWeights(spec, params, 2 if precision == "fp32" else 1)
+            pw = ops.PackedWeights(spec, params, 1 if precision == "bf16" else 2)
             self._pack_cache = {key: (versions, pw)}      # one live pack: weights change every optimiser step
         else:
             pw = cached[1]

@@ -32,15 +32,20 @@ _step_counter = [0]
 
 
 def resolve_precision(requested: Optional[str]) -> str:
-    """'fp32' (3-pass split-bf16 tcgen05, fp32-grade) or 'bf16' (1 pass).  'auto' follows torch autocast, which is
-    how the reference picks bf16 (--precision bfloat16 → torch.amp.autocast, trainer.py:108)."""
+    """'fp32' (3-pass split-bf16 tcgen05, fp32-grade, forward and backward), 'bf16' (1 pass) or 'fp32_fwd' (fp32-grade
+    forward — outputs and losses at the reference's fp32 values — with 1-pass bf16 GEMMs in the backward pass: gradients
+    at the accuracy the reference's own bf16-autocast training gives, for a third of the backward tensor work).
+    'auto' follows torch autocast, which is how the reference picks bf16 (--precision bfloat16 → torch.amp.autocast,
+    trainer.py:108)."""
     req = (requested or os.environ.get("MADELEINE_B200_PRECISION", "auto")).lower()
     if req in ("fp32", "float32", "fp32x3", "bf16x3"):
         return "fp32"
+    if req in ("fp32_fwd", "fp32-fwd", "mixed"):
+        return "fp32_fwd"
     if req in ("bf16", "bfloat16"):
         return "bf16"
     if req != "auto":
-        raise ValueError(f"unknown precision {requested!r}; use 'auto', 'fp32' or 'bf16'")
+        raise ValueError(f"unknown precision {requested!r}; use 'auto', 'fp32', 'fp32_fwd' or 'bf16'")
     if torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") in (torch.bfloat16, torch.float16):
         return "bf16"
     return "fp32"
@@ -291,6 +296,12 @@ class EncodeOptions:
 
 
 def _nsplit(precision):
+    """(GEMM passes, operand planes) of the forward pass."""
+    return (3, 2) if precision in ("fp32", "fp32_fwd") else (1, 1)
+
+
+def _nsplit_bwd(precision):
+    """(GEMM passes, planes of the gradient operands) of the backward pass."""
     return (3, 2) if precision == "fp32" else (1, 1)
 
 
@@ -397,7 +408,8 @@ def encoder_backward(sv, d_slide: Optional[torch.Tensor], d_logits: Optional[tor
     spec = pw.spec
     dev = sv.h3.device
     st = stream_ptr(dev)
-    nsplit, npl = _nsplit(opt.precision)
+    _, fwd_npl = _nsplit(opt.precision)          # planes of the saved forward activations
+    nsplit, npl = _nsplit_bwd(opt.precision)     # passes / planes of everything the backward pass produces and multiplies
     H = opt.n_heads
     C = HID * H
     M, R = sv.M, sv.R
@@ -428,13 +440,13 @@ def encoder_backward(sv, d_slide: Optional[torch.Tensor], d_logits: Optional[tor
     if d_logits is not None:
         dlogit.copy_(d_logits.reshape(M, H))
         accumulate = 1
-    call("mdl_pool_bwd_dlogit", sv.h3, M * C, npl, dS, sv.pooled, sv.attn_p, sv.cu, None, R, M, H, HID, dlogit, accumulate,
+    call("mdl_pool_bwd_dlogit", sv.h3, M * C, fwd_npl, dS, sv.pooled, sv.attn_p, sv.cu, None, R, M, H, HID, dlogit, accumulate,
          sv.logits, act, 0, st)
     pool_terms = [(sv.attn_p, dS, sv.row2bag)]
     if opt.views is not None:
         tok_idx, cu2, row2seg2 = opt.views
         dS2 = dS_all[R:]
-        call("mdl_pool_bwd_dlogit", sv.h3, M * C, npl, dS2, sv.pooled_views, sv.attn_p2, cu2, tok_idx, cu2.numel() - 1, tok_idx.numel(),
+        call("mdl_pool_bwd_dlogit", sv.h3, M * C, fwd_npl, dS2, sv.pooled_views, sv.attn_p2, cu2, tok_idx, cu2.numel() - 1, tok_idx.numel(),
              H, HID, dlogit, 1, sv.logits, act, 0, st)
         pool_terms.append((sv.attn_p2, dS2, row2seg2))
 

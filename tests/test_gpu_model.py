@@ -297,6 +297,54 @@ def test_token_window_too_small_raises(golden):
             GOT(toks["HE"][:, :, :, 0], toks[mods[1]], subsample=256)
 
 
+def test_fp32_fwd_mode_same_forward_bf16_backward(golden):
+    """b200_precision='fp32_fwd': the forward pass (embeddings, loss) is bit-identical to the fp32-grade mode — it is the
+    same kernels — and matches the reference's fixture; the backward GEMMs run one bf16 pass, so parameter gradients agree
+    with the fp32-grade ones to bf16-GEMM accuracy (norm-wise 2e-2; tolerance written here)."""
+    g = golden("losses_grads")["global_only"]
+    mods = g["modalities"]
+    x = make_feats(g["seed_x"], *g["shape"]) * g["labels"][:, :, None, None]
+    args = Namespace(global_loss="info-nce", symmetric_cl=True, local_loss_weight=1.0)
+    res = []
+    for prec in ("fp32", "fp32_fwd"):
+        model = build(mods, g["stain_encoding"], g["seed_w"], precision=prec)
+        embs, toks = model({"feats": x}, DEV, train=True, n_views=1)
+        torch.manual_seed(g["torch_seed"])
+        loss, _ = calculate_losses(mods[1:], InfoNCE(temperature=0.001), None, None, embs, toks, g["labels"][:, 1:], args)
+        loss.backward()
+        res.append((embs, loss.detach(), {n: p.grad.clone() for n, p in model.named_parameters()}))
+    (e0, l0, g0), (e1, l1, g1) = res
+    for m in mods:
+        assert torch.equal(e0[m], e1[m])
+    assert torch.equal(l0, l1)
+    close(l1, g["loss"], rtol=1e-3, atol=1e-3)
+    for n in g0:
+        denom = float(g0[n].norm())
+        if denom > 1e-4:
+            assert float((g1[n] - g0[n]).norm()) / denom < 2e-2, n
+
+
+def test_extraction_driver_matches_per_slide_encode_he(golden):
+    """utils/inference.extract_slide_embeddings (packed batches, prefetch; pinned bags copied in place, pageable ones through
+    staging) == encode_he slide by slide, for ragged bags and under rank striding."""
+    from madeleine_b200.utils.inference import extract_slide_embeddings
+    g = golden("encoder")["cfg1"]
+    model = build(["HE"], False, g["seed_w"])
+    gen = torch.Generator().manual_seed(11)
+    lens = [256, 31, 700, 1, 90, 512, 333, 64, 5]
+    bags = [torch.randn(n, 512, generator=gen) for n in lens]
+    bags = [b.pin_memory() if i % 3 == 0 else b for i, b in enumerate(bags)]          # a mix of pinned and pageable inputs
+    with torch.no_grad():
+        ref = torch.cat([model.encode_he(b[None].to(DEV), DEV) for b in bags]).cpu()
+    emb, idx = extract_slide_embeddings(model, bags, DEV, token_budget=800)           # several batches, one oversize slide
+    assert idx == list(range(len(bags)))
+    torch.testing.assert_close(torch.from_numpy(emb), ref, rtol=1e-5, atol=1e-6)
+    emb1, idx1 = extract_slide_embeddings(model, bags, DEV, token_budget=800, rank=1, world=2)
+    assert idx1 == list(range(1, len(bags), 2))
+    torch.testing.assert_close(torch.from_numpy(emb1), ref[1::2], rtol=1e-5, atol=1e-6)
+    close(torch.from_numpy(extract_slide_embeddings(model, [make_feats(g["seed_x"], *g["shape"])[0]], DEV)[0]), g["encode_he"])
+
+
 def test_fused_adamw_matches_torch():
     from madeleine_b200.optim import FusedAdamW
     torch.manual_seed(0)

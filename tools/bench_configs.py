@@ -203,6 +203,47 @@ def resident_loader(precision, steps, bs=65, n_cases=130, token_window="batch"):
                       "cases_per_s_resident": round(bs / (ms_resident * 1e-3), 1)}))
 
 
+def config2_ragged(precision, steps):
+    """BASELINE configs[1] as written: 16 cases x 2 stains, N_i ~ U[200, 4000] per bag (generator seed 1234), symmetric
+    InfoNCE.  The reference can only batch equal-length bags (it loops bs = 1 or pads); here the 32 bags are packed
+    back to back ([sum N_i, 512] + cu_seqlens) and go through forward_packed in one pass, no padding."""
+    dev = torch.device("cuda")
+    mods = ["HE", "IHC"]
+    model = MADELEINE(cfg(mods, precision), stain_encoding=False)
+    model.load_state_dict(make_state_dict(0, n_mod=2))
+    model.to(dev).train()
+    g = torch.Generator().manual_seed(1234)
+    lens = torch.randint(200, 4001, (32,), generator=g)
+    cu = torch.zeros(33, dtype=torch.int32)
+    cu[1:] = lens.cumsum(0)
+    total = int(cu[-1])
+    x = torch.randn(total, 512, device=dev)
+    cu_dev = cu.to(dev)
+    loss_fn = InfoNCE(temperature=0.001)
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        slide, _ = model.forward_packed(x, cu_dev, want_tokens=False)      # bags 2c / 2c+1 = HE / IHC slide of case c
+        loss = loss_fn(query=slide[0::2], positive_key=slide[1::2], symmetric=True)
+        loss.backward()
+        return loss
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    print(json.dumps({"config": "BASELINE configs[1], ragged: 16 cases x 2 stains, N_i ~ U[200,4000] (seed 1234), packed, symmetric InfoNCE, fwd+bwd",
+                      "precision": precision, "tokens": total, "max_len": int(lens.max()), "ms_per_step": round(ms, 3),
+                      "slides_per_s": round(32 / (ms * 1e-3), 1), "tokens_per_s": round(total / (ms * 1e-3)),
+                      "padded_tokens_if_batched_dense": int(lens.max()) * 32, "loss": float(loss.detach())}))
+
+
 def got_sizes():
     """Graph-OT loss alone (forward + token gradients) for a range of problem counts / sizes, incl. the n > 96 path."""
     from madeleine_b200 import ops
@@ -241,6 +282,8 @@ if __name__ == "__main__":
         # the reference's shipped pre-training configuration (scripts/launch_pretrain_withStainEncodings.sh): batch 65
         config3(a.precision, a.steps, 2, skip=True, bs=65, tag="reference canonical config: batch=65", breakdown=a.breakdown,
                 token_window=a.token_window)
+    if "ragged" in a.which:
+        config2_ragged(a.precision, a.steps)
     if "got" in a.which:
         got_sizes()
     if "resident" in a.which:

@@ -46,8 +46,8 @@ int mdl_row2bag(const int* cu_seqlens, int n_bags, int* row2bag, long long rows,
  * (per-head operand slabs).  bias / rowbias / row2bag may be NULL. */
 int mdl_gemm_nt(const void* a_planes, long long a_rows, long long a_cols, long long lda, long long a_plane_stride,
                 const void* b_planes, long long b_rows, long long b_cols, long long ldb, long long b_plane_stride,
-                float* out, long long ldc, int M, int N, int K, int nsplit, int grp_n_cols, int a_koff,
-                const float* bias, const float* rowbias, const int* row2bag, void* stream);
+                void* out, long long ldc, int M, int N, int K, int nsplit, int grp_n_cols, int a_koff,
+                const float* bias, const float* rowbias, const int* row2bag, int out_bf16, void* stream);
 /* Gated-attention scores of all heads in one launch (BatchedABMIL.forward, abmil.py:49-52; head loop Model.py:406-409):
  * logits[m,h] = sum_j tanh(x_h Wa_h^T + ba)_j * sigmoid(x_h Wb_h^T + bb)_j * wc_hj + bc_h, x_h = A[:, h*512:(h+1)*512].
  * b_planes = packed [n_heads*4][128 Wa rows | 128 Wb rows][512].  gate_a/gate_b (fp16 [M, n_heads*512]) may be NULL. */
@@ -73,22 +73,22 @@ int mdl_gemm_tn_simt(const void* a_planes, long long lda, long long a_plane_stri
 
 /* ---- LayerNorm + GELU (+dropout) ------------------------------------------------------------------------------ */
 /* nn.LayerNorm -> nn.GELU -> nn.Dropout of ABMILEmbedder.pre_attn (Model.py:352-354, 356-358, 360-362). */
-int mdl_ln_gelu_fwd(const float* z, long long M, int C, const float* gamma, const float* beta, float eps,
+int mdl_ln_gelu_fwd(const void* z, long long M, int C, const float* gamma, const float* beta, float eps,
                     float drop_p, unsigned long long seed, unsigned stream_id,
-                    void* planes, long long plane_stride, int nplanes, float* mean, float* rstd, void* stream);
+                    void* planes, long long plane_stride, int nplanes, float* mean, float* rstd, int z_bf16, void* stream);
 /* Backward of the above; dh = dh_a + dh_b + sum_v pool_p_v[m, head] * pool_dS_v[pool_seg_v[m], c] (any may be NULL).
  * dh_b_rows == NULL: dh_b is dense [M, C]; otherwise dh_b is compact [n_sel, C] and dh_b_rows[m] is token m's compact row
  * or -1 (the token_projector gradient of the token window, Model.py:138-146 + loss.py:281-284).
  * Accumulates dgamma, dbeta and the preceding Linear's bias grad dbias (all [C], caller zero-fills).
  * bag_dz != NULL (C == 512, no dh_b / pooling term): also accumulates per-bag column sums of dz into bag_dz[row2bag[m], c]
  * ([n_bags, C], caller zero-fills) — the stain-encoding backward of Model.py:126-133. */
-int mdl_ln_gelu_bwd(const float* z, long long M, int C, const float* gamma, const float* beta, const float* mean,
-                    const float* rstd, const float* dh_a, const float* dh_b, const int* dh_b_rows,
+int mdl_ln_gelu_bwd(const void* z, long long M, int C, const float* gamma, const float* beta, const float* mean,
+                    const float* rstd, const void* dh_a, const void* dh_b, const int* dh_b_rows,
                     const float* pool_p0, const float* pool_dS0, const int* pool_seg0,
                     const float* pool_p1, const float* pool_dS1, const int* pool_seg1, int n_heads,
                     float drop_p, unsigned long long seed, unsigned stream_id,
                     void* dz_planes, long long plane_stride, int nplanes,
-                    float* dgamma, float* dbeta, float* dbias, const int* row2bag, float* bag_dz, void* stream);
+                    float* dgamma, float* dbeta, float* dbias, const int* row2bag, float* bag_dz, int in_bf16, void* stream);
 /* Backward of the gate nonlinearities of mdl_gemm_gated; dpre planes [M, n_heads*1024] in packed gate order. */
 int mdl_gate_bwd(const void* gate_a, const void* gate_b, const float* dlogit, const float* wc, long long M, int n_heads,
                  float drop_p, unsigned long long seed, void* dpre_planes, long long plane_stride, int nplanes,

@@ -34,16 +34,16 @@ SIGNATURES = {
     "mdl_scatter_f32": [c_p, c_p, c_ll, c_p, c_i, c_p],
     "mdl_row2bag": [c_p, c_i, c_p, c_ll, c_p],
     "mdl_gemm_nt": [c_p, c_ll, c_ll, c_ll, c_ll, c_p, c_ll, c_ll, c_ll, c_ll, c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_i,
-                    c_p, c_p, c_p, c_p],
+                    c_p, c_p, c_p, c_i, c_p],
     "mdl_gemm_gated": [c_p, c_ll, c_ll, c_ll, c_ll, c_p, c_ll, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_f,
                        c_ull, c_p],
     "mdl_gemm_tn_accum": [c_p, c_ll, c_ll, c_ll, c_p, c_ll, c_ll, c_ll, c_ll, c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "mdl_gemm_debug_flags": [c_i],
     "mdl_gemm_nt_simt": [c_p, c_ll, c_ll, c_p, c_ll, c_ll, c_p, c_ll, c_i, c_i, c_i, c_i, c_p],
     "mdl_gemm_tn_simt": [c_p, c_ll, c_ll, c_p, c_ll, c_ll, c_ll, c_p, c_ll, c_i, c_i, c_i, c_p],
-    "mdl_ln_gelu_fwd": [c_p, c_ll, c_i, c_p, c_p, c_f, c_f, c_ull, c_u, c_p, c_ll, c_i, c_p, c_p, c_p],
+    "mdl_ln_gelu_fwd": [c_p, c_ll, c_i, c_p, c_p, c_f, c_f, c_ull, c_u, c_p, c_ll, c_i, c_p, c_p, c_i, c_p],
     "mdl_ln_gelu_bwd": [c_p, c_ll, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_f, c_ull, c_u,
-                        c_p, c_ll, c_i, c_p, c_p, c_p, c_p, c_p, c_p],
+                        c_p, c_ll, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_p],
     "mdl_gate_bwd": [c_p, c_p, c_p, c_p, c_ll, c_i, c_f, c_ull, c_p, c_ll, c_i, c_p, c_p, c_p, c_p, c_p],
     "mdl_pool_tsplit": [c_i, c_ll, c_i, c_i],
     "mdl_pool_workspace_bytes": [c_i, c_i, c_i, c_i],

@@ -68,14 +68,30 @@ __global__ void row2bag_kernel(const int* __restrict__ cu, int n_bags, int* __re
     }
 }
 
+// Four consecutive activations as fp32: the GEMM outputs that feed these kernels are fp32 in the fp32-grade modes and bf16
+// in the bf16 mode (what torch autocast hands LayerNorm after an nn.Linear).  `off` is an ELEMENT offset.
+template <bool BF16>
+__device__ __forceinline__ float4 ld_act4(const void* base, size_t off) {
+    if (BF16) {
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + off));
+        return make_float4(bf16_lo_of(u.x), bf16_hi_of(u.x), bf16_lo_of(u.y), bf16_hi_of(u.y));
+    }
+    return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off));
+}
+template <bool BF16>
+__device__ __forceinline__ void prefetch_act(const void* base, size_t off) {
+    const char* p = reinterpret_cast<const char*>(base) + off * (BF16 ? 2 : 4);
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // ---------------------------------------------------------------------------------------------------
 // LayerNorm + exact GELU (+ dropout) forward.  One warp owns RPW whole rows (C/32 values per lane per row, float4
 // columns j*128 + lane*4), so the two row reductions are shuffles only and RPW*C/128 16-byte loads are in flight
 // per lane.  No shared memory, no block barriers.
 // ---------------------------------------------------------------------------------------------------
-template <int C, int RPW>
+template <int C, int RPW, bool ZBF16>
 __global__ void __launch_bounds__(256, 2)
-ln_gelu_fwd_kernel(const float* __restrict__ z, int M, const float* __restrict__ gamma, const float* __restrict__ beta,
+ln_gelu_fwd_kernel(const void* __restrict__ z, int M, const float* __restrict__ gamma, const float* __restrict__ beta,
                    float eps, float drop_p, unsigned long long seed, unsigned stream_id,
                    __nv_bfloat16* __restrict__ planes, long long plane_stride, int nplanes,
                    float* __restrict__ mean_out, float* __restrict__ rstd_out) {
@@ -90,9 +106,8 @@ ln_gelu_fwd_kernel(const float* __restrict__ z, int M, const float* __restrict__
 #pragma unroll
             for (int r = 0; r < RPW; ++r) {
                 if (mp + r < M) {
-                    const float* zp = z + (size_t)(mp + r) * C + lane * 4;
 #pragma unroll
-                    for (int j = 0; j < V; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(zp + j * 128));
+                    for (int j = 0; j < V; ++j) prefetch_act<ZBF16>(z, (size_t)(mp + r) * C + lane * 4 + j * 128);
                 }
             }
         }
@@ -100,9 +115,8 @@ ln_gelu_fwd_kernel(const float* __restrict__ z, int M, const float* __restrict__
 #pragma unroll
         for (int r = 0; r < RPW; ++r) {
             const int mr = m0 + r < M ? m0 + r : m0;                 // clamp: a duplicate row is loaded, never stored
-            const float4* zr = reinterpret_cast<const float4*>(z + (size_t)mr * C) + lane;
 #pragma unroll
-            for (int j = 0; j < V; ++j) v[r][j] = __ldg(zr + j * 32);
+            for (int j = 0; j < V; ++j) v[r][j] = ld_act4<ZBF16>(z, (size_t)mr * C + lane * 4 + j * 128);
         }
 #pragma unroll
         for (int r = 0; r < RPW; ++r) {
@@ -174,11 +188,11 @@ struct PoolTerm {
 // row of token m (or -1): the token-projector gradient exists only for the token window the local loss can read.
 // BAGSUM: additionally accumulate per-bag column sums of dz into bag_dz[row2bag[m], c] (the stain-encoding backward needs
 // them); a thread flushes its bag accumulator only when the bag id changes.
-template <int C, int HAS_B, int NPOOL, bool BAGSUM>
+template <int C, int HAS_B, int NPOOL, bool BAGSUM, bool INBF16>
 __global__ void __launch_bounds__(256, 2)
-ln_gelu_bwd_kernel(const float* __restrict__ z, int M, const float* __restrict__ gamma, const float* __restrict__ beta,
+ln_gelu_bwd_kernel(const void* __restrict__ z, int M, const float* __restrict__ gamma, const float* __restrict__ beta,
                    const float* __restrict__ mean, const float* __restrict__ rstd_in,
-                   const float* __restrict__ dh_a, const float* __restrict__ dh_b, const int* __restrict__ dh_b_rows,
+                   const void* __restrict__ dh_a, const void* __restrict__ dh_b, const int* __restrict__ dh_b_rows,
                    PoolTerm pt0, PoolTerm pt1, int n_heads,
                    float drop_p, unsigned long long seed, unsigned stream_id,
                    __nv_bfloat16* __restrict__ dz_planes, long long plane_stride, int nplanes,
@@ -218,9 +232,9 @@ ln_gelu_bwd_kernel(const float* __restrict__ z, int M, const float* __restrict__
                 const size_t po = (size_t)mp * C + c0;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(z + po + 128 * j));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(dh_a + po + 128 * j));
-                    if (HAS_B == 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(dh_b + po + 128 * j));
+                    prefetch_act<INBF16>(z, po + 128 * j);
+                    prefetch_act<INBF16>(dh_a, po + 128 * j);
+                    if (HAS_B == 1) prefetch_act<INBF16>(dh_b, po + 128 * j);
                 }
             }
         }
@@ -229,13 +243,13 @@ ln_gelu_bwd_kernel(const float* __restrict__ z, int M, const float* __restrict__
             float4 zv[4], dv[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                zv[j] = __ldg(reinterpret_cast<const float4*>(z + row_off + 128 * j));
-                dv[j] = __ldg(reinterpret_cast<const float4*>(dh_a + row_off + 128 * j));
+                zv[j] = ld_act4<INBF16>(z, row_off + 128 * j);
+                dv[j] = ld_act4<INBF16>(dh_a, row_off + 128 * j);
             }
             if (HAS_B == 1) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float4 t = __ldg(reinterpret_cast<const float4*>(dh_b + row_off + 128 * j));
+                    const float4 t = ld_act4<INBF16>(dh_b, row_off + 128 * j);
                     dv[j].x += t.x; dv[j].y += t.y; dv[j].z += t.z; dv[j].w += t.w;
                 }
             }
@@ -244,7 +258,7 @@ ln_gelu_bwd_kernel(const float* __restrict__ z, int M, const float* __restrict__
                 if (sel >= 0) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const float4 t = __ldg(reinterpret_cast<const float4*>(dh_b + (size_t)sel * C + c0 + 128 * j));
+                        const float4 t = ld_act4<INBF16>(dh_b, (size_t)sel * C + c0 + 128 * j);
                         dv[j].x += t.x; dv[j].y += t.y; dv[j].z += t.z; dv[j].w += t.w;
                     }
                 }
@@ -581,19 +595,21 @@ int mdl_row2bag(const int* cu_seqlens, int n_bags, int* row2bag, long long rows,
     return 0;
 }
 
-int mdl_ln_gelu_fwd(const float* z, long long M, int C, const float* gamma, const float* beta, float eps,
+int mdl_ln_gelu_fwd(const void* z, long long M, int C, const float* gamma, const float* beta, float eps,
                     float drop_p, unsigned long long seed, unsigned stream_id,
-                    void* planes, long long plane_stride, int nplanes, float* mean, float* rstd, void* stream) {
+                    void* planes, long long plane_stride, int nplanes, float* mean, float* rstd, int z_bf16, void* stream) {
     MDL_REQUIRE(C == 512 || C == 2048, "ln_gelu_fwd: C must be 512 or 2048 (got %d)", C);
     MDL_REQUIRE(M < (1LL << 31), "ln_gelu_fwd: too many rows");
     if (M == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (C == 512) {
         const int grid = grid_for(M, 8 * 2, 6);
-        ln_gelu_fwd_kernel<512, 2><<<grid, 256, 0, st>>>(z, (int)M, gamma, beta, eps, drop_p, seed, stream_id, (__nv_bfloat16*)planes, plane_stride, nplanes, mean, rstd);
+        if (z_bf16) ln_gelu_fwd_kernel<512, 2, true><<<grid, 256, 0, st>>>(z, (int)M, gamma, beta, eps, drop_p, seed, stream_id, (__nv_bfloat16*)planes, plane_stride, nplanes, mean, rstd);
+        else ln_gelu_fwd_kernel<512, 2, false><<<grid, 256, 0, st>>>(z, (int)M, gamma, beta, eps, drop_p, seed, stream_id, (__nv_bfloat16*)planes, plane_stride, nplanes, mean, rstd);
     } else {
         const int grid = grid_for(M, 8, 4);
-        ln_gelu_fwd_kernel<2048, 1><<<grid, 256, 0, st>>>(z, (int)M, gamma, beta, eps, drop_p, seed, stream_id, (__nv_bfloat16*)planes, plane_stride, nplanes, mean, rstd);
+        if (z_bf16) ln_gelu_fwd_kernel<2048, 1, true><<<grid, 256, 0, st>>>(z, (int)M, gamma, beta, eps, drop_p, seed, stream_id, (__nv_bfloat16*)planes, plane_stride, nplanes, mean, rstd);
+        else ln_gelu_fwd_kernel<2048, 1, false><<<grid, 256, 0, st>>>(z, (int)M, gamma, beta, eps, drop_p, seed, stream_id, (__nv_bfloat16*)planes, plane_stride, nplanes, mean, rstd);
     }
     MDL_CHECK_LAUNCH();
     return 0;
@@ -601,13 +617,13 @@ int mdl_ln_gelu_fwd(const float* z, long long M, int C, const float* gamma, cons
 
 }  // extern "C"
 
-template <int C>
-static void launch_ln_bwd(int has_b, int npool, int grid, cudaStream_t st, const float* z, int M, const float* gamma, const float* beta,
-                          const float* mean, const float* rstd, const float* dh_a, const float* dh_b, const int* dh_b_rows,
+template <int C, bool INBF16>
+static void launch_ln_bwd(int has_b, int npool, int grid, cudaStream_t st, const void* z, int M, const float* gamma, const float* beta,
+                          const float* mean, const float* rstd, const void* dh_a, const void* dh_b, const int* dh_b_rows,
                           PoolTerm t0, PoolTerm t1, int n_heads,
                           float drop_p, unsigned long long seed, unsigned stream_id, __nv_bfloat16* dz, long long ps, int npl,
                           float* dgamma, float* dbeta, float* dbias, const int* row2bag, float* bag_dz) {
-#define MDL_LN_BWD(HB, NP, BS) ln_gelu_bwd_kernel<C, HB, NP, BS><<<grid, 256, 0, st>>>(z, M, gamma, beta, mean, rstd, dh_a, dh_b, dh_b_rows, t0, t1, n_heads, drop_p, seed, stream_id, dz, ps, npl, dgamma, dbeta, dbias, row2bag, bag_dz)
+#define MDL_LN_BWD(HB, NP, BS) ln_gelu_bwd_kernel<C, HB, NP, BS, INBF16><<<grid, 256, 0, st>>>(z, M, gamma, beta, mean, rstd, dh_a, dh_b, dh_b_rows, t0, t1, n_heads, drop_p, seed, stream_id, dz, ps, npl, dgamma, dbeta, dbias, row2bag, bag_dz)
     if constexpr (C == 512) {
         if (bag_dz != nullptr) { MDL_LN_BWD(0, 0, true); return; }   // only the first layer (no second gradient, no pooling term)
     }
@@ -625,13 +641,13 @@ static void launch_ln_bwd(int has_b, int npool, int grid, cudaStream_t st, const
 
 extern "C" {
 
-int mdl_ln_gelu_bwd(const float* z, long long M, int C, const float* gamma, const float* beta, const float* mean, const float* rstd,
-                    const float* dh_a, const float* dh_b, const int* dh_b_rows,
+int mdl_ln_gelu_bwd(const void* z, long long M, int C, const float* gamma, const float* beta, const float* mean, const float* rstd,
+                    const void* dh_a, const void* dh_b, const int* dh_b_rows,
                     const float* pool_p0, const float* pool_dS0, const int* pool_seg0,
                     const float* pool_p1, const float* pool_dS1, const int* pool_seg1, int n_heads,
                     float drop_p, unsigned long long seed, unsigned stream_id,
                     void* dz_planes, long long plane_stride, int nplanes,
-                    float* dgamma, float* dbeta, float* dbias, const int* row2bag, float* bag_dz, void* stream) {
+                    float* dgamma, float* dbeta, float* dbias, const int* row2bag, float* bag_dz, int in_bf16, void* stream) {
     MDL_REQUIRE(C == 512 || C == 2048, "ln_gelu_bwd: C must be 512 or 2048 (got %d)", C);
     MDL_REQUIRE(n_heads > 0 && C % n_heads == 0 && (C / n_heads) % 4 == 0, "ln_gelu_bwd: bad n_heads");
     MDL_REQUIRE(M < (1LL << 31), "ln_gelu_bwd: too many rows");
@@ -648,13 +664,17 @@ int mdl_ln_gelu_bwd(const float* z, long long M, int C, const float* gamma, cons
     cudaStream_t st = (cudaStream_t)stream;
     if (C == 512) {
         const int grid = grid_for(M, 8 * 4, 2);       // two blocks per SM, several rows per warp so the column atomics amortise
-        launch_ln_bwd<512>(has_b, npool, grid, st, z, (int)M, gamma, beta, mean, rstd, dh_a, dh_b, dh_b_rows, t0, t1, n_heads, drop_p, seed, stream_id,
-                           (__nv_bfloat16*)dz_planes, plane_stride, nplanes, dgamma, dbeta, dbias, row2bag, bag_dz);
+        if (in_bf16) launch_ln_bwd<512, true>(has_b, npool, grid, st, z, (int)M, gamma, beta, mean, rstd, dh_a, dh_b, dh_b_rows, t0, t1, n_heads, drop_p, seed, stream_id,
+                                              (__nv_bfloat16*)dz_planes, plane_stride, nplanes, dgamma, dbeta, dbias, row2bag, bag_dz);
+        else launch_ln_bwd<512, false>(has_b, npool, grid, st, z, (int)M, gamma, beta, mean, rstd, dh_a, dh_b, dh_b_rows, t0, t1, n_heads, drop_p, seed, stream_id,
+                                       (__nv_bfloat16*)dz_planes, plane_stride, nplanes, dgamma, dbeta, dbias, row2bag, bag_dz);
     } else {
         const int grid = grid_for(M, 2 * 8, 2);
         MDL_REQUIRE(bag_dz == nullptr, "ln_gelu_bwd: per-bag sums are only built for C == 512");
-        launch_ln_bwd<2048>(has_b, npool, grid, st, z, (int)M, gamma, beta, mean, rstd, dh_a, dh_b, dh_b_rows, t0, t1, n_heads, drop_p, seed, stream_id,
-                            (__nv_bfloat16*)dz_planes, plane_stride, nplanes, dgamma, dbeta, dbias, nullptr, nullptr);
+        if (in_bf16) launch_ln_bwd<2048, true>(has_b, npool, grid, st, z, (int)M, gamma, beta, mean, rstd, dh_a, dh_b, dh_b_rows, t0, t1, n_heads, drop_p, seed, stream_id,
+                                               (__nv_bfloat16*)dz_planes, plane_stride, nplanes, dgamma, dbeta, dbias, nullptr, nullptr);
+        else launch_ln_bwd<2048, false>(has_b, npool, grid, st, z, (int)M, gamma, beta, mean, rstd, dh_a, dh_b, dh_b_rows, t0, t1, n_heads, drop_p, seed, stream_id,
+                                        (__nv_bfloat16*)dz_planes, plane_stride, nplanes, dgamma, dbeta, dbias, nullptr, nullptr);
     }
     MDL_CHECK_LAUNCH();
     return 0;

@@ -28,6 +28,7 @@ struct GemmArgs {
     int grp_n_tiles, a_koff;  // kKMajor: A k-offset = (n_tile / grp_n_tiles) * a_koff
     int grp_m_tiles, b_coff;  // kMNMajor: B column offset = (m_tile / grp_m_tiles) * b_coff
     float* out; int ldc;
+    int out_bf16;             // EPI_STORE only: `out` is a bf16 matrix (leading dimension ldc in ELEMENTS), values rounded RN
     const float* bias;        // [N] or null
     const float* rowbias;     // [R, N] or null (per-bag bias, stain encodings)
     const int* row2bag;       // [M]
@@ -105,7 +106,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, float* aux, uin
                 if (m_warp + row < p.M && !(p.debug_flags & 2)) {
                     float* dst = p.out + (size_t)(m_warp + row) * p.ldc + n0 + col4;
                     if constexpr (EPI == EPI_STORE) {
-                        *reinterpret_cast<float4*>(dst) = make_float4(x0, x1, x2, x3);
+                        if (p.out_bf16) {
+                            __nv_bfloat16* d16 = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)(m_warp + row) * p.ldc + n0 + col4;
+                            const __nv_bfloat162 lo = __floats2bfloat162_rn(x0, x1), hi = __floats2bfloat162_rn(x2, x3);
+                            *reinterpret_cast<uint2*>(d16) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+                        } else {
+                            *reinterpret_cast<float4*>(dst) = make_float4(x0, x1, x2, x3);
+                        }
                     } else {
                         if (have_k)
                             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x0), "f"(x1), "f"(x2), "f"(x3) : "memory");

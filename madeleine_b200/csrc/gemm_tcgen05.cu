@@ -335,9 +335,9 @@ extern "C" {
 
 int mdl_gemm_nt(const void* a_planes, long long a_rows, long long a_cols, long long lda, long long a_plane_stride,
                 const void* b_planes, long long b_rows, long long b_cols, long long ldb, long long b_plane_stride,
-                float* out, long long ldc, int M, int N, int K, int nsplit,
+                void* out, long long ldc, int M, int N, int K, int nsplit,
                 int grp_n_cols, int a_koff,
-                const float* bias, const float* rowbias, const int* row2bag, void* stream) {
+                const float* bias, const float* rowbias, const int* row2bag, int out_bf16, void* stream) {
     MDL_REQUIRE(nsplit == 1 || nsplit == 3, "nsplit must be 1 or 3");
     MDL_REQUIRE(K % BLOCK_K == 0, "K (%d) must be a multiple of %d", K, BLOCK_K);
     MDL_REQUIRE(N % 128 == 0, "N (%d) must be a multiple of 128", N);
@@ -359,7 +359,7 @@ int mdl_gemm_nt(const void* a_planes, long long a_rows, long long a_cols, long l
     MDL_REQUIRE(ldc % 4 == 0, "ldc must be a multiple of 4");
     g.grp_n_tiles = grp_n_cols > 0 ? grp_n_cols / bn : (1 << 30); g.a_koff = a_koff;
     g.grp_m_tiles = 1 << 30; g.b_coff = 0;
-    g.out = out; g.ldc = (int)ldc; g.bias = bias; g.rowbias = rowbias; g.row2bag = row2bag;
+    g.out = (float*)out; g.ldc = (int)ldc; g.out_bf16 = out_bf16 ? 1 : 0; g.bias = bias; g.rowbias = rowbias; g.row2bag = row2bag;
     g.debug_flags = g_debug_flags;
     if (two_cta) {
         g.num_m_tiles = (M + 255) / 256;

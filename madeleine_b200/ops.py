@@ -213,15 +213,16 @@ def split_planes(x: torch.Tensor, nplanes: int) -> torch.Tensor:
 
 
 def gemm_nt(a: torch.Tensor, K: int, bw: Tuple, out_cols: int, nsplit: int, bias=None, rowbias=None, row2bag=None,
-            grp_n_cols: int = 0, a_koff: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out[M, N] = a[:, :K(+offsets)] @ B^T (+bias). a: planes [np, M, Ca]; bw = (ptr tensor, rows, cols, plane_stride)."""
+            grp_n_cols: int = 0, a_koff: int = 0, out: Optional[torch.Tensor] = None, out_dtype=torch.float32) -> torch.Tensor:
+    """out[M, N] = a[:, :K(+offsets)] @ B^T (+bias). a: planes [np, M, Ca]; bw = (ptr tensor, rows, cols, plane_stride).
+    out_dtype torch.bfloat16: the fp32 accumulator is rounded to bf16 on the way out (bf16 mode: what autocast's Linear returns)."""
     npl, M, Ca = a.shape
     bt, b_rows, b_cols, b_ps = bw
     N = out_cols
     if out is None:
-        out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+        out = torch.empty(M, N, dtype=out_dtype, device=a.device)
     call("mdl_gemm_nt", a, M, Ca, Ca, M * Ca, bt, b_rows, b_cols, b_cols, b_ps, out, out.stride(0), M, N, K, nsplit,
-         grp_n_cols, a_koff, bias, rowbias, row2bag, stream_ptr(a.device))
+         grp_n_cols, a_koff, bias, rowbias, row2bag, int(out.dtype == torch.bfloat16), stream_ptr(a.device))
     return out
 
 
@@ -257,7 +258,8 @@ def ln_gelu_fwd(z, gamma, beta, nplanes, drop_p, seed, stream_id):
     planes = _planes_empty(nplanes, M, C, z.device)
     mean = torch.empty(M, dtype=torch.float32, device=z.device)
     rstd = torch.empty(M, dtype=torch.float32, device=z.device)
-    call("mdl_ln_gelu_fwd", z, M, C, gamma, beta, LN_EPS, drop_p, seed, stream_id, planes, M * C, nplanes, mean, rstd, stream_ptr(z.device))
+    call("mdl_ln_gelu_fwd", z, M, C, gamma, beta, LN_EPS, drop_p, seed, stream_id, planes, M * C, nplanes, mean, rstd,
+         int(z.dtype == torch.bfloat16), stream_ptr(z.device))
     return planes, mean, rstd
 
 
@@ -268,8 +270,12 @@ def ln_gelu_bwd(z, gamma, beta, mean, rstd, dh_a, dh_b, pool_terms, n_heads, npl
     M, C = z.shape
     dz = _planes_empty(nplanes, M, C, z.device)
     t = list(pool_terms) + [(None, None, None)] * (2 - len(pool_terms))
+    in_bf16 = z.dtype == torch.bfloat16              # z, dh_a and dh_b share one storage type
+    for g_in in (dh_a, dh_b):
+        if g_in is not None and g_in.dtype != z.dtype:
+            raise RuntimeError(f"ln_gelu_bwd: upstream gradient dtype {g_in.dtype} != activation dtype {z.dtype}")
     call("mdl_ln_gelu_bwd", z, M, C, gamma, beta, mean, rstd, dh_a, dh_b, dh_b_rows, t[0][0], t[0][1], t[0][2], t[1][0], t[1][1], t[1][2],
-         n_heads, drop_p, seed, stream_id, dz, M * C, nplanes, dgamma, dbeta, dbias, row2bag, bag_dz, stream_ptr(z.device))
+         n_heads, drop_p, seed, stream_id, dz, M * C, nplanes, dgamma, dbeta, dbias, row2bag, bag_dz, int(in_bf16), stream_ptr(z.device))
     return dz
 
 
@@ -298,6 +304,11 @@ class EncodeOptions:
 def _nsplit(precision):
     """(GEMM passes, operand planes) of the forward pass."""
     return (3, 2) if precision in ("fp32", "fp32_fwd") else (1, 1)
+
+
+def _act_dtype(precision):
+    """Storage type of the pre-LayerNorm activations and of the dgrad outputs."""
+    return torch.bfloat16 if precision == "bf16" else torch.float32
 
 
 def _nsplit_bwd(precision):
@@ -337,12 +348,15 @@ def encoder_forward(x: torch.Tensor, cu: torch.Tensor, codes: Optional[torch.Ten
         call("mdl_stain_rowbias", emb, codes, w1, spec.d_in_total, opt.d_in, opt.se_dim, HID, R, rowbias, st)
     sv.codes = codes
 
+    # bf16 mode: the Linear outputs that feed LayerNorm are stored as bf16, exactly what torch autocast hands LayerNorm in
+    # the reference's --precision bfloat16 runs (trainer.py:108); the fp32-grade modes keep them fp32
+    zdt = _act_dtype(opt.precision)
     xp = split_planes(x, npl)
-    z1 = gemm_nt(xp, HID, pw.planes("w1"), HID, nsplit, bias=pw.vec("b1"), rowbias=rowbias, row2bag=row2bag)
+    z1 = gemm_nt(xp, HID, pw.planes("w1"), HID, nsplit, bias=pw.vec("b1"), rowbias=rowbias, row2bag=row2bag, out_dtype=zdt)
     h1, mean1, rstd1 = ln_gelu_fwd(z1, pw.vec("g1"), pw.vec("be1"), npl, p_pre, opt.seed, 1)
-    z2 = gemm_nt(h1, HID, pw.planes("w2"), HID, nsplit, bias=pw.vec("b2"))
+    z2 = gemm_nt(h1, HID, pw.planes("w2"), HID, nsplit, bias=pw.vec("b2"), out_dtype=zdt)
     h2, mean2, rstd2 = ln_gelu_fwd(z2, pw.vec("g2"), pw.vec("be2"), npl, p_pre, opt.seed, 2)
-    z3 = gemm_nt(h2, HID, pw.planes("w3"), C, nsplit, bias=pw.vec("b3"))
+    z3 = gemm_nt(h2, HID, pw.planes("w3"), C, nsplit, bias=pw.vec("b3"), out_dtype=zdt)
     h3, mean3, rstd3 = ln_gelu_fwd(z3, pw.vec("g3"), pw.vec("be3"), npl, p_pre, opt.seed, 3)
     if not keep_for_backward:
         del z1, z2, z3, h1, h2
@@ -454,7 +468,8 @@ def encoder_backward(sv, d_slide: Optional[torch.Tensor], d_logits: Optional[tor
     dpre = _planes_empty(npl, M, H * 1024, dev)
     call("mdl_gate_bwd", sv.gate_a, sv.gate_b, dlogit, pw.vec("wc"), M, H, sv.p_gate, opt.seed, dpre, M * H * 1024, npl,
          g("ba"), g("bb"), g("wc"), g("bc"), st)
-    dh3_attn = gemm_nt(dpre, 1024, pw.planes("wabT"), C, nsplit, grp_n_cols=HID, a_koff=1024)
+    zdt = _act_dtype(opt.precision)
+    dh3_attn = gemm_nt(dpre, 1024, pw.planes("wabT"), C, nsplit, grp_n_cols=HID, a_koff=1024, out_dtype=zdt)
     gemm_tn_accum(dpre, sv.h3, g("wab"), nsplit, grp_m_rows=1024, b_coff=HID)
     del dpre
 
@@ -466,14 +481,14 @@ def encoder_backward(sv, d_slide: Optional[torch.Tensor], d_logits: Optional[tor
         n_tok = tok_src.shape[1]
         d_tokens = d_tokens.reshape(n_tok, TOK).contiguous().float()
         dtp = split_planes(d_tokens, npl)
-        dh3_tok = gemm_nt(dtp, TOK, pw.planes("tpT"), C, nsplit)      # [n_tok, C]; compact when a token window is active
+        dh3_tok = gemm_nt(dtp, TOK, pw.planes("tpT"), C, nsplit, out_dtype=zdt)   # [n_tok, C]; compact under a token window
         gemm_tn_accum(dtp, tok_src, g("tp"), nsplit)
         call("mdl_colsum_f32", d_tokens, n_tok, TOK, g("btp"), st)
         if sv.h3_sel is not None:
             dh3_tok_rows = opt.token_sel_of_row
     if d_ref_feats is not None:
         # gradient w.r.t. the reference-order features → head-major, added as a second dh source
-        extra = d_ref_feats.float().reshape(M, HID, H).transpose(1, 2).contiguous().view(M, C)
+        extra = d_ref_feats.float().reshape(M, HID, H).transpose(1, 2).contiguous().view(M, C).to(zdt)
         if dh3_tok_rows is not None:
             raise RuntimeError("madeleine_b200: a token window cannot be combined with gradients through the pre-attention features")
         dh3_tok = extra if dh3_tok is None else dh3_tok.add_(extra)
@@ -482,12 +497,12 @@ def encoder_backward(sv, d_slide: Optional[torch.Tensor], d_logits: Optional[tor
     dz3 = ln_gelu_bwd(sv.z3, pw.vec("g3"), pw.vec("be3"), sv.mean3, sv.rstd3, dh3_attn, dh3_tok, pool_terms, H, npl,
                       sv.p_pre, opt.seed, 3, g("g3"), g("be3"), g("b3"), dh_b_rows=dh3_tok_rows)
     del dh3_attn, dh3_tok
-    dh2 = gemm_nt(dz3, C, pw.planes("w3T"), HID, nsplit)
+    dh2 = gemm_nt(dz3, C, pw.planes("w3T"), HID, nsplit, out_dtype=zdt)
     gemm_tn_accum(dz3, sv.h2, g("w3"), nsplit)
     del dz3
     dz2 = ln_gelu_bwd(sv.z2, pw.vec("g2"), pw.vec("be2"), sv.mean2, sv.rstd2, dh2, None, [], 1, npl, sv.p_pre, opt.seed, 2,
                       g("g2"), g("be2"), g("b2"))
-    dh1 = gemm_nt(dz2, HID, pw.planes("w2T"), HID, nsplit)
+    dh1 = gemm_nt(dz2, HID, pw.planes("w2T"), HID, nsplit, out_dtype=zdt)
     gemm_tn_accum(dz2, sv.h1, g("w2"), nsplit)
     G = torch.zeros(R, HID, dtype=torch.float32, device=dev) if opt.se_dim > 0 else None   # per-bag column sums of dz1
     dz1 = ln_gelu_bwd(sv.z1, pw.vec("g1"), pw.vec("be1"), sv.mean1, sv.rstd1, dh1, None, [], 1, npl, sv.p_pre, opt.seed, 1,

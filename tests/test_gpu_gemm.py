@@ -26,6 +26,22 @@ def ref_nt(ap, bp, nsplit):
 
 
 @pytest.mark.parametrize("nsplit", [1, 3])
+@pytest.mark.parametrize("M,N,K", [(300, 512, 512), (1000, 2048, 512), (257, 128, 2048), (512, 512, 2048)])
+def test_gemm_nt_bf16_output_is_the_rounded_fp32_output(M, N, K, nsplit):
+    """out_bf16 (bf16 mode: Linear outputs as autocast returns them) = round-to-nearest of the fp32 result, bias included;
+    covers the single-CTA and CTA-pair store epilogues."""
+    npl = 2 if nsplit == 3 else 1
+    torch.manual_seed(M + N + K)
+    A = torch.randn(M, K, device=DEV)
+    B = torch.randn(N, K, device=DEV)
+    bias = torch.randn(N, device=DEV)
+    ap, bp = ops.split_planes(A, npl), ops.split_planes(B, npl)
+    out32 = ops.gemm_nt(ap, K, (bp, N, K, N * K), N, nsplit, bias=bias)
+    out16 = ops.gemm_nt(ap, K, (bp, N, K, N * K), N, nsplit, bias=bias, out_dtype=torch.bfloat16)
+    assert out16.dtype == torch.bfloat16 and torch.equal(out16, out32.bfloat16())
+
+
+@pytest.mark.parametrize("nsplit", [1, 3])
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 512), (300, 512, 512), (1000, 2048, 512), (257, 128, 2048),
                                    (64, 128, 128), (4096, 512, 2048)])
 def test_gemm_nt(M, N, K, nsplit):

@@ -150,6 +150,34 @@ def test_ln_gelu_bwd_per_bag_sums(lens):
     torch.testing.assert_close(acc[2], G.sum(0), rtol=1e-4, atol=1e-3)
 
 
+@pytest.mark.parametrize("C", [512, 2048])
+def test_ln_gelu_bf16_activations_equal_fp32_kernels_on_rounded_inputs(C):
+    """bf16 mode stores the pre-LayerNorm activations and the dgrad outputs as bf16: the kernels must give exactly what the
+    fp32-input kernels give on the same (bf16-representable) values."""
+    M, H, R = 777, 4 if C == 2048 else 1, 3
+    z16 = (torch.randn(M, C, device=DEV) * 2).bfloat16()
+    g = 1 + 0.1 * torch.randn(C, device=DEV)
+    b = 0.1 * torch.randn(C, device=DEV)
+    p16, mean16, rstd16 = ops.ln_gelu_fwd(z16, g, b, 1, 0.1, 77, 2)
+    p32, mean32, rstd32 = ops.ln_gelu_fwd(z16.float(), g, b, 1, 0.1, 77, 2)
+    assert torch.equal(p16, p32) and torch.equal(mean16, mean32) and torch.equal(rstd16, rstd32)
+    dh_a = torch.randn(M, C, device=DEV).bfloat16()
+    dh_b = torch.randn(M, C, device=DEV).bfloat16()
+    p = torch.rand(M, H, device=DEV)
+    dS = torch.randn(R, C, device=DEV)
+    seg = torch.randint(0, R, (M,), device=DEV, dtype=torch.int32)
+    res = []
+    for cast in (lambda t: t, lambda t: t.float()):
+        acc = [torch.zeros(C, device=DEV) for _ in range(3)]
+        dz = ops.ln_gelu_bwd(cast(z16), g, b, mean16, rstd16, cast(dh_a), cast(dh_b), [(p, dS, seg)], H, 1, 0.1, 77, 2, *acc)
+        res.append((dz, acc))
+    assert torch.equal(res[0][0], res[1][0])
+    for a0, a1 in zip(res[0][1], res[1][1]):
+        torch.testing.assert_close(a0, a1, rtol=1e-4, atol=1e-3)
+    with pytest.raises(RuntimeError, match="dtype"):
+        ops.ln_gelu_bwd(z16, g, b, mean16, rstd16, dh_a.float(), None, [], H, 1, 0.0, 0, 1, *[torch.zeros(C, device=DEV) for _ in range(3)])
+
+
 def test_gather_rows_planes():
     M, C = 777, 2048
     x = torch.randn(M, C, device=DEV)

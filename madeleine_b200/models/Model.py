@@ -124,7 +124,7 @@ class ABMILEmbedder(nn.Module):
         key = (precision, str(dev), se_dim)
         spec = self._spec_cache.get((str(dev), se_dim))
         if spec is None:
-            spec = ops.PackSpec([tuple(p.shape) for p in params], self.n_heads, d_in_total, dev)
+            spec = ops.PackSpec([tuple(p.shape) for p in params], self.n_heads, d_in_total, dev, d_in=d_in)
             self._spec_cache[(str(dev), se_dim)] = spec
         versions = tuple((p.data_ptr(), p._version) for p in params)
         cached = self._pack_cache.get(key)
@@ -134,6 +134,9 @@ class ABMILEmbedder(nn.Module):
         else:
             pw = cached[1]
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        if need_grad and d_in % 128 != 0:
+            raise NotImplementedError(f"training needs a feature width that is a multiple of 128 (got {d_in}); "
+                                      "inference works for any multiple of 64")
         ops._step_counter[0] += 1
         seed = (torch.initial_seed() * 1000003 + ops._step_counter[0]) & 0x7FFFFFFFFFFFFFFF
         opt = ops.EncodeOptions(n_heads=self.n_heads, activation=self.attention_params["params"]["activation"],

@@ -70,8 +70,11 @@ class _Seg:
 class PackSpec:
     """Index maps from kernel-layout buffers into a flat 'master' concatenation of the module parameters."""
 
-    def __init__(self, param_shapes: Sequence[Tuple[int, ...]], n_heads: int, d_in_total: int, device):
+    def __init__(self, param_shapes: Sequence[Tuple[int, ...]], n_heads: int, d_in_total: int, device, d_in: Optional[int] = None):
+        """d_in_total = columns of pre_attn.0.weight (patch features + stain-encoding channels); d_in = patch features alone
+        (the GEMM operand; the stain columns act through a per-bag bias).  Defaults to d_in_total."""
         H = n_heads
+        d_in = d_in_total if d_in is None else d_in
         C = HID * H
         self.n_heads, self.C, self.d_in_total = H, C, d_in_total
         offs, o = [], 0
@@ -97,7 +100,7 @@ class PackSpec:
             return base + rows_src[:, None] * ld + cols_src[None, :]
 
         k512 = ar(HID)
-        w1 = mat(off("pre0.w"), ar(HID), k512, d_in_total)                 # [512, 512] (stain columns excluded)
+        w1 = mat(off("pre0.w"), ar(HID), ar(d_in), d_in_total)             # [512, d_in] (stain columns excluded)
         w2 = mat(off("pre4.w"), ar(HID), k512, HID)
         w3 = mat(off("pre8.w"), perm, k512, HID)                           # [2048, 512] head-major rows
         # gated weights: packed row p = h*1024 + g*256 + is_b*128 + i, gate column j = g*128 + i
@@ -352,7 +355,7 @@ def encoder_forward(x: torch.Tensor, cu: torch.Tensor, codes: Optional[torch.Ten
     # the reference's --precision bfloat16 runs (trainer.py:108); the fp32-grade modes keep them fp32
     zdt = _act_dtype(opt.precision)
     xp = split_planes(x, npl)
-    z1 = gemm_nt(xp, HID, pw.planes("w1"), HID, nsplit, bias=pw.vec("b1"), rowbias=rowbias, row2bag=row2bag, out_dtype=zdt)
+    z1 = gemm_nt(xp, opt.d_in, pw.planes("w1"), HID, nsplit, bias=pw.vec("b1"), rowbias=rowbias, row2bag=row2bag, out_dtype=zdt)
     h1, mean1, rstd1 = ln_gelu_fwd(z1, pw.vec("g1"), pw.vec("be1"), npl, p_pre, opt.seed, 1)
     z2 = gemm_nt(h1, HID, pw.planes("w2"), HID, nsplit, bias=pw.vec("b2"), out_dtype=zdt)
     h2, mean2, rstd2 = ln_gelu_fwd(z2, pw.vec("g2"), pw.vec("be2"), npl, p_pre, opt.seed, 2)
@@ -507,7 +510,13 @@ def encoder_backward(sv, d_slide: Optional[torch.Tensor], d_logits: Optional[tor
     G = torch.zeros(R, HID, dtype=torch.float32, device=dev) if opt.se_dim > 0 else None   # per-bag column sums of dz1
     dz1 = ln_gelu_bwd(sv.z1, pw.vec("g1"), pw.vec("be1"), sv.mean1, sv.rstd1, dh1, None, [], 1, npl, sv.p_pre, opt.seed, 1,
                       g("g1"), g("be1"), g("b1"), row2bag=sv.row2bag if G is not None else None, bag_dz=G)
-    gemm_tn_accum(dz1, sv.xp, g("w1"), nsplit)
+    if opt.d_in % 256 == 0:
+        gemm_tn_accum(dz1, sv.xp, g("w1"), nsplit)
+    else:
+        # the wgrad tile is 128 x 256: for feature widths that are a multiple of 128 only (384, 640, ...) compute dW1^T
+        w1t = torch.zeros(opt.d_in, HID, dtype=torch.float32, device=dev)
+        gemm_tn_accum(sv.xp, dz1, w1t, nsplit)
+        g("w1").add_(w1t.t())
 
     gmaster = torch.zeros(spec.master_numel, dtype=torch.float32, device=dev)
     # scatter packed grads into parameter layout (gr_pos → gr_dst): gather the compact list, then scatter

@@ -297,6 +297,58 @@ def test_token_window_too_small_raises(golden):
             GOT(toks["HE"][:, :, :, 0], toks[mods[1]], subsample=256)
 
 
+@pytest.mark.parametrize("d_in,se", [(1024, False), (768, True), (384, False), (1536, True), (128, True)])
+def test_other_patch_embedding_widths_against_oracle(d_in, se):
+    """config.patch_embedding_dim is free in the reference (Model.py:60-64); any multiple of 64 is built here.  Forward,
+    loss and gradients against the CPU oracle for UNI-style 1024-d, 768-d (+ stain encodings), 384-d, 1536-d and 128-d
+    features (training needs a multiple of 128, inference a multiple of 64)."""
+    import oracle
+    mods = ["HE", "ER", "PR"]
+    bs, T = 3, 40
+    c = Namespace(MODALITIES=mods, wsi_encoder="abmil", patch_embedding_dim=d_in, wsi_encoder_hidden_dim=512,
+                  activation="softmax", n_heads=4, b200_precision="fp32")
+    sd = make_state_dict(21, n_mod=3, stain_encoding=se, d_in=d_in)
+    model = MADELEINE(c, stain_encoding=se)
+    model.load_state_dict(sd, strict=True)
+    model.to(DEV).eval()
+    feats = make_feats(d_in, bs, 3, T, d_in)
+    labels = torch.ones(bs, 3)
+    args = Namespace(global_loss="info-nce", symmetric_cl=True, local_loss_weight=1.0)
+    embs, toks = model({"feats": feats}, DEV, train=True, n_views=1)
+    torch.manual_seed(5)
+    loss, _ = calculate_losses(mods[1:], InfoNCE(temperature=0.1), GOT, None, embs, toks, labels[:, 1:], args)
+    loss.backward()
+    sd_o = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    embs_o, toks_o = oracle.madeleine_forward_train(sd_o, feats, mods, stain_encoding=se)
+    torch.manual_seed(5)
+    loss_o, _ = oracle.calculate_losses(mods[1:], embs_o, toks_o, labels[:, 1:], temperature=0.1, symmetric=True, use_local=True)
+    loss_o.backward()
+    for m in mods:
+        close(embs[m], embs_o[m].detach())
+        close(toks[m], toks_o[m].detach())
+    close(loss, loss_o.detach(), rtol=1e-3, atol=1e-3)
+    for name, p in model.named_parameters():
+        ref = sd_o[name].grad
+        if ref is None or float(ref.norm()) < 1e-5:
+            continue
+        assert float((p.grad.cpu() - ref).norm() / ref.norm()) < 5e-2, name
+
+
+def test_inference_width_64_and_training_width_check():
+    import oracle
+    c = Namespace(MODALITIES=["HE"], wsi_encoder="abmil", patch_embedding_dim=64, wsi_encoder_hidden_dim=512,
+                  activation="softmax", n_heads=4, b200_precision="fp32")
+    sd = make_state_dict(2, n_mod=1, d_in=64)
+    model = MADELEINE(c, stain_encoding=False)
+    model.load_state_dict(sd, strict=True)
+    model.to(DEV).eval()
+    feats = make_feats(64, 2, 50, 64)
+    with torch.no_grad():
+        close(model.encode_he(feats, DEV), oracle.encode_he(sd, feats))
+    with pytest.raises(NotImplementedError, match="multiple of 128"):
+        model.encode_he(feats, DEV)                      # grad mode: the first-layer wgrad has no 64-wide tile
+
+
 def test_bf16_mode_training_step(golden):
     """bf16 mode end to end (1-pass GEMMs, bf16 Linear outputs and dgrad results — the reference's autocast recipe): loss
     within the bf16 tolerance of the reference's fp32 fixture at tau = 0.1-scale logits, gradients norm-wise close to the

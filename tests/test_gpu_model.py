@@ -97,6 +97,59 @@ def test_ragged_packed(golden):
     close(out, g["encode_he"])
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_ragged_packed_with_stain_codes_fwd_bwd_against_oracle(seed):
+    """forward_packed on random ragged bags (length 1 included) with per-bag stain codes: slide embeddings, token embeddings
+    and parameter gradients against the oracle evaluated bag by bag with the stain encoding concatenated (Model.py:125-132)."""
+    import oracle
+    mods = ["HE", "ER", "PR", "KI67"]
+    g = torch.Generator().manual_seed(100 + seed)
+    R = 7
+    lens = [1] + torch.randint(1, 300, (R - 1,), generator=g).tolist()
+    codes = torch.randint(0, len(mods), (R,), generator=g).tolist()
+    sd = make_state_dict(40 + seed, n_mod=len(mods), stain_encoding=True)
+    model = MADELEINE(cfg(mods), stain_encoding=True)
+    model.load_state_dict(sd, strict=True)
+    model.to(DEV).eval()
+    x = make_feats(seed, sum(lens), 512)
+    cu = [0]
+    for n in lens:
+        cu.append(cu[-1] + n)
+    slide, tokens = model.forward_packed(x.to(DEV), torch.tensor(cu, dtype=torch.int32), stain_codes=codes)
+    ws = torch.randn(slide.shape, generator=g)
+    wt = torch.randn(tokens.shape, generator=g)
+    ((slide * ws.to(DEV)).sum() + (tokens * wt.to(DEV)).sum()).backward()
+    sd_o = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    s_ref, t_ref = [], []
+    for r in range(R):
+        bag = x[cu[r]:cu[r + 1]]
+        enc = sd_o["embedding.weight"][codes[r]].unsqueeze(0).expand(bag.shape[0], -1)
+        sl, tok, _ = oracle.abmil_embedder(sd_o, torch.cat([bag, enc], dim=-1).unsqueeze(0))
+        s_ref.append(torch.nn.functional.linear(sl.reshape(1, -1), sd_o["projector.weight"], sd_o["projector.bias"]))
+        t_ref.append(torch.nn.functional.linear(tok.reshape(bag.shape[0], -1), sd_o["token_projector.weight"], sd_o["token_projector.bias"]))
+    s_ref, t_ref = torch.cat(s_ref), torch.cat(t_ref)
+    ((s_ref * ws).sum() + (t_ref * wt).sum()).backward()
+    close(slide, s_ref.detach())
+    close(tokens, t_ref.detach())
+    for name, p in model.named_parameters():
+        ref = sd_o[name].grad
+        if ref is None or float(ref.norm()) < 1e-5:
+            continue
+        assert float((p.grad.cpu() - ref).norm() / ref.norm()) < 2e-2, name
+
+
+def test_long_bag_inference_against_oracle():
+    """One slide of 30 000 patches (large WSIs at 20x reach this): single-bag softmax over many token chunks."""
+    import oracle
+    sd = make_state_dict(8, n_mod=1)
+    model = build(["HE"], False, 8)
+    x = make_feats(3, 1, 30000, 512)
+    with torch.no_grad():
+        out = model.encode_he(x, DEV)
+        ref = oracle.encode_he(sd, x)
+    close(out, ref)
+
+
 @pytest.mark.parametrize("tag", ["plain", "stain_enc"])
 def test_forward_train(golden, tag):
     g = golden("forward_train")[tag]
@@ -332,6 +385,31 @@ def test_other_patch_embedding_widths_against_oracle(d_in, se):
         if ref is None or float(ref.norm()) < 1e-5:
             continue
         assert float((p.grad.cpu() - ref).norm() / ref.norm()) < 5e-2, name
+
+
+@pytest.mark.parametrize("activation", ["leaky_relu", "relu", "sigmoid"])
+def test_embedder_activation_variants_against_oracle(activation):
+    """config.activation other than softmax (abmil.py:54-63): ABMILEmbedder forward and parameter gradients vs the oracle."""
+    import oracle
+    c = Namespace(MODALITIES=["HE"], wsi_encoder="abmil", patch_embedding_dim=512, wsi_encoder_hidden_dim=512,
+                  activation=activation, n_heads=4, b200_precision="fp32")
+    sd = make_state_dict(31, n_mod=1)
+    model = MADELEINE(c, stain_encoding=False)
+    model.load_state_dict(sd, strict=True)
+    model.to(DEV).eval()
+    x = make_feats(77, 2, 37, 512)
+    slide = model.wsi_embedders(x.to(DEV))                       # [B, E, H]
+    w = torch.randn(slide.shape, generator=torch.Generator().manual_seed(1))
+    (slide * w.to(DEV)).sum().backward()
+    sd_o = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    slide_o, _, _ = oracle.abmil_embedder(sd_o, x, activation=activation)
+    (slide_o * w).sum().backward()
+    close(slide, slide_o.detach(), rtol=1e-3, atol=1e-3)
+    for name, p in model.named_parameters():
+        ref = sd_o[name].grad
+        if ref is None or p.grad is None or float(ref.norm()) < 1e-5:
+            continue
+        assert float((p.grad.cpu() - ref).norm() / ref.norm()) < 2e-2, name
 
 
 def test_inference_width_64_and_training_width_check():

@@ -407,6 +407,33 @@ def test_infonce_golden(golden):
             torch.testing.assert_close(got, ref, rtol=1e-2, atol=1e-2 * float(ref.abs().max()) + 1e-6)
 
 
+@pytest.mark.parametrize("m", [65, 512, 1031])
+@pytest.mark.parametrize("symmetric", [True, False])
+def test_infonce_large_batches_against_fp64(m, symmetric):
+    """Global batches of 8 x 64 cases and more (sharded runs gather every rank's slide embeddings): loss and gradients
+    against an fp64 evaluation of loss.py:111-127."""
+    g = torch.Generator().manual_seed(m)
+    q = torch.randn(m, 512, generator=g)
+    k = q + 2.0 * torch.randn(m, 512, generator=g)      # cos ~ 0.45: a loss of order one, well-conditioned gradients
+    tau = 0.1
+    qd = q.double().to(DEV).requires_grad_(True)
+    kd = k.double().to(DEV).requires_grad_(True)
+    qn, kn = torch.nn.functional.normalize(qd, dim=-1), torch.nn.functional.normalize(kd, dim=-1)
+    logits = qn @ kn.t() / tau
+    labels = torch.arange(m, device=DEV)
+    ref = torch.nn.functional.cross_entropy(logits, labels)
+    if symmetric:
+        ref = 0.5 * ref + 0.5 * torch.nn.functional.cross_entropy(logits.t(), labels)
+    ref.backward()
+    a = q.to(DEV).requires_grad_(True)
+    b = k.to(DEV).requires_grad_(True)
+    loss = ops.info_nce(a, b, temperature=tau, reduction="mean", symmetric=symmetric)
+    loss.backward()
+    torch.testing.assert_close(loss.double(), ref.detach(), rtol=1e-4, atol=1e-5)
+    for got, want in ((a.grad, qd.grad), (b.grad, kd.grad)):
+        assert float((got.double() - want).norm() / want.norm()) < 1e-3
+
+
 def test_infonce_reductions():
     q = torch.randn(9, 512, device=DEV, requires_grad=True)
     k = torch.randn(9, 512, device=DEV, requires_grad=True)

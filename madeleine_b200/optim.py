@@ -54,4 +54,8 @@ class FusedAdamW(torch.optim.Optimizer):
                 call("mdl_adamw_step", n, ctypes.cast(P, ctypes.c_void_p), ctypes.cast(G, ctypes.c_void_p),
                      ctypes.cast(M, ctypes.c_void_p), ctypes.cast(V, ctypes.c_void_p), ctypes.cast(N, ctypes.c_void_p),
                      lr, beta1, beta2, group["eps"], group["weight_decay"], step, 1.0, stream_ptr(chunk[0].device))
+            # the kernel wrote the parameters behind autograd's back: bump their version counters so that everything keyed
+            # on them sees the update (the encoder re-packs its bf16 operand planes when a parameter's version changes)
+            for p in ps:
+                torch.autograd.graph.increment_version(p)
         return loss

@@ -521,6 +521,28 @@ def test_fused_adamw_matches_torch():
         torch.testing.assert_close(b, a, rtol=1e-5, atol=1e-6)
 
 
+def test_fused_adamw_step_reaches_the_packed_weights():
+    """The optimiser kernel writes parameters through raw pointers; the encoder must still notice (version counters) and
+    re-pack its bf16 operand planes — i.e. the model's output after optimizer.step() equals that of a fresh model holding
+    the updated parameters."""
+    from madeleine_b200.optim import FusedAdamW
+    model = build(["HE"], False, 3).train(False)
+    x = make_feats(1, 2, 64, 512)
+    opt = FusedAdamW(model.parameters(), lr=1e-2)
+    out0 = model.encode_he(x, DEV)
+    out0.square().sum().backward()
+    opt.step()
+    with torch.no_grad():
+        out1 = model.encode_he(x, DEV)
+    fresh = MADELEINE(cfg(["HE"]), stain_encoding=False)
+    fresh.load_state_dict({k: v.detach().cpu() for k, v in model.state_dict().items()}, strict=True)
+    fresh.to(DEV).eval()
+    with torch.no_grad():
+        want = fresh.encode_he(x, DEV)
+    assert not torch.allclose(out1, out0.detach())
+    assert torch.equal(out1, want)
+
+
 @pytest.mark.parametrize("scale,offset", [(10.0, 0.0), (0.01, 0.0), (1.0, 3.0), (30.0, -5.0)])
 def test_encode_he_input_scale_robustness(scale, offset):
     """CONCH features are un-normalised ViT outputs: parity must not depend on the input scale / mean.

@@ -117,3 +117,23 @@ def test_run_inference_output_format():
     with torch.no_grad():
         want = model.encode_he(loader[1][0], DEV).cpu().numpy()
     np.testing.assert_allclose(res["embeds"][1], want[0], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("activation", ["softmax", "sigmoid"])
+def test_standalone_batched_abmil_head(activation):
+    """BatchedABMIL used on its own (abmil.py:41-68): activated attention and raw logits against plain torch math."""
+    from madeleine.models.abmil import BatchedABMIL
+    torch.manual_seed(3)
+    head = BatchedABMIL(input_dim=512, hidden_dim=512, dropout=True, n_classes=1, n_heads=1, activation=activation).to(DEV).eval()
+    x = torch.randn(2, 77, 512, device=DEV)
+    with torch.no_grad():
+        act, raw = head(x, return_raw_attention=True)
+        a = torch.tanh(torch.nn.functional.linear(x.double(), head.attention_a[0].weight.double(), head.attention_a[0].bias.double()))
+        b = torch.sigmoid(torch.nn.functional.linear(x.double(), head.attention_b[0].weight.double(), head.attention_b[0].bias.double()))
+        ref = torch.nn.functional.linear(a * b, head.attention_c.weight.double(), head.attention_c.bias.double())
+    assert raw.shape == (2, 77, 1) and act.shape == (2, 77, 1)
+    torch.testing.assert_close(raw.double(), ref, rtol=1e-3, atol=1e-4)
+    want = torch.softmax(ref, dim=1) if activation == "softmax" else torch.sigmoid(ref)
+    torch.testing.assert_close(act.double(), want, rtol=1e-3, atol=1e-5)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        head(x.cpu())

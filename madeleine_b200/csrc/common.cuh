@@ -6,6 +6,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 
 namespace mdl {
 
@@ -35,6 +36,20 @@ const char* get_last_error();
     } while (0)
 
 #define MDL_CHECK_LAUNCH() MDL_CHECK_CUDA(cudaGetLastError())
+
+// Function attributes (opt-in dynamic shared memory) belong to a device, not to the process: a host that drives several
+// GPUs from one process (nn.DataParallel replicas, one thread per GPU) must set them on each.  One bit per device ordinal;
+// setting an attribute twice from racing threads is harmless.
+struct PerDeviceOnce {
+    std::atomic<unsigned long long> done{0};
+    bool needed(unsigned long long& bit) const {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        bit = 1ull << (dev & 63);
+        return (done.load(std::memory_order_acquire) & bit) == 0;
+    }
+    void mark(unsigned long long bit) { done.fetch_or(bit, std::memory_order_release); }
+};
 
 // ---------------------------------------------------------------------------------------------------
 // small math

@@ -243,10 +243,11 @@ gemm2_kf_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 template <int EPI, bool kMN>
 static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t stream) {
     auto kern = gemm2_kf_kernel<EPI, kMN>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;   // per instantiation and per device
+    unsigned long long dev_bit;
+    if (attr_set.needed(dev_bit)) {
         MDL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2::TOTAL));
-        attr_set = true;
+        attr_set.mark(dev_bit);
     }
     const int units = args.num_m_tiles * (args.num_n_tiles / args.n_inner) * args.ksplit;
     if (units == 0) return 0;

@@ -288,10 +288,11 @@ template <int BLOCK_N, int MODE, int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t stream) {
     using L = SmemLayout<BLOCK_N>;
     auto kern = gemm_tcgen05_kernel<BLOCK_N, MODE, EPI>;
-    static bool attr_set = false;  // per instantiation
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;   // per instantiation and per device
+    unsigned long long dev_bit;
+    if (attr_set.needed(dev_bit)) {
         MDL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-        attr_set = true;
+        attr_set.mark(dev_bit);
     }
     const int units = args.num_m_tiles * (args.num_n_tiles / args.n_inner) * args.ksplit;
     if (units == 0) return 0;

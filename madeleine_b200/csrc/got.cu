@@ -614,10 +614,11 @@ int mdl_got_extrema(const float* v, const float* q, int m, int n, int D, void* w
     if (got_use_big(n)) return got_big_extrema(v, q, m, n, D, workspace, extrema, st);
     GotLayout lay(m, n, D, got_use_big(n));
     const size_t smem = sizeof(float) * (size_t)2 * n * (D + 1);
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    unsigned long long dev_bit;
+    if (attr.needed(dev_bit)) {
         MDL_CHECK_CUDA(cudaFuncSetAttribute(got_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * 2 * GOT_NMAX * 129)));
-        attr = true;
+        attr.mark(dev_bit);
     }
     got_cost_kernel<<<m, GOT_THREADS, smem, st>>>(v, q, lay, (float*)workspace);
     MDL_CHECK_LAUNCH();
@@ -625,11 +626,12 @@ int mdl_got_extrema(const float* v, const float* q, int m, int n, int D, void* w
 }
 
 static int got_set_attrs() {
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    unsigned long long dev_bit;
+    if (attr.needed(dev_bit)) {
         MDL_CHECK_CUDA(cudaFuncSetAttribute(got_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)main_smem_bytes(GOT_NMAX)));
         MDL_CHECK_CUDA(cudaFuncSetAttribute(got_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * (2 * GOT_NMAX * 129 + 2 * GOT_NMAX))));
-        attr = true;
+        attr.mark(dev_bit);
     }
     return 0;
 }

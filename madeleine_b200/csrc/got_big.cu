@@ -585,13 +585,14 @@ static size_t big_main_smem_bytes(int n) {
 }
 
 static int big_set_attrs() {
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    unsigned long long dev_bit;
+    if (attr.needed(dev_bit)) {
         MDL_CHECK_CUDA(cudaFuncSetAttribute(got_cost_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)(sizeof(float) * GOT_BIG_NMAX * 129)));
         MDL_CHECK_CUDA(cudaFuncSetAttribute(got_main_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)big_main_smem_bytes(GOT_BIG_NMAX)));
-        attr = true;
+        attr.mark(dev_bit);
     }
     return 0;
 }

@@ -121,6 +121,12 @@ class SimpleDataset(Dataset):
         return load_features(os.path.join(self.features_path, name)), os.path.splitext(name)[0]
 
 
+def simple_collate(batch):
+    """wsi_dataset.py:122-125: (features, slide_id) items → ([bs, N, D] stacked features, list of ids)."""
+    feats, ids = zip(*batch)
+    return torch.stack(feats), list(ids)
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # HBM-resident store + on-device resampling
 # ----------------------------------------------------------------------------------------------------------------------

@@ -43,6 +43,38 @@ def run_inference(ssl_model, val_dataloader, config=None, torch_precision=None):
     return {"embeds": all_embeds, "slide_ids": all_slide_ids}, rank
 
 
+def extract_slide_level_embeddings(args, val_dataloaders, ssl_model):
+    """utils.py:68-90: run_inference on every downstream loader and pickle ``{"embeds", "slide_ids"}`` to
+    ``<RESULS_SAVE_PATH>/<dataset>.pkl`` (the rank goes to wandb when ``args.log_ml``)."""
+    from .file_utils import save_pkl
+    for dataset_name, loader in val_dataloaders.items():
+        print(f"\n* Extracting slide-level embeddings of {dataset_name}")
+        results, rank = run_inference(ssl_model, loader, config=args)
+        print(f"Rank for {dataset_name} = {rank}")
+        print("\033[92mDone \033[0m")
+        if getattr(args, "log_ml", False):
+            import wandb
+            wandb.run.summary[f"{dataset_name}_rank"] = rank
+        save_pkl(os.path.join(args.RESULS_SAVE_PATH, f"{dataset_name}.pkl"), results)
+
+
+def set_deterministic_mode(SEED, disable_cudnn=False):
+    """utils.py:147-178: seed torch (CPU + every GPU), python and numpy.  The B200 kernels draw their dropout masks from
+    torch's seed (ops.py: ``torch.initial_seed()``), so this makes a run repeatable end to end; cuDNN plays no part in the
+    hot path, the flags are set only for whatever else the caller runs."""
+    import random
+    torch.manual_seed(SEED)
+    random.seed(SEED)
+    np.random.seed(SEED)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(SEED)
+    if not disable_cudnn:
+        torch.backends.cudnn.benchmark = False
+        torch.backends.cudnn.deterministic = True
+    else:
+        torch.backends.cudnn.enabled = False
+
+
 def load_checkpoint(args, ssl_model, path_to_checkpoint=None):
     """utils.py:92-122: strict load, retrying with the DataParallel ``module.`` prefix stripped."""
     path = path_to_checkpoint if path_to_checkpoint is not None else os.path.join(args.RESULS_SAVE_PATH, "model.pt")

@@ -69,7 +69,7 @@ def _params(n_heads=4, se=True, n_mod=3):
 
 def test_pack_spec_index_maps():
     sd, ps = _params()
-    spec = ops.PackSpec([tuple(p.shape) for p in ps], 4, 544, "cpu")
+    spec = ops.PackSpec([tuple(p.shape) for p in ps], 4, 544, "cpu", d_in=512)
     master = torch.cat([p.reshape(-1) for p in ps])
     assert spec.master_numel == master.numel()
 

@@ -47,3 +47,52 @@ def test_module_construction_and_state_dict_keys():
     import pytest
     with pytest.raises(ValueError):
         MADELEINE(Namespace(**{**vars(cfg), "wsi_encoder": "transformer"}))
+
+
+def test_error_behaviour_matches_the_reference():
+    """ValueError for an unsupported encoder and for InfoNCE shape mismatches (Model.py:66-67, loss.py:66-89),
+    NotImplementedError for unknown aggregation / activation (Model.py:372,443; abmil.py:63) — all raised before any kernel."""
+    from argparse import Namespace
+    import pytest
+    from madeleine.models.Model import MADELEINE, ABMILEmbedder
+    from madeleine.models.abmil import BatchedABMIL
+    from madeleine.utils.loss import InfoNCE
+    cfg = dict(MODALITIES=["HE"], patch_embedding_dim=512, wsi_encoder_hidden_dim=512, activation="softmax", n_heads=4)
+    with pytest.raises(ValueError, match="abmil"):
+        MADELEINE(Namespace(wsi_encoder="transformer", **cfg))
+    loss = InfoNCE(temperature=0.1)
+    q = torch.zeros(4, 8)
+    with pytest.raises(ValueError, match="2 dimensions"):
+        loss(torch.zeros(4, 2, 8), q)
+    with pytest.raises(ValueError, match="same number of samples"):
+        loss(q, torch.zeros(5, 8))
+    with pytest.raises(ValueError, match="same number of components"):
+        loss(q, torch.zeros(4, 9))
+    with pytest.raises(ValueError, match="negative_keys"):
+        loss(q, q, negative_keys=torch.zeros(3, 2, 8))
+    assert loss(q, q, negative_keys=torch.zeros(3, 8)) is None          # the reference's explicit-negatives branch returns None
+    emb = ABMILEmbedder({"input_dim": 512, "hidden_dim": 512},
+                        {"model": "ABMIL", "params": {"input_dim": 512, "hidden_dim": 512, "dropout": True, "activation": "softmax",
+                                                      "n_heads": 4, "n_classes": 1}}, aggregation="max")
+    with pytest.raises(NotImplementedError, match="Agg type"):
+        emb(torch.zeros(1, 4, 512))
+    with pytest.raises(NotImplementedError, match="Attention model"):
+        ABMILEmbedder({"input_dim": 512, "hidden_dim": 512}, {"model": "TransMIL", "params": {"n_heads": 4}})
+    with pytest.raises(NotImplementedError, match="Activation"):
+        BatchedABMIL(512, 512, activation="gelu")(torch.zeros(1, 4, 512))
+    model = MADELEINE(Namespace(wsi_encoder="abmil", **cfg))
+    keys = set(model.state_dict())
+    assert len(keys) == 40 and "wsi_embedders.attn.3.attention_c.bias" in keys and "token_projector.weight" in keys
+
+
+def test_state_dict_layout_with_stain_encodings():
+    from argparse import Namespace
+    from madeleine.models.Model import MADELEINE
+    cfg = Namespace(MODALITIES=["HE", "A", "B"], wsi_encoder="abmil", patch_embedding_dim=512, wsi_encoder_hidden_dim=512,
+                    activation="softmax", n_heads=4)
+    sd = MADELEINE(cfg, stain_encoding=True).state_dict()
+    assert len(sd) == 41 and tuple(sd["embedding.weight"].shape) == (3, 32)      # 40 tensors + the stain embedding table
+    assert tuple(sd["wsi_embedders.pre_attn.0.weight"].shape) == (512, 544)
+    want = (128 * 2048 + 128) + (512 * 544 + 512) + (512 * 512 + 512) + (2048 * 512 + 2048) + 2 * (512 + 512 + 2048) \
+        + 4 * (2 * (512 * 512 + 512) + 512 + 1) + (512 * 2048 + 512) + 3 * 32
+    assert sum(v.numel() for v in sd.values()) == want == 5013284 - 2 * 32        # SURVEY §8a1 quotes the 5-modality count

@@ -107,6 +107,9 @@ gemm2_kf_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_generic;
 
+    // p.nsplit == 1 (bf16 mode, or the backward pass of fp32_fwd): one plane, a stage carries 64 of k; p.k_blocks counts stages
+    const bool one_pass = p.nsplit == 1;
+    const int kstep = one_pass ? 2 : 1;
     const int n_groups = p.num_n_tiles / p.n_inner;
     const int num_units = p.num_m_tiles * n_groups * p.ksplit;     // m tiles of 256 rows
     const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
@@ -138,18 +141,24 @@ gemm2_kf_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         const uint32_t leader_full = full_bar(stage) & kPeerMask;
                         if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * L::STAGE_BYTES);
                         const int row_a = m_tile * 256 + rank * 128, row_b = n_tile * BLOCK_N + rank * 128;
+                        // the two half-slots of a stage: 3-pass = (hi, lo) planes of one 32-wide k-block;
+                        // 1-pass = two consecutive 32-wide k-blocks of the only plane
+                        const int kc0 = kb * BLOCK_KF * kstep;
+                        const int kc1 = one_pass ? kc0 + BLOCK_KF : kc0;
+                        const int pl1 = one_pass ? 0 : 1;
                         if constexpr (!kMN) {
-                            tma_load_3d_2sm(sa, &tmap_a, leader_full, a_k0 + kb * BLOCK_KF, row_a, 0);
-                            tma_load_3d_2sm(sa + L::A_BYTES / 2, &tmap_a, leader_full, a_k0 + kb * BLOCK_KF, row_a, 1);
-                            tma_load_3d_2sm(sb, &tmap_b, leader_full, kb * BLOCK_KF, row_b, 0);
-                            tma_load_3d_2sm(sb + L::B_BYTES / 2, &tmap_b, leader_full, kb * BLOCK_KF, row_b, 1);
+                            tma_load_3d_2sm(sa, &tmap_a, leader_full, a_k0 + kc0, row_a, 0);
+                            tma_load_3d_2sm(sa + L::A_BYTES / 2, &tmap_a, leader_full, a_k0 + kc1, row_a, pl1);
+                            tma_load_3d_2sm(sb, &tmap_b, leader_full, kc0, row_b, 0);
+                            tma_load_3d_2sm(sb + L::B_BYTES / 2, &tmap_b, leader_full, kc1, row_b, pl1);
                         } else {
 #pragma unroll
                             for (int pl = 0; pl < 2; ++pl) {
+                                const int tok = pl == 0 ? kc0 : kc1, plane = pl == 0 ? 0 : pl1;
 #pragma unroll
                                 for (int j = 0; j < 2; ++j) {
-                                    tma_load_3d_2sm(sa + pl * (L::A_BYTES / 2) + j * BOX, &tmap_a, leader_full, row_a + 64 * j, kb * BLOCK_KF, pl);
-                                    tma_load_3d_2sm(sb + pl * (L::B_BYTES / 2) + j * BOX, &tmap_b, leader_full, b_c0 + row_b + 64 * j, kb * BLOCK_KF, pl);
+                                    tma_load_3d_2sm(sa + pl * (L::A_BYTES / 2) + j * BOX, &tmap_a, leader_full, row_a + 64 * j, tok, plane);
+                                    tma_load_3d_2sm(sb + pl * (L::B_BYTES / 2) + j * BOX, &tmap_b, leader_full, b_c0 + row_b + 64 * j, tok, plane);
                                 }
                             }
                         }
@@ -193,8 +202,12 @@ gemm2_kf_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                                 b_lo = make_umma_desc_sw128(sb + L::B_BYTES / 2 + k * (UMMA_K * 128), BOX, 1024);
                             }
                             umma_bf16_2cta(tmem_d, a_hi, b_hi, idesc, accumulate);
-                            umma_bf16_2cta(tmem_d, a_hi, b_lo, idesc, 1u);
-                            umma_bf16_2cta(tmem_d, a_lo, b_hi, idesc, 1u);
+                            if (one_pass) {
+                                umma_bf16_2cta(tmem_d, a_lo, b_lo, idesc, 1u);        // the second k-block of the stage
+                            } else {
+                                umma_bf16_2cta(tmem_d, a_hi, b_lo, idesc, 1u);
+                                umma_bf16_2cta(tmem_d, a_lo, b_hi, idesc, 1u);
+                            }
                             accumulate = 1;
                         }
                         umma_commit_2cta(empty_bar(stage));      // frees the slot in BOTH CTAs

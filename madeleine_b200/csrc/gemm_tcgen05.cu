@@ -327,6 +327,20 @@ static bool use_2cta() {
     }
     return v == 1;
 }
+// 1-pass (bf16) problems on the CTA-pair kernel.  Measured on the bench step (tools/step_breakdown.py --precision bf16): the
+// gated-attention GEMM gains 8 % (0.483 -> 0.443 ms; its epilogue math leaves the pair's halved operand traffic visible), the
+// store and wgrad GEMMs are output-bandwidth-bound at one pass and gain nothing (0.749 -> 0.772, 0.513 -> 0.516 ms).
+// MDL_GEMM_2CTA_BF16: 0 = never, 1 (default) = gated GEMM only, 2 = every 1-pass GEMM.
+static int cta_pair_1pass_level() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MDL_GEMM_2CTA_BF16");
+        v = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+    }
+    return v;
+}
+static bool use_2cta_1pass() { return cta_pair_1pass_level() >= 2; }
+static bool use_2cta_1pass_gated() { return cta_pair_1pass_level() >= 1; }
 
 }  // namespace mdl
 
@@ -346,15 +360,16 @@ int mdl_gemm_nt(const void* a_planes, long long a_rows, long long a_cols, long l
     const int planes = nsplit == 3 ? 2 : 1;
     const int bn = (N % 256 == 0) ? 256 : 128;
     const bool fused = nsplit == 3 && use_fused();
-    const bool two_cta = fused && bn == 256 && use_2cta() && g_debug_flags == 0;
-    const int bk = fused ? BLOCK_KF : BLOCK_K;
+    // the CTA-pair kernel also takes 1-pass problems (a stage then holds two k-blocks of the single plane)
+    const bool two_cta = (fused || (nsplit == 1 && use_fused() && use_2cta_1pass())) && bn == 256 && use_2cta() && g_debug_flags == 0;
+    const int bk = (fused || two_cta) ? BLOCK_KF : BLOCK_K;
     CUtensorMap ta, tb;
     int rc = make_plane_tmap(&ta, a_planes, a_rows, a_cols, lda, a_plane_stride, planes, BLOCK_M, bk);
     if (rc) return rc;
     rc = make_plane_tmap(&tb, b_planes, b_rows, b_cols, ldb, b_plane_stride, planes, two_cta ? 128 : bn, bk);
     if (rc) return rc;
     GemmArgs g{};
-    g.M = M; g.N = N; g.k_blocks = K / bk; g.nsplit = nsplit;
+    g.M = M; g.N = N; g.k_blocks = (two_cta && nsplit == 1) ? K / (2 * bk) : K / bk; g.nsplit = nsplit;
     g.num_m_tiles = (M + BLOCK_M - 1) / BLOCK_M; g.num_n_tiles = N / bn; g.n_inner = 1; g.ksplit = 1;
     MDL_REQUIRE(grp_n_cols <= 0 || grp_n_cols % bn == 0, "grp_n_cols (%d) must be a multiple of the N tile (%d)", grp_n_cols, bn);
     MDL_REQUIRE(ldc % 4 == 0, "ldc must be a multiple of 4");
@@ -387,15 +402,15 @@ int mdl_gemm_gated(const void* a_planes, long long a_rows, long long a_cols, lon
     const int planes = nsplit == 3 ? 2 : 1;
     const int K = 512, N = n_heads * 1024;
     const bool fused = nsplit == 3 && use_fused();
-    const bool two_cta = fused && use_2cta();
-    const int bk = fused ? BLOCK_KF : BLOCK_K;
+    const bool two_cta = (fused || (nsplit == 1 && use_fused() && use_2cta_1pass_gated())) && use_2cta();
+    const int bk = (fused || two_cta) ? BLOCK_KF : BLOCK_K;
     CUtensorMap ta, tb;
     int rc = make_plane_tmap(&ta, a_planes, a_rows, a_cols, lda, a_plane_stride, planes, BLOCK_M, bk);
     if (rc) return rc;
     rc = make_plane_tmap(&tb, b_planes, N, K, K, b_plane_stride, planes, two_cta ? 128 : 256, bk);
     if (rc) return rc;
     GemmArgs g{};
-    g.M = M; g.N = N; g.k_blocks = K / bk; g.nsplit = nsplit;
+    g.M = M; g.N = N; g.k_blocks = (two_cta && nsplit == 1) ? K / (2 * bk) : K / bk; g.nsplit = nsplit;
     g.num_m_tiles = (M + BLOCK_M - 1) / BLOCK_M; g.num_n_tiles = N / 256; g.n_inner = 4; g.ksplit = 1;
     g.grp_n_tiles = 4; g.a_koff = 512; g.grp_m_tiles = 1 << 30; g.b_coff = 0;
     g.ba = ba; g.bb = bb; g.wc = wc; g.bc = bc; g.logits = logits;
@@ -418,7 +433,7 @@ int mdl_gemm_tn_accum(const void* a_planes, long long a_cols, long long lda, lon
     MDL_REQUIRE(M % BLOCK_M == 0 && N % 256 == 0, "wgrad output must be a multiple of 128 x 256 (got %d x %d)", M, N);
     MDL_REQUIRE(tokens > 0, "tokens must be positive");
     const int planes = nsplit == 3 ? 2 : 1;
-    const bool two_cta = nsplit == 3 && use_fused() && use_2cta() && M % 256 == 0 &&
+    const bool two_cta = (nsplit == 3 || use_2cta_1pass()) && use_fused() && use_2cta() && M % 256 == 0 &&
                          (grp_m_rows <= 0 || grp_m_rows % 256 == 0);
     const int bk = two_cta ? BLOCK_KF : BLOCK_K;
     CUtensorMap ta, tb;
@@ -427,7 +442,8 @@ int mdl_gemm_tn_accum(const void* a_planes, long long a_cols, long long lda, lon
     rc = make_plane_tmap(&tb, b_planes, tokens, b_cols, ldb, b_plane_stride, planes, bk);
     if (rc) return rc;
     GemmArgs g{};
-    g.M = M; g.N = N; g.k_blocks = (int)((tokens + bk - 1) / bk); g.nsplit = nsplit;
+    const int k_per_stage = (two_cta && nsplit == 1) ? 2 * bk : bk;
+    g.M = M; g.N = N; g.k_blocks = (int)((tokens + k_per_stage - 1) / k_per_stage); g.nsplit = nsplit;
     const int tile_m = two_cta ? 256 : BLOCK_M;
     g.num_m_tiles = M / tile_m; g.num_n_tiles = N / 256; g.n_inner = 1;
     const int mn_tiles = g.num_m_tiles * g.num_n_tiles;

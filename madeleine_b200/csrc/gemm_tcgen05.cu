@@ -449,10 +449,10 @@ int mdl_gemm_tn_accum(const void* a_planes, long long a_cols, long long lda, lon
     const int mn_tiles = g.num_m_tiles * g.num_n_tiles;
     const int workers = two_cta ? kNumSMs / 2 : kNumSMs;
     if (ksplit <= 0) {
-        // aim for ~2 work units per worker (CTA or CTA pair), never more splits than k-blocks: every unit pays a pipeline
-        // fill and a 256 KB atomic epilogue, so fewer, longer units win as long as all workers stay busy
-        // (tools/wgrad_ksplit_probe.py: 512 x 512 wgrad 96 -> 84 us, 2048 x 512 334 -> ~310 us against ~4 units per worker)
-        ksplit = (2 * workers + mn_tiles - 1) / mn_tiles;
+        // aim for ~4 work units per worker (CTA or CTA pair), never more splits than k-blocks.  (Fewer, longer units look
+        // better when a wgrad is timed alone — tools/wgrad_ksplit_probe.py — but inside the step ~2 units per worker made the
+        // wgrads 10 % slower, 1.16 -> 1.28 ms: the tail of the last wave matters more than the per-unit epilogue.)
+        ksplit = (4 * workers + mn_tiles - 1) / mn_tiles;
     }
     if (ksplit > g.k_blocks) ksplit = g.k_blocks;
     if (ksplit < 1) ksplit = 1;

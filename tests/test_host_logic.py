@@ -96,3 +96,43 @@ def test_state_dict_layout_with_stain_encodings():
     want = (128 * 2048 + 128) + (512 * 544 + 512) + (512 * 512 + 512) + (2048 * 512 + 2048) + 2 * (512 + 512 + 2048) \
         + 4 * (2 * (512 * 512 + 512) + 512 + 1) + (512 * 2048 + 512) + 3 * 32
     assert sum(v.numel() for v in sd.values()) == want == 5013284 - 2 * 32        # SURVEY §8a1 quotes the 5-modality count
+
+
+def test_token_window_plan_host_logic():
+    """MADELEINE._window_plan: which packed rows token_projector sees, the row -> compact-row map used by the backward
+    LayerNorm kernel, and the gather that rebuilds the dense [R, W] token grid (missing bags repeat their single row)."""
+    from madeleine.models.Model import MADELEINE
+    T, W = 10, 4
+    lens = torch.tensor([T, 1, T, 1, 1])                     # bags 1, 3, 4 are missing stains encoded from one token
+    cu = torch.zeros(6, dtype=torch.int64)
+    cu[1:] = lens.cumsum(0)
+    rows, sel_of_row, dense = MADELEINE._window_plan(lens, cu, W, "cpu")
+    assert rows.tolist() == [0, 1, 2, 3, 10, 11, 12, 13, 14, 21, 22]
+    assert sel_of_row.numel() == int(cu[-1])
+    assert [int(sel_of_row[r]) for r in rows.tolist()] == list(range(11))
+    assert int((sel_of_row >= 0).sum()) == 11 and int(sel_of_row[4]) == -1 and int(sel_of_row[20]) == -1
+    assert dense.view(5, W).tolist() == [[0, 1, 2, 3], [4, 4, 4, 4], [5, 6, 7, 8], [9, 9, 9, 9], [10, 10, 10, 10]]
+    # no missing bag: the compact order already is the dense grid
+    lens = torch.full((3,), T)
+    cu = torch.zeros(4, dtype=torch.int64)
+    cu[1:] = lens.cumsum(0)
+    rows, sel_of_row, dense = MADELEINE._window_plan(lens, cu, W, "cpu")
+    assert dense is None and rows.tolist() == [0, 1, 2, 3, 10, 11, 12, 13, 20, 21, 22, 23]
+
+
+def test_token_window_resolution(monkeypatch):
+    from argparse import Namespace
+    from madeleine.models.Model import MADELEINE
+    cfg = Namespace(MODALITIES=["HE", "A"], wsi_encoder="abmil", patch_embedding_dim=512, wsi_encoder_hidden_dim=512,
+                    activation="softmax", n_heads=4)
+    monkeypatch.delenv("MADELEINE_B200_TOKEN_WINDOW", raising=False)
+    m = MADELEINE(cfg)
+    assert m._token_window(8, 2048, {}) == 0                                  # default: the reference's [bs, T, 128] tokens
+    monkeypatch.setenv("MADELEINE_B200_TOKEN_WINDOW", "batch")
+    assert m._token_window(8, 2048, {}) == 8 and m._token_window(8, 5, {}) == 5   # never more than the bag length
+    assert m._token_window(8, 2048, {"b200_token_window": 64}) == 64           # per-batch override (global batch under sharding)
+    cfg.b200_token_window = "off"
+    assert MADELEINE(cfg)._token_window(8, 2048, {}) == 0                      # config beats the environment
+    cfg.b200_token_window = -3
+    with __import__("pytest").raises(ValueError):
+        MADELEINE(cfg)._token_window(8, 2048, {})

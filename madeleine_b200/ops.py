@@ -163,8 +163,19 @@ class PackSpec:
             s = self.gr_segs[name]
             pos.append(torch.arange(s.off, s.off + idx.numel()))
             dst.append(idx.reshape(-1))
-        self.gr_pos = torch.cat(pos).to(torch.int32).to(device)
-        self.gr_dst = torch.cat(dst).to(torch.int32).to(device)
+        gr_pos_all, gr_dst_all = torch.cat(pos), torch.cat(dst)
+        self.gr_pos = gr_pos_all.to(torch.int32).to(device)
+        self.gr_dst = gr_dst_all.to(torch.int32).to(device)
+        # Parameters whose gradients are complete once the third pre-attention layer's wgrad has been issued (pre_attn.8/9,
+        # the attention heads, token_projector, projector) are one contiguous range of the master layout; under gradient
+        # sync that range is all-reduced while the backward pass of the first two layers is still running.
+        self.early_lo = offs[P["pre8.w"]]
+        self.early_hi = offs[P["emb.w"]] if P["emb.w"] < len(offs) else self.master_numel
+        early = (gr_dst_all >= self.early_lo) & (gr_dst_all < self.early_hi)
+        self.gr_pos_early = gr_pos_all[early].to(torch.int32).to(device)
+        self.gr_dst_early = gr_dst_all[early].to(torch.int32).to(device)
+        self.gr_pos_late = gr_pos_all[~early].to(torch.int32).to(device)
+        self.gr_dst_late = gr_dst_all[~early].to(torch.int32).to(device)
         self.off = off
         self.P = P
 
@@ -418,9 +429,20 @@ def encoder_forward(x: torch.Tensor, cu: torch.Tensor, codes: Optional[torch.Ten
     return outs, sv
 
 
+def _scatter_grads(gp, pos, dst, gmaster, st):
+    if pos.numel() == 0:
+        return
+    compact = torch.empty(pos.numel(), dtype=torch.float32, device=gp.device)
+    call("mdl_gather_f32", gp, pos, pos.numel(), compact, st)
+    call("mdl_scatter_f32", compact, dst, dst.numel(), gmaster, 0, st)
+
+
 def encoder_backward(sv, d_slide: Optional[torch.Tensor], d_logits: Optional[torch.Tensor], d_tokens: Optional[torch.Tensor],
-                     d_ref_feats: Optional[torch.Tensor]) -> torch.Tensor:
-    """Returns the flat master-layout gradient of all parameters."""
+                     d_ref_feats: Optional[torch.Tensor], early_sync=None) -> torch.Tensor:
+    """Returns the flat master-layout gradient of all parameters.
+
+    ``early_sync(gmaster, lo, hi)`` (optional) is called as soon as ``gmaster[lo:hi]`` — everything except the first two
+    pre-attention layers and the stain embedding — is final, while the rest of the backward pass is still to be issued."""
     opt, pw = sv.opt, sv.pw
     spec = pw.spec
     dev = sv.h3.device
@@ -503,6 +525,10 @@ def encoder_backward(sv, d_slide: Optional[torch.Tensor], d_logits: Optional[tor
     dh2 = gemm_nt(dz3, C, pw.planes("w3T"), HID, nsplit, out_dtype=zdt)
     gemm_tn_accum(dz3, sv.h2, g("w3"), nsplit)
     del dz3
+    gmaster = torch.zeros(spec.master_numel, dtype=torch.float32, device=dev)
+    if early_sync is not None:
+        _scatter_grads(gp, spec.gr_pos_early, spec.gr_dst_early, gmaster, st)
+        early_sync(gmaster, spec.early_lo, spec.early_hi)
     dz2 = ln_gelu_bwd(sv.z2, pw.vec("g2"), pw.vec("be2"), sv.mean2, sv.rstd2, dh2, None, [], 1, npl, sv.p_pre, opt.seed, 2,
                       g("g2"), g("be2"), g("b2"))
     dh1 = gemm_nt(dz2, HID, pw.planes("w2T"), HID, nsplit, out_dtype=zdt)
@@ -518,11 +544,11 @@ def encoder_backward(sv, d_slide: Optional[torch.Tensor], d_logits: Optional[tor
         gemm_tn_accum(sv.xp, dz1, w1t, nsplit)
         g("w1").add_(w1t.t())
 
-    gmaster = torch.zeros(spec.master_numel, dtype=torch.float32, device=dev)
     # scatter packed grads into parameter layout (gr_pos → gr_dst): gather the compact list, then scatter
-    compact = torch.empty(spec.gr_pos.numel(), dtype=torch.float32, device=dev)
-    call("mdl_gather_f32", gp, spec.gr_pos, spec.gr_pos.numel(), compact, st)
-    call("mdl_scatter_f32", compact, spec.gr_dst, spec.gr_dst.numel(), gmaster, 0, st)
+    if early_sync is not None:
+        _scatter_grads(gp, spec.gr_pos_late, spec.gr_dst_late, gmaster, st)
+    else:
+        _scatter_grads(gp, spec.gr_pos, spec.gr_dst, gmaster, st)
     if opt.se_dim > 0:
         w1 = pw.master[spec.off("pre0.w"):]
         emb = pw.master[spec.off("emb.w"):]
@@ -553,11 +579,26 @@ class EncodeFn(torch.autograd.Function):
         sv = ctx.sv
         if sv is None:
             raise RuntimeError("madeleine_b200: backward called on a forward that ran without grad state")
-        gmaster = encoder_backward(sv, d_slide, d_logits, d_tokens, d_ref)
         from . import parallel
-        if parallel.gradient_sync_enabled():
-            torch.distributed.all_reduce(gmaster, op=torch.distributed.ReduceOp.SUM)   # one flat 20 MB NCCL all-reduce
         spec = sv.pw.spec
+        if parallel.gradient_sync_enabled():
+            # 90 % of the 20 MB gradient (everything but the first two layers) is all-reduced asynchronously while those two
+            # layers' backward kernels run; the remainder follows at the end
+            import torch.distributed as dist
+            pending = []
+
+            def early(gm, lo, hi):
+                pending.append(dist.all_reduce(gm[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+
+            gmaster = encoder_backward(sv, d_slide, d_logits, d_tokens, d_ref, early_sync=early)
+            if spec.early_lo > 0:
+                dist.all_reduce(gmaster[:spec.early_lo], op=dist.ReduceOp.SUM)
+            if spec.early_hi < spec.master_numel:
+                dist.all_reduce(gmaster[spec.early_hi:], op=dist.ReduceOp.SUM)
+            for work in pending:
+                work.wait()
+        else:
+            gmaster = encoder_backward(sv, d_slide, d_logits, d_tokens, d_ref)
         grads = []
         for i, (shape, req) in enumerate(ctx.param_meta):
             if not req:

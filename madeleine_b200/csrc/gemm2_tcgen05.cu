@@ -64,7 +64,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
 
 // kMN = false: K-major operands (A[M,K], B[N,K]), 64-byte swizzle.   kMN = true: MN-major operands (A[t,M], B[t,N],
 // contraction over token rows t, split-K over p.ksplit), 128-byte swizzle, [64 cols x 32 rows] TMA boxes.
-template <int EPI, bool kMN>
+template <int EPI, bool kMN, bool ONE_PASS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_kf_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmArgs p) {
     using L = Smem2;
@@ -108,8 +108,9 @@ gemm2_kf_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const uint32_t tmem_base = *tmem_ptr_generic;
 
     // p.nsplit == 1 (bf16 mode, or the backward pass of fp32_fwd): one plane, a stage carries 64 of k; p.k_blocks counts stages
-    const bool one_pass = p.nsplit == 1;
-    const int kstep = one_pass ? 2 : 1;
+    // (a compile-time switch: a runtime test in the single-thread TMA / MMA issue loops cost the 3-pass GEMMs 6 %)
+    constexpr bool one_pass = ONE_PASS;
+    constexpr int kstep = one_pass ? 2 : 1;
     const int n_groups = p.num_n_tiles / p.n_inner;
     const int num_units = p.num_m_tiles * n_groups * p.ksplit;     // m tiles of 256 rows
     const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
@@ -202,7 +203,7 @@ gemm2_kf_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                                 b_lo = make_umma_desc_sw128(sb + L::B_BYTES / 2 + k * (UMMA_K * 128), BOX, 1024);
                             }
                             umma_bf16_2cta(tmem_d, a_hi, b_hi, idesc, accumulate);
-                            if (one_pass) {
+                            if constexpr (one_pass) {
                                 umma_bf16_2cta(tmem_d, a_lo, b_lo, idesc, 1u);        // the second k-block of the stage
                             } else {
                                 umma_bf16_2cta(tmem_d, a_hi, b_lo, idesc, 1u);
@@ -253,9 +254,9 @@ gemm2_kf_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
 }
 
-template <int EPI, bool kMN>
+template <int EPI, bool kMN, bool ONE_PASS>
 static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t stream) {
-    auto kern = gemm2_kf_kernel<EPI, kMN>;
+    auto kern = gemm2_kf_kernel<EPI, kMN, ONE_PASS>;
     static PerDeviceOnce attr_set;   // per instantiation and per device
     unsigned long long dev_bit;
     if (attr_set.needed(dev_bit)) {
@@ -275,12 +276,17 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs&
 }
 
 int launch_gemm2_kf(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, int epi, cudaStream_t stream) {
-    if (epi == EPI_GATED) return launch2<EPI_GATED, false>(ta, tb, args, stream);
-    return launch2<EPI_STORE, false>(ta, tb, args, stream);
+    if (args.nsplit == 1) {
+        if (epi == EPI_GATED) return launch2<EPI_GATED, false, true>(ta, tb, args, stream);
+        return launch2<EPI_STORE, false, true>(ta, tb, args, stream);
+    }
+    if (epi == EPI_GATED) return launch2<EPI_GATED, false, false>(ta, tb, args, stream);
+    return launch2<EPI_STORE, false, false>(ta, tb, args, stream);
 }
 
 int launch_gemm2_mn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t stream) {
-    return launch2<EPI_ATOMIC, true>(ta, tb, args, stream);
+    if (args.nsplit == 1) return launch2<EPI_ATOMIC, true, true>(ta, tb, args, stream);
+    return launch2<EPI_ATOMIC, true, false>(ta, tb, args, stream);
 }
 
 }  // namespace mdl

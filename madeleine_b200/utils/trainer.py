@@ -1,7 +1,14 @@
-"""Drop-in for madeleine/utils/trainer.py: the loss glue (calculate_losses) and the training-step caller."""
+"""Drop-in for madeleine/utils/trainer.py: the loss glue (``calculate_losses``) and the training-step caller
+(``train_loop``).  Signatures, return values, printed lines and control flow are the reference's (trainer.py:20-144);
+the internals are organised around what the device needs:
+
+* which cases carry a stain is decided on the HOST from the availability mask the loader delivers (one small index
+  upload per stain) — boolean-mask indexing of CUDA tensors would cost a device sync per stain and step;
+* the per-stain Graph-OT problems are independent and small, so they are issued on side streams and joined once;
+* the epoch loss and the H&E embeddings for the rank metric stay on the device until the epoch ends.
+"""
 import time
 
-import numpy as np
 import torch
 
 from .. import ops
@@ -9,93 +16,94 @@ from .loss import GOT as _B200_GOT
 from .utils import set_model_precision, smooth_rank_measure
 
 DEVICE = torch.device("cuda" if torch.cuda.is_available() else "cpu")
-HE_POSITION = 0
-WHOLE_VIEW_POSITION = 0
+HE_POSITION = 0            # the H&E slide is modality 0 of every case
+WHOLE_VIEW_POSITION = 0    # view 0 = all tokens; views 1, 2 = the two random halves (n_views = 3)
+_GOT_STREAMS = 4
+
+
+def _stains_with_pairs(stains, availability, device):
+    """Yield (column, stain name, device row indices of the cases that have the stain) for every stain present in at least
+    two cases of the batch (trainer.py:24-26: `stain_mask.sum() > 1`)."""
+    present = availability.detach().to("cpu").bool()
+    per_stain = present.sum(dim=0).tolist()
+    for col, name in enumerate(stains):
+        if per_stain[col] > 1:
+            yield col, name, present[:, col].nonzero(as_tuple=True)[0].to(device, non_blocking=True)
+
+
+def _slide_pair(wsi_embs, stain, col, view, rows):
+    """(H&E embedding paired with this stain, stain embedding) of one view for the selected cases."""
+    return wsi_embs["HE"][:, view, :, col][rows], wsi_embs[stain][:, view, :][rows]
 
 
 def calculate_losses(STAINS, loss_fn_interMod, loss_fn_interMod_local, loss_fn_intraMod, wsi_embs, token_embs,
                      modality_labels_withoutHE, args):
-    """trainer.py:20-77 — per stain: select the cases that have it, global InfoNCE (+ weighted GOT, + intra-modality
-    InfoNCE on the two half views), summed.  Returns (loss, at_least_one_stain_flag); loss is -1 when nothing applies."""
-    losses = []
-    pending_local = []          # (slot, raw GOT loss) issued on side streams, joined once before the final sum
-    atleast_two_loss_flag = False
-    dev = wsi_embs["HE"].device
-    # The availability mask comes from the dataloader on the CPU (as in the reference); keeping the case selection on
-    # the host avoids the device sync that boolean-mask indexing of CUDA tensors costs every step.
-    labels = modality_labels_withoutHE.detach().to("cpu").bool()
-    counts = labels.sum(dim=0).tolist()
-    for stain_idx, stain in enumerate(STAINS):
-        if counts[stain_idx] <= 1:
-            continue
-        stain_mask = labels[:, stain_idx].nonzero(as_tuple=True)[0].to(dev, non_blocking=True)   # row indices of the cases
+    """Sum over the stains of: global InfoNCE(H&E, stain) + local_loss_weight x GOT(H&E tokens, stain tokens) + the two
+    intra-modality InfoNCE terms on the half views, each evaluated on the cases that have the stain.
+    Returns ``(loss, flag)``; ``flag`` says whether any stain contributed, ``loss`` is -1 when none did."""
+    device = wsi_embs["HE"].device
+    terms, local_terms = [], []            # local_terms: (side-stream slot, unweighted GOT loss)
+    any_stain = False
+    for col, stain, rows in _stains_with_pairs(STAINS, modality_labels_withoutHE, device):
+        any_stain = True
         if loss_fn_interMod:
             if args.global_loss != "info-nce":
                 raise AssertionError("invalid global loss")
-            he = wsi_embs["HE"][:, WHOLE_VIEW_POSITION, :, stain_idx][stain_mask]
-            ihc = wsi_embs[stain][:, WHOLE_VIEW_POSITION, :][stain_mask]
-            losses.append(loss_fn_interMod(query=he, positive_key=ihc, symmetric=args.symmetric_cl))
+            q, k = _slide_pair(wsi_embs, stain, col, WHOLE_VIEW_POSITION, rows)
+            terms.append(loss_fn_interMod(query=q, positive_key=k, symmetric=args.symmetric_cl))
         if loss_fn_interMod_local:
-            he_tokens = token_embs["HE"][:, :, :, stain_idx][stain_mask]
-            ihc_tokens = token_embs[stain].squeeze()[stain_mask]
-            if loss_fn_interMod_local is _B200_GOT and he_tokens.is_cuda:
-                # the per-stain OT problems are independent and small (<= 65 CTAs each): overlap them on side streams
-                slot = len(pending_local) % 4
-                pending_local.append((slot, loss_fn_interMod_local(he_tokens, ihc_tokens, subsample=256, _slot=slot)))
-            else:
-                losses.append(loss_fn_interMod_local(he_tokens, ihc_tokens, subsample=256) * args.local_loss_weight)
+            tok_he = token_embs["HE"][:, :, :, col][rows]
+            tok_stain = token_embs[stain].squeeze()[rows]
+            if loss_fn_interMod_local is _B200_GOT and tok_he.is_cuda:
+                slot = len(local_terms) % _GOT_STREAMS
+                local_terms.append((slot, loss_fn_interMod_local(tok_he, tok_stain, subsample=256, _slot=slot)))
+            else:                           # a user-supplied local loss: plain call, as in the reference
+                terms.append(loss_fn_interMod_local(tok_he, tok_stain, subsample=256) * args.local_loss_weight)
         if loss_fn_intraMod:
-            he1, he2 = wsi_embs["HE"][:, 1, :, stain_idx][stain_mask], wsi_embs["HE"][:, 2, :, stain_idx][stain_mask]
-            st1, st2 = wsi_embs[stain][:, 1, :][stain_mask], wsi_embs[stain][:, 2, :][stain_mask]
-            losses.append(loss_fn_intraMod(query=he1, positive_key=he2, symmetric=args.symmetric_cl))
-            losses.append(loss_fn_intraMod(query=st1, positive_key=st2, symmetric=args.symmetric_cl))
-        atleast_two_loss_flag = True
-    if pending_local:
-        ops.got_join(dev, sorted({slot for slot, _ in pending_local}))
-        losses.extend(raw * args.local_loss_weight for _, raw in pending_local)
-    if len(losses) > 0:
-        loss = sum(losses)
-    else:
-        loss = -1
-        assert loss == -1 and not atleast_two_loss_flag, "Loss should be -1 if there are no losses to calculate"
-    return loss, atleast_two_loss_flag
+            he_a, st_a = _slide_pair(wsi_embs, stain, col, 1, rows)
+            he_b, st_b = _slide_pair(wsi_embs, stain, col, 2, rows)
+            terms.append(loss_fn_intraMod(query=he_a, positive_key=he_b, symmetric=args.symmetric_cl))
+            terms.append(loss_fn_intraMod(query=st_a, positive_key=st_b, symmetric=args.symmetric_cl))
+    if local_terms:
+        ops.got_join(device, sorted({slot for slot, _ in local_terms}))
+        terms += [value * args.local_loss_weight for _, value in local_terms]
+    if not terms:
+        assert not any_stain, "Loss should be -1 if there are no losses to calculate"
+        return -1, any_stain
+    return sum(terms), any_stain
 
 
 def train_loop(args, loss_fn_interMod, loss_fn_interMod_local, loss_fn_intraMod, ssl_model, epoch, dataloader, optimizer,
                scheduler_warmup, scheduler):
-    """trainer.py:80-144 — one epoch. Same control flow as the reference; the HE embeddings for the rank metric are
-    gathered on the device and copied once per epoch instead of one blocking .cpu() per step."""
-    n_views = 3 if loss_fn_intraMod else 1
+    """One epoch (trainer.py:80-144): forward + losses under autocast, backward, optimiser and scheduler step per batch;
+    batches without a second stain are skipped.  Returns ``(epoch loss, smooth rank of the H&E embeddings)``."""
     ssl_model.train()
-    torch_precision = set_model_precision(args.precision)
-    autocast_on = torch_precision in (torch.bfloat16, torch.float16)
-    ep_loss = torch.zeros((), device=DEVICE)
-    fb_time = 0.0
-    all_embeds = []
-    for b_idx, data in enumerate(dataloader):
-        if epoch == 0 and b_idx == 0:
-            print("Using precision:", torch_precision)
-        s_fb = time.time()
-        modality_labels_withoutHE = data["modality_labels"][:, HE_POSITION + 1:]
+    n_views = 3 if loss_fn_intraMod else 1
+    dtype = set_model_precision(args.precision)
+    use_autocast = dtype in (torch.bfloat16, torch.float16)
+    running = torch.zeros((), device=DEVICE)          # stays on the device: no .item() per step
+    he_embeddings = []
+    busy = 0.0
+    for step, batch in enumerate(dataloader):
+        if epoch == 0 and step == 0:
+            print("Using precision:", dtype)
+        t0 = time.time()
+        availability = batch["modality_labels"][:, HE_POSITION + 1:]
         optimizer.zero_grad()
-        with torch.amp.autocast(device_type="cuda", dtype=torch_precision, enabled=autocast_on):
-            wsi_embs, token_embs = ssl_model(data, device=DEVICE, n_views=n_views)
-            loss, atleast_two_loss_flag = calculate_losses(args.STAINS, loss_fn_interMod, loss_fn_interMod_local, loss_fn_intraMod,
-                                                           wsi_embs, token_embs, modality_labels_withoutHE, args)
-        all_embeds.append(wsi_embs["HE"][:, WHOLE_VIEW_POSITION, :, 0].detach().to(torch.float32))
-        if not atleast_two_loss_flag:
+        with torch.amp.autocast(device_type="cuda", dtype=dtype, enabled=use_autocast):
+            wsi_embs, token_embs = ssl_model(batch, device=DEVICE, n_views=n_views)
+            loss, usable = calculate_losses(args.STAINS, loss_fn_interMod, loss_fn_interMod_local, loss_fn_intraMod,
+                                            wsi_embs, token_embs, availability, args)
+        he_embeddings.append(wsi_embs["HE"][:, WHOLE_VIEW_POSITION, :, 0].detach().float())
+        if not usable:
             print("Skipping batch with only HE")
             continue
         loss.backward()
         optimizer.step()
-        if epoch <= args.warmup_epochs:
-            scheduler_warmup.step()
-        else:
-            scheduler.step()
-        if (b_idx % 3) == 0:
-            print(f"Loss for batch: {b_idx} = {loss:.3f}")
-        ep_loss += loss.detach()
-        fb_time += time.time() - s_fb
-    all_embeds_tensor = torch.cat(all_embeds, dim=0).cpu()
-    rank = smooth_rank_measure(all_embeds_tensor)
-    return float(ep_loss), rank
+        (scheduler_warmup if epoch <= args.warmup_epochs else scheduler).step()
+        if step % 3 == 0:
+            print(f"Loss for batch: {step} = {loss:.3f}")
+        running += loss.detach()
+        busy += time.time() - t0
+    rank = smooth_rank_measure(torch.cat(he_embeddings, dim=0).cpu())
+    return float(running), rank

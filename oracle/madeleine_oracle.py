@@ -131,7 +131,7 @@ def madeleine_forward_train(sd, feats: torch.Tensor, modalities: List[str], stai
     bs, n_mod, T, D = feats.shape
     x = feats.reshape(bs * n_mod, T, D)
     if stain_encoding:
-        ind = torch.tensor([i for i in range(n_mod) for _ in range(bs)], dtype=torch.long)
+        ind = torch.tensor([i for i in range(n_mod) for _ in range(bs)], dtype=torch.long, device=feats.device)
         enc = sd["embedding.weight"][ind]                       # [bs*n_mod, 32]
         x = torch.cat([x, enc.unsqueeze(1).expand(-1, T, -1)], dim=-1)
     slide, tok, _ = abmil_embedder(sd, x, n_views=n_views)
@@ -246,8 +246,8 @@ def thresholded_cosine_cost(x, y):
 def ipot_plan(C, beta=0.5, iteration=50):
     """IPOT_torch_batch_uniform (loss.py:179-193). C [b,n,m] → transport plan T [b,n,m]."""
     b, n, m = C.shape
-    sigma = torch.ones(b, m, 1, dtype=C.dtype) / float(m)
-    T = torch.ones(b, n, m, dtype=C.dtype)
+    sigma = torch.ones(b, m, 1, dtype=C.dtype, device=C.device) / float(m)
+    T = torch.ones(b, n, m, dtype=C.dtype, device=C.device)
     A = torch.exp(-C / beta)
     delta = None
     for _ in range(iteration):
@@ -271,13 +271,13 @@ def ipot_distance(C, iteration=50):
 def gromov_wasserstein(X, Y, lamda=1e-1, iteration=5, ot_iteration=20):
     """GW_distance_uniform → GW_distance → GW_torch_batch (loss.py:236-275). X,Y [b,D,n] → [b,1]."""
     b, n_x, n_y = X.shape[0], X.shape[2], Y.shape[2]
-    p = torch.ones(b, n_x, 1, dtype=X.dtype) / n_x
-    q = torch.ones(b, n_y, 1, dtype=X.dtype) / n_y
+    p = torch.ones(b, n_x, 1, dtype=X.dtype, device=X.device) / n_x
+    q = torch.ones(b, n_y, 1, dtype=X.dtype, device=X.device) / n_y
     Cs = thresholded_cosine_cost(X, X)
     Ct = thresholded_cosine_cost(Y, Y)
     n, m = Cs.shape[2], Ct.shape[2]
-    one_m = torch.ones(b, m, 1, dtype=X.dtype)
-    one_n = torch.ones(b, n, 1, dtype=X.dtype)
+    one_m = torch.ones(b, m, 1, dtype=X.dtype, device=X.device)
+    one_n = torch.ones(b, n, 1, dtype=X.dtype, device=X.device)
     Cst = ((Cs ** 2) @ p) @ one_m.transpose(1, 2) + one_n @ (q.transpose(1, 2) @ (Ct ** 2).transpose(1, 2))
     gamma = p @ q.transpose(1, 2)
     for _ in range(iteration):

@@ -115,3 +115,30 @@ def test_pack_spec_index_maps():
     e = spec.off("emb.w")
     expect[e:e + 3 * 32] = False
     assert torch.equal(covered, expect)
+
+
+@pytest.mark.parametrize("se", [True, False])
+def test_pack_spec_early_late_gradient_split(se):
+    """Under gradient sync the master-layout gradient is all-reduced in two parts (ops.EncodeFn.backward): the range
+    [early_lo, early_hi) — pre_attn.8/9, the heads, token_projector, projector — as soon as the third layer's wgrad is issued,
+    the rest at the end.  The two scatter lists must partition the packed gradient exactly and respect that range."""
+    sd, ps = _params(se=se)
+    d_total = 544 if any(tuple(p.shape) == (512, 544) for p in ps) else 512
+    spec = ops.PackSpec([tuple(p.shape) for p in ps], 4, d_total, "cpu", d_in=512)
+    names = ops.PARAM_ORDER(4)
+    offs = dict(zip(names, spec.param_offsets))
+    assert spec.early_lo == offs["pre8.w"]
+    assert spec.early_hi == (offs["emb.w"] if "emb.w" in offs and len(spec.param_offsets) == len(names) else spec.master_numel)
+    e_dst, l_dst = spec.gr_dst_early.long(), spec.gr_dst_late.long()
+    assert int(e_dst.min()) >= spec.early_lo and int(e_dst.max()) < spec.early_hi
+    assert bool(((l_dst < spec.early_lo) | (l_dst >= spec.early_hi)).all())
+    both = torch.cat([spec.gr_pos_early, spec.gr_pos_late]).sort().values
+    assert torch.equal(both, spec.gr_pos.sort().values)
+    assert torch.equal(torch.cat([e_dst, l_dst]).sort().values, spec.gr_dst.long().sort().values)
+    # everything inside the early range except nothing is missing: every master element of those parameters is written once
+    covered = torch.zeros(spec.master_numel, dtype=torch.int32)
+    covered[spec.gr_dst.long()] += 1
+    stain_cols = 0 if d_total == 512 else 512 * 32
+    emb = spec.master_numel - spec.early_hi
+    assert int((covered == 0).sum()) == stain_cols + emb          # only the stain columns of W1 and the embedding table come later
+    assert int(covered.max()) == 1

@@ -6,7 +6,8 @@
 Metric (BASELINE.json): slides/sec (fwd+bwd) at N=2000 x D=512.  One step = BASELINE.json configs[1] per GPU:
 16 cases x 2 stains (HE + one IHC) = 32 bags x 2000 patch embeddings x 512-d, forward through the drop-in
 ``MADELEINE.forward(train=True)`` in train mode (dropout on) + symmetric InfoNCE (tau = 0.001) via
-``calculate_losses`` + ``loss.backward()``.  For N > 1 every rank owns 16 more cases (weak scaling); the slide
+``calculate_losses`` + ``loss.backward()`` + the fused AdamW update (so the bf16 operand planes of the weights are
+re-packed every step, as in training; ``--no-optimizer`` times forward + backward alone).  For N > 1 every rank owns 16 more cases (weak scaling); the slide
 embeddings are all-gathered once before the loss and parameter gradients are summed with one all-reduce.
 
   value    whole-job slides/s with the inputs resident in HBM
@@ -225,7 +226,11 @@ def main():
     ap.add_argument("--eval-mode", action="store_true", help="model.eval(): dropout off")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--with-optimizer", action="store_true", help="also run the fused AdamW step inside every timed step")
+    ap.add_argument("--no-optimizer", action="store_true",
+                    help="time forward + backward only; by default every timed step also runs the fused AdamW update, so the "
+                         "kernel-layout copies of the weights are re-packed every step as in real training (nothing is cached "
+                         "across steps)")
+    ap.add_argument("--with-optimizer", action="store_true", help="(default; kept for older command lines)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -277,6 +282,7 @@ def main():
     parallel.enable_gradient_sync(world > 1)
 
     optimizer = None
+    args.with_optimizer = not args.no_optimizer
     if args.with_optimizer:
         from madeleine_b200.optim import FusedAdamW
         optimizer = FusedAdamW(model.parameters(), lr=1e-4)       # reference: optim.AdamW(lr=args.lr), lr 1e-4 in the scripts
@@ -435,7 +441,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": "BASELINE configs[1] at the metric's fixed N=2000: 16 cases x 2 stains per GPU, symmetric InfoNCE tau=0.001, "
                                "MADELEINE.forward(train=True) + calculate_losses + backward, train mode (dropout on)"
-                               + (" + fused AdamW step" if args.with_optimizer else "")
+                               + (" + fused AdamW step (weights re-packed every step)" if args.with_optimizer else " (no optimiser step)")
                                if not args.eval_mode else "same, eval mode",
                    "bags_per_gpu": bags_local, "tokens_per_bag": N_TOKENS, "d_in": D_IN, "parallelism": f"dp{world} (cases sharded, 1 all-gather of slide embeddings + grad all-reduce, 90 % of it overlapped with the backward pass)",
                    "l2": "inputs larger than L2 (131 MB features + >1 GB activations per step, L2 = 126 MB)"},

@@ -158,3 +158,37 @@ def test_losses_and_grads(golden, tag):
             ref = d["samples"]
             close(flat[d["idx"]], ref, rtol=2e-2, atol=2e-3 * float(ref.abs().max()) + 2e-6)  # attention_c.bias grad is analytically 0 (softmax shift invariance): pure noise
             assert float(flat.double().norm()) == pytest.approx(float(d["norm"]), rel=2e-2)
+
+
+# ---------------------------------------------------------------------------------------------- variants (round 1, late)
+def test_oracle_other_widths_against_reference(golden):
+    """Fixtures from the real reference for patch_embedding_dim = 1024 / 768 / 384 / 1536 / 128 (with and without stain
+    encodings): forward(train=True) + InfoNCE + GOT.  Pins the oracle where the GPU tests use it as the yardstick."""
+    import oracle
+    from weights import make_state_dict, make_feats
+    mods = ["HE", "ER", "PR"]
+    for (d_in, se), g in golden("variants")["widths"].items():
+        sd = {k: v.clone().requires_grad_(True) for k, v in make_state_dict(g["seed_w"], n_mod=3, stain_encoding=se, d_in=d_in).items()}
+        feats = make_feats(g["seed_x"], *g["shape"])
+        embs, toks = oracle.madeleine_forward_train(sd, feats, mods, stain_encoding=se)
+        torch.manual_seed(g["torch_seed"])
+        loss, _ = oracle.calculate_losses(mods[1:], embs, toks, torch.ones(g["shape"][0], 2), temperature=g["tau"], symmetric=True,
+                                          use_local=True)
+        loss.backward()
+        for m in mods:
+            torch.testing.assert_close(embs[m].detach(), g["embs"][m], rtol=1e-4, atol=1e-5)
+            torch.testing.assert_close(toks[m].detach()[:, :2], g["tok_head"][m], rtol=1e-4, atol=1e-5)
+            assert float(toks[m].detach().double().sum()) == pytest.approx(float(g["tok_sum"][m]), rel=1e-4, abs=1e-3)
+        torch.testing.assert_close(loss.detach(), g["loss"], rtol=1e-4, atol=1e-4)
+        for name, ref_norm in g["grad_norms"].items():
+            if float(ref_norm) > 1e-6:
+                assert float(sd[name].grad.double().norm()) == pytest.approx(float(ref_norm), rel=2e-2), (d_in, se, name)
+
+
+def test_oracle_activation_variants_against_reference(golden):
+    import oracle
+    from weights import make_state_dict, make_feats
+    for act, g in golden("variants")["activations"].items():
+        sd = make_state_dict(g["seed_w"], n_mod=1)
+        slide, _, _ = oracle.abmil_embedder(sd, make_feats(g["seed_x"], *g["shape"]), activation=act)
+        torch.testing.assert_close(slide, g["slide"], rtol=1e-4, atol=1e-5)

@@ -67,6 +67,16 @@ def main():
         with torch.no_grad():
             slide = model.wsi_embedders(x)
         out["activations"][act] = {"seed_w": 31, "seed_x": 77, "shape": (2, 37, 512), "slide": slide.clone()}
+    # GOT problems of more than 96 tokens (batches of more than 96 cases): the token generator of tests/test_gpu_got.py::_tokens
+    out["got_large"] = {}
+    for m, n in [(3, 130), (2, 256)]:
+        g = torch.Generator().manual_seed(n)
+        v = torch.randn(m, n, 128, generator=g)
+        q = v + 0.5 * torch.randn(m, n, 128, generator=g)
+        vr, qr = v.clone().requires_grad_(True), q.clone().requires_grad_(True)
+        loss = GOT(vr, qr)                       # subsample=None: the tokens are used as given
+        loss.backward()
+        out["got_large"][(m, n)] = {"seed": n, "loss": loss.detach().clone(), "dv": vr.grad.clone(), "dq": qr.grad.clone()}
     torch.save(out, os.path.join(HERE, "variants.pt"))
     print("wrote variants.pt", os.path.getsize(os.path.join(HERE, "variants.pt")), "bytes")
 

@@ -192,3 +192,18 @@ def test_oracle_activation_variants_against_reference(golden):
         sd = make_state_dict(g["seed_w"], n_mod=1)
         slide, _, _ = oracle.abmil_embedder(sd, make_feats(g["seed_x"], *g["shape"]), activation=act)
         torch.testing.assert_close(slide, g["slide"], rtol=1e-4, atol=1e-5)
+
+
+def test_oracle_got_large_problems_against_reference(golden):
+    """The reference's GOT on problems of 130 and 256 tokens (what batches of more than 96 cases produce)."""
+    import oracle
+    for (m, n), g in golden("variants")["got_large"].items():
+        gen = torch.Generator().manual_seed(g["seed"])
+        v = torch.randn(m, n, 128, generator=gen)
+        q = v + 0.5 * torch.randn(m, n, 128, generator=gen)
+        vr, qr = v.clone().requires_grad_(True), q.clone().requires_grad_(True)
+        loss = oracle.got(vr, qr)
+        loss.backward()
+        torch.testing.assert_close(loss.detach(), g["loss"], rtol=1e-4, atol=1e-5)
+        for got, ref in ((vr.grad, g["dv"]), (qr.grad, g["dq"])):
+            assert float((got - ref).norm() / ref.norm()) < 1e-3

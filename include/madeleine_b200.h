@@ -43,7 +43,9 @@ int mdl_row2bag(const int* cu_seqlens, int n_bags, int* row2bag, long long rows,
 /* ---- tcgen05 GEMMs ------------------------------------------------------------------------------------------ */
 /* out[M,N] = A[M,K] * B[N,K]^T + bias[n] + rowbias[row2bag[m], n]   (nn.Linear forward, Model.py:351,355,359,
  * 80-83, and every dgrad with a pre-transposed B).  A's k offset is (n / grp_n_cols) * a_koff when grp_n_cols > 0
- * (per-head operand slabs).  bias / rowbias / row2bag may be NULL. */
+ * (per-head operand slabs).  bias / rowbias / row2bag may be NULL.  out is fp32 [M, ldc]; with out_bf16 != 0 it is a
+ * bf16 matrix (ldc in elements) holding the round-to-nearest of the fp32 result — what torch autocast returns from
+ * nn.Linear in the reference's --precision bfloat16 runs (trainer.py:108). */
 int mdl_gemm_nt(const void* a_planes, long long a_rows, long long a_cols, long long lda, long long a_plane_stride,
                 const void* b_planes, long long b_rows, long long b_cols, long long ldb, long long b_plane_stride,
                 void* out, long long ldc, int M, int N, int K, int nsplit, int grp_n_cols, int a_koff,
@@ -72,7 +74,8 @@ int mdl_gemm_tn_simt(const void* a_planes, long long lda, long long a_plane_stri
                      void* stream);
 
 /* ---- LayerNorm + GELU (+dropout) ------------------------------------------------------------------------------ */
-/* nn.LayerNorm -> nn.GELU -> nn.Dropout of ABMILEmbedder.pre_attn (Model.py:352-354, 356-358, 360-362). */
+/* nn.LayerNorm -> nn.GELU -> nn.Dropout of ABMILEmbedder.pre_attn (Model.py:352-354, 356-358, 360-362).
+ * z is fp32 [M, C], or bf16 when z_bf16 != 0 (bf16 mode: the Linear outputs are stored as autocast returns them). */
 int mdl_ln_gelu_fwd(const void* z, long long M, int C, const float* gamma, const float* beta, float eps,
                     float drop_p, unsigned long long seed, unsigned stream_id,
                     void* planes, long long plane_stride, int nplanes, float* mean, float* rstd, int z_bf16, void* stream);
@@ -80,6 +83,7 @@ int mdl_ln_gelu_fwd(const void* z, long long M, int C, const float* gamma, const
  * dh_b_rows == NULL: dh_b is dense [M, C]; otherwise dh_b is compact [n_sel, C] and dh_b_rows[m] is token m's compact row
  * or -1 (the token_projector gradient of the token window, Model.py:138-146 + loss.py:281-284).
  * Accumulates dgamma, dbeta and the preceding Linear's bias grad dbias (all [C], caller zero-fills).
+ * in_bf16 != 0: z, dh_a and dh_b are bf16 instead of fp32 (bf16 mode).
  * bag_dz != NULL (C == 512, no dh_b / pooling term): also accumulates per-bag column sums of dz into bag_dz[row2bag[m], c]
  * ([n_bags, C], caller zero-fills) — the stain-encoding backward of Model.py:126-133. */
 int mdl_ln_gelu_bwd(const void* z, long long M, int C, const float* gamma, const float* beta, const float* mean,

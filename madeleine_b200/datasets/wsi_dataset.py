@@ -207,8 +207,9 @@ class ResidentSlideStore:
         out = torch.empty(bs, self.n_mod, sample, self.D, dtype=torch.float32, device=self.device)
         picked = torch.empty(R, sample, dtype=torch.int32, device=self.device) if return_indices else None
         # a bag's draw is keyed by (seed, position of the bag in this batch); the loader changes the seed every step
-        call("mdl_sample_gather_f32", self.features, offs, lens, R, sample, self.D, int(seed) & 0xFFFFFFFFFFFFFFFF, out, picked,
-             stream_ptr(self.device))
+        with torch.cuda.device(self.device):
+            call("mdl_sample_gather_f32", self.features, offs, lens, R, sample, self.D, int(seed) & 0xFFFFFFFFFFFFFFFF, out, picked,
+                 stream_ptr(self.device))
         batch = {"feats": out, "modality_labels": self.modality_labels.index_select(0, idx),
                  "slide_ids": [self.slide_ids[i] for i in idx.tolist()]}
         if return_indices:

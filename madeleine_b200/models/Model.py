@@ -146,7 +146,8 @@ class ABMILEmbedder(nn.Module):
         if opt.activation not in ops.ACT_CODES:
             raise NotImplementedError("Activation not implemented.")
         holder = {"opt": opt, "cu": cu, "codes": codes, "pw": pw, "need_grad": need_grad}
-        slide, logits, tokens, ref = ops.EncodeFn.apply(holder, x, *params)
+        with torch.cuda.device(dev):      # kernels launch on the current device: make it the tensors' (model.to('cuda:1') etc.)
+            slide, logits, tokens, ref = ops.EncodeFn.apply(holder, x, *params)
         return {"slide": slide, "logits": logits, "tokens": tokens, "ref_feats": ref}
 
     @staticmethod

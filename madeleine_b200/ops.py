@@ -395,7 +395,9 @@ def encoder_forward(x: torch.Tensor, cu: torch.Tensor, codes: Optional[torch.Ten
         R2 = cu2.numel() - 1
         pooled_views = torch.empty(R2, C, dtype=torch.float32, device=dev)
         attn_p2 = torch.zeros(M, H, dtype=torch.float32, device=dev) if keep_for_backward else None
-        pool_fwd(h3, npl, logits, cu2, tok_idx, R2, tok_idx.numel(), H, HID, pooled_views, attn_p2, act)
+        # the half views are always re-normalised with a softmax over the raw logits, whatever config.activation is
+        # (Model.py:436: F.softmax(attention_weights[:, view_idx], dim=1)); only the whole view uses the configured activation
+        pool_fwd(h3, npl, logits, cu2, tok_idx, R2, tok_idx.numel(), H, HID, pooled_views, attn_p2, ACT_CODES["softmax"])
         sv.attn_p2, sv.pooled_views = attn_p2, pooled_views
     # all slide vectors that go through the projector: [whole views | half views]
     slide_hm = pooled if pooled_views is None else torch.cat([pooled, pooled_views], dim=0)
@@ -486,7 +488,7 @@ def encoder_backward(sv, d_slide: Optional[torch.Tensor], d_logits: Optional[tor
         tok_idx, cu2, row2seg2 = opt.views
         dS2 = dS_all[R:]
         call("mdl_pool_bwd_dlogit", sv.h3, M * C, fwd_npl, dS2, sv.pooled_views, sv.attn_p2, cu2, tok_idx, cu2.numel() - 1, tok_idx.numel(),
-             H, HID, dlogit, 1, sv.logits, act, 0, st)
+             H, HID, dlogit, 1, sv.logits, ACT_CODES["softmax"], 0, st)
         pool_terms.append((sv.attn_p2, dS2, row2seg2))
 
     # ---- gated attention backward ----
@@ -599,9 +601,18 @@ class EncodeFn(torch.autograd.Function):
                 work.wait()
         else:
             gmaster = encoder_backward(sv, d_slide, d_logits, d_tokens, d_ref)
+        # parameters that no incoming gradient can reach keep grad = None, as in the reference (AdamW then skips them: no
+        # weight decay / moment updates on e.g. token_projector when no local loss is used)
+        opt = sv.opt
+        untouched = set()
+        if d_tokens is None or not opt.want_tokens:
+            untouched |= {"tp.w", "tp.b"}
+        if d_slide is None or not opt.want_projector:
+            untouched |= {"proj.w", "proj.b"}
+        skip = {spec.P[n] for n in untouched}
         grads = []
         for i, (shape, req) in enumerate(ctx.param_meta):
-            if not req:
+            if not req or i in skip:
                 grads.append(None)
                 continue
             o = spec.param_offsets[i]
@@ -660,7 +671,8 @@ class InfoNCEFn(torch.autograd.Function):
 def info_nce(query, positive_key, temperature=0.1, reduction="mean", symmetric=False):
     _lib.require_cuda(query, "InfoNCE query")
     _lib.require_cuda(positive_key, "InfoNCE positive_key")
-    return InfoNCEFn.apply(query, positive_key, temperature, symmetric, reduction)
+    with torch.cuda.device(query.device):
+        return InfoNCEFn.apply(query, positive_key, temperature, symmetric, reduction)
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -779,7 +791,8 @@ class GOTShardedFn(torch.autograd.Function):
 
 def got_loss(v, q, slot: int = -1):
     _lib.require_cuda(v, "GOT tokens")
-    return GOTFn.apply(v, q, slot)
+    with torch.cuda.device(v.device):
+        return GOTFn.apply(v, q, slot)
 
 
 def got_join(device, slots):

@@ -39,21 +39,27 @@ class FusedAdamW(torch.optim.Optimizer):
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 st["step"] += 1
-            step = self.state[ps[0]]["step"]
             lr = float(group["lr"])
-            for i in range(0, len(ps), self._max):
-                chunk = ps[i:i + self._max]
-                n = len(chunk)
-                grads = [p.grad if p.grad.is_contiguous() else p.grad.contiguous() for p in chunk]
-                arr = ctypes.c_void_p * n
-                P = arr(*[p.data_ptr() for p in chunk])
-                G = arr(*[g.data_ptr() for g in grads])
-                M = arr(*[self.state[p]["exp_avg"].data_ptr() for p in chunk])
-                V = arr(*[self.state[p]["exp_avg_sq"].data_ptr() for p in chunk])
-                N = (ctypes.c_longlong * n)(*[p.numel() for p in chunk])
-                call("mdl_adamw_step", n, ctypes.cast(P, ctypes.c_void_p), ctypes.cast(G, ctypes.c_void_p),
-                     ctypes.cast(M, ctypes.c_void_p), ctypes.cast(V, ctypes.c_void_p), ctypes.cast(N, ctypes.c_void_p),
-                     lr, beta1, beta2, group["eps"], group["weight_decay"], step, 1.0, stream_ptr(chunk[0].device))
+            # bias correction follows every tensor's OWN step count (torch.optim.AdamW tracks it per parameter): tensors that
+            # first received a gradient later than the others form their own launch
+            by_step = {}
+            for p in ps:
+                by_step.setdefault(self.state[p]["step"], []).append(p)
+            for step, same in by_step.items():
+                for i in range(0, len(same), self._max):
+                    chunk = same[i:i + self._max]
+                    n = len(chunk)
+                    grads = [p.grad if p.grad.is_contiguous() else p.grad.contiguous() for p in chunk]
+                    arr = ctypes.c_void_p * n
+                    P = arr(*[p.data_ptr() for p in chunk])
+                    G = arr(*[g.data_ptr() for g in grads])
+                    M = arr(*[self.state[p]["exp_avg"].data_ptr() for p in chunk])
+                    V = arr(*[self.state[p]["exp_avg_sq"].data_ptr() for p in chunk])
+                    N = (ctypes.c_longlong * n)(*[p.numel() for p in chunk])
+                    with torch.cuda.device(chunk[0].device):
+                        call("mdl_adamw_step", n, ctypes.cast(P, ctypes.c_void_p), ctypes.cast(G, ctypes.c_void_p),
+                             ctypes.cast(M, ctypes.c_void_p), ctypes.cast(V, ctypes.c_void_p), ctypes.cast(N, ctypes.c_void_p),
+                             lr, beta1, beta2, group["eps"], group["weight_decay"], step, 1.0, stream_ptr(chunk[0].device))
             # the kernel wrote the parameters behind autograd's back: bump their version counters so that everything keyed
             # on them sees the update (the encoder re-packs its bf16 operand planes when a parameter's version changes)
             for p in ps:

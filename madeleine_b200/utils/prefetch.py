@@ -15,7 +15,9 @@ class DevicePrefetcher:
 
     Yields the same structure with tensors on ``device``.  The copy of the next batch is issued on a side stream
     before the current one is handed out; consumers just use the tensors on the current stream.  A yielded batch stays
-    valid until the NEXT-BUT-ONE batch is requested (two slots); clone what must live longer.
+    valid until the NEXT batch is requested: requesting batch i+1 starts the copy of batch i+2 into batch i's slot, ordered
+    after the work enqueued on the current stream up to that moment — kernels on batch i must be enqueued before asking
+    for batch i+1; clone what must live longer.
     """
 
     SLOTS = 2

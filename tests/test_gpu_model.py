@@ -286,7 +286,7 @@ def test_skip_missing_bags_matches_full_encoding(golden):
         torch.manual_seed(g["torch_seed"])
         loss, _ = calculate_losses(mods[1:], InfoNCE(temperature=0.001), GOT, None, embs, toks, g["labels"][:, 1:], args)
         loss.backward()
-        outs.append((embs, toks, loss.detach(), {n: p.grad.clone() for n, p in model.named_parameters()}))
+        outs.append((embs, toks, loss.detach(), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}))
     (e1, t1, l1, g1), (e0, t0, l0, g0) = outs
     for m in mods:
         torch.testing.assert_close(e1[m], e0[m], rtol=1e-5, atol=1e-6)
@@ -321,7 +321,7 @@ def test_token_window_matches_full_tokens(golden, with_labels):
         torch.manual_seed(g["torch_seed"])
         loss, _ = calculate_losses(mods[1:], InfoNCE(temperature=0.001), GOT, None, embs, toks, g["labels"][:, 1:], args)
         loss.backward()
-        outs.append((embs, toks, loss.detach(), {n: p.grad.clone() for n, p in model.named_parameters()}))
+        outs.append((embs, toks, loss.detach(), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}))
     (e1, t1, l1, g1), (e0, t0, l0, g0) = outs
     W = min(bs, T)
     for m in mods:
@@ -442,7 +442,7 @@ def test_bf16_mode_training_step(golden):
         torch.manual_seed(g["torch_seed"])
         loss, _ = calculate_losses(mods[1:], InfoNCE(temperature=0.1), None, None, embs, toks, g["labels"][:, 1:], args)
         loss.backward()
-        res.append((embs, loss.detach(), {n: p.grad.clone() for n, p in model.named_parameters()}))
+        res.append((embs, loss.detach(), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}))
     (e0, l0, g0), (e1, l1, g1) = res
     for m in mods:
         torch.testing.assert_close(e1[m], e0[m], rtol=5e-2, atol=2e-2)
@@ -468,7 +468,7 @@ def test_fp32_fwd_mode_same_forward_bf16_backward(golden):
         torch.manual_seed(g["torch_seed"])
         loss, _ = calculate_losses(mods[1:], InfoNCE(temperature=0.001), None, None, embs, toks, g["labels"][:, 1:], args)
         loss.backward()
-        res.append((embs, loss.detach(), {n: p.grad.clone() for n, p in model.named_parameters()}))
+        res.append((embs, loss.detach(), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}))
     (e0, l0, g0), (e1, l1, g1) = res
     for m in mods:
         assert torch.equal(e0[m], e1[m])

@@ -325,15 +325,13 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    _lib.kernel_events.clear()
-    _lib.timed_kernels = {"mdl_pool_fwd", "mdl_pool_weights", "mdl_pool_bwd_dlogit", "mdl_gemm_nt", "mdl_gemm_gated", "mdl_gemm_tn_accum"}
+    _lib.start_timing({"mdl_pool_fwd", "mdl_pool_weights", "mdl_pool_bwd_dlogit", "mdl_gemm_nt", "mdl_gemm_gated", "mdl_gemm_tn_accum"})
     _lib.launch_count[0] = 0
+    _lib.native_launches(reset=True)
     ms_step = timed(args.steps, lambda i: feats_dev, read_loss=False)
-    launches = _lib.launch_count[0] // args.steps
-    _lib.timed_kernels = None
+    launches = (_lib.launch_count[0] + _lib.native_launches()) // args.steps
     clocks = sampler.stop() if rank == 0 else None
-    kt = {name: [a.elapsed_time(b) for a, b in ev] for name, ev in _lib.kernel_events.items()}
-    _lib.kernel_events.clear()
+    kt = _lib.stop_timing()
 
     bags_per_step = B * N_STAINS * world
     value = bags_per_step / (ms_step * 1e-3)

@@ -172,6 +172,79 @@ int mdl_got_finish(const float* v, const float* q, int m, int n, int D, void* wo
                    const float* dthr_global, const float* wd, const float* gwd, float* loss, float* dv, float* dq,
                    void* stream);
 
+/* ---- native step executor (train-step caller) ------------------------------------------------------ */
+/* ONE call runs the whole encoder forward (ABMILEmbedder.forward + projector + token_projector, Model.py:110-159,
+ * 346-451) and ONE call its backward, over a caller-provided arena: every launch of the sequence that
+ * madeleine_b200/ops.py used to issue through ~45 separate host calls is issued here, natively, on `stream`.
+ * Arguments travel in three flat arrays indexed by the enums below (so the ABI survives new fields):
+ *   ip  const long long[MDL_ENC_I_COUNT]   sizes, flags and element offsets
+ *   fp  const double[MDL_ENC_F_COUNT]      dropout probabilities
+ *   pp  void* const[MDL_ENC_P_COUNT]       device pointers (and the stream)
+ * The arena (mdl_encoder_fwd_arena_bytes) holds every activation the backward pass needs; the caller keeps it alive
+ * until mdl_encoder_bwd ran.  mdl_encoder_bwd needs a scratch arena of mdl_encoder_bwd_arena_bytes as well.
+ * MDL_ENC_I_PHASE: 0 = whole backward; 1 = up to and including the moment the gradients of everything except the first
+ * two pre-attention layers and the stain embedding are final in `gmaster` (the caller may start reducing that range
+ * across ranks); 2 = the rest.  Weight/gradient segment offsets are those of ops.PackSpec. */
+enum mdl_enc_i {
+    MDL_ENC_I_M = 0, MDL_ENC_I_R, MDL_ENC_I_D_IN, MDL_ENC_I_D_IN_TOTAL, MDL_ENC_I_SE_DIM, MDL_ENC_I_N_HEADS,
+    MDL_ENC_I_NSPLIT_FWD, MDL_ENC_I_NPL_FWD, MDL_ENC_I_NSPLIT_BWD, MDL_ENC_I_NPL_BWD, MDL_ENC_I_ACT_BF16,
+    MDL_ENC_I_ACTIVATION, MDL_ENC_I_KEEP, MDL_ENC_I_WANT_TOKENS, MDL_ENC_I_WANT_PROJECTOR, MDL_ENC_I_WANT_REF,
+    MDL_ENC_I_N_VIEW_TOK, MDL_ENC_I_R2, MDL_ENC_I_N_SEL, MDL_ENC_I_SEED, MDL_ENC_I_PHASE,
+    MDL_ENC_I_BF_NUMEL, MDL_ENC_I_BF_W1, MDL_ENC_I_BF_W2, MDL_ENC_I_BF_W2T, MDL_ENC_I_BF_W3, MDL_ENC_I_BF_W3T,
+    MDL_ENC_I_BF_WAB, MDL_ENC_I_BF_WABT, MDL_ENC_I_BF_TP, MDL_ENC_I_BF_TPT,
+    /* fp32 vectors, in this order: b1 g1 be1 b2 g2 be2 b3 g3 be3 ba bb wc bc btp wp bp */
+    MDL_ENC_I_F32_B1, MDL_ENC_I_F32_G1, MDL_ENC_I_F32_BE1, MDL_ENC_I_F32_B2, MDL_ENC_I_F32_G2, MDL_ENC_I_F32_BE2,
+    MDL_ENC_I_F32_B3, MDL_ENC_I_F32_G3, MDL_ENC_I_F32_BE3, MDL_ENC_I_F32_BA, MDL_ENC_I_F32_BB, MDL_ENC_I_F32_WC,
+    MDL_ENC_I_F32_BC, MDL_ENC_I_F32_BTP, MDL_ENC_I_F32_WP, MDL_ENC_I_F32_BP,
+    /* packed gradient buffer: matrices then the same 16 vectors */
+    MDL_ENC_I_GR_NUMEL, MDL_ENC_I_GR_W1, MDL_ENC_I_GR_W2, MDL_ENC_I_GR_W3, MDL_ENC_I_GR_WAB, MDL_ENC_I_GR_TP,
+    MDL_ENC_I_GR_B1, MDL_ENC_I_GR_G1, MDL_ENC_I_GR_BE1, MDL_ENC_I_GR_B2, MDL_ENC_I_GR_G2, MDL_ENC_I_GR_BE2,
+    MDL_ENC_I_GR_B3, MDL_ENC_I_GR_G3, MDL_ENC_I_GR_BE3, MDL_ENC_I_GR_BA, MDL_ENC_I_GR_BB, MDL_ENC_I_GR_WC,
+    MDL_ENC_I_GR_BC, MDL_ENC_I_GR_BTP, MDL_ENC_I_GR_WP, MDL_ENC_I_GR_BP,
+    MDL_ENC_I_MASTER_NUMEL, MDL_ENC_I_MASTER_PRE0W, MDL_ENC_I_MASTER_EMB,
+    MDL_ENC_I_GR_N, MDL_ENC_I_GR_N_EARLY, MDL_ENC_I_GR_N_LATE,
+    MDL_ENC_I_COUNT
+};
+enum mdl_enc_f { MDL_ENC_F_P_PRE = 0, MDL_ENC_F_P_GATE, MDL_ENC_F_COUNT };
+enum mdl_enc_p {
+    MDL_ENC_P_STREAM = 0, MDL_ENC_P_X, MDL_ENC_P_CU, MDL_ENC_P_CODES, MDL_ENC_P_MASTER, MDL_ENC_P_WBF, MDL_ENC_P_WF32,
+    MDL_ENC_P_ARENA, MDL_ENC_P_SLIDE_HM, MDL_ENC_P_SLIDE, MDL_ENC_P_LOGITS, MDL_ENC_P_TOKENS, MDL_ENC_P_REF,
+    MDL_ENC_P_VIEW_TOK_IDX, MDL_ENC_P_VIEW_CU, MDL_ENC_P_VIEW_ROW2SEG, MDL_ENC_P_TOKEN_ROWS, MDL_ENC_P_TOKEN_SEL_OF_ROW,
+    MDL_ENC_P_BWD_ARENA, MDL_ENC_P_D_SLIDE, MDL_ENC_P_D_LOGITS, MDL_ENC_P_D_TOKENS, MDL_ENC_P_D_REF_HM, MDL_ENC_P_GMASTER,
+    MDL_ENC_P_GR_POS, MDL_ENC_P_GR_DST, MDL_ENC_P_GR_POS_EARLY, MDL_ENC_P_GR_DST_EARLY, MDL_ENC_P_GR_POS_LATE,
+    MDL_ENC_P_GR_DST_LATE,
+    MDL_ENC_P_COUNT
+};
+/* MDL_ENC_I_COUNT * 10000 + MDL_ENC_F_COUNT * 1000 + MDL_ENC_P_COUNT of the built library (binding sanity check). */
+int mdl_encoder_abi(void);
+long long mdl_encoder_fwd_arena_bytes(const long long* ip);
+long long mdl_encoder_bwd_arena_bytes(const long long* ip);
+/* Inputs: X fp32 [M, d_in] bag-packed, CU int32 [R+1], CODES int32 [R] (se_dim > 0), MASTER flat fp32 parameters,
+ * WBF / WF32 packed operand planes / vectors (mdl_gather_split / mdl_gather_f32 of MASTER).  Outputs: SLIDE_HM fp32
+ * [R + R2, n_heads*512] head-major pooled vectors (always), SLIDE [R + R2, 512] (want_projector), LOGITS [M, n_heads],
+ * TOKENS [M or n_sel, 128] (want_tokens), REF [M, 512, n_heads] (want_ref). */
+int mdl_encoder_fwd(const long long* ip, const double* fp, void* const* pp);
+/* D_SLIDE: [R + R2, 512] (want_projector) or head-major [R + R2, n_heads*512]; D_LOGITS [M, n_heads]; D_TOKENS
+ * [M or n_sel, 128]; D_REF_HM [M, n_heads*512] head-major in the activation dtype; any may be NULL.
+ * GMASTER [master_numel] receives the parameter gradients in MASTER's layout (overwritten). */
+int mdl_encoder_bwd(const long long* ip, const double* fp, void* const* pp);
+/* out[dst[i]] = src[pos[i]] — packed gradient buffer -> parameter layout in one pass. */
+int mdl_permute_f32(const float* src, const int* pos, const int* dst, long long n, float* out, void* stream);
+/* Number of C-ABI kernel entry points mdl_encoder_fwd / mdl_encoder_bwd called (all threads) since the last reset. */
+long long mdl_executor_launches(int reset);
+
+/* Per-launch device timing of the executor's kernels (process-wide switch; for bench.py's roofline only).  While enabled every
+ * launch issued by mdl_encoder_fwd / mdl_encoder_bwd whose tag is selected is bracketed by CUDA events on its stream
+ * (`on`: 0 = off, 1 = every launch, otherwise a bit mask, bit t = tag t; bit 0 set alone is spelled 1 = all).  mdl_profile_read
+ * synchronises on the recorded events, writes up to `max` (tag, milliseconds) pairs in launch order, clears the
+ * record and returns the number of pairs that were available. */
+enum mdl_prof_tag {
+    MDL_PROF_OTHER = 0, MDL_PROF_GEMM_NT, MDL_PROF_GEMM_GATED, MDL_PROF_GEMM_TN, MDL_PROF_LN_FWD, MDL_PROF_LN_BWD,
+    MDL_PROF_GATE_BWD, MDL_PROF_POOL_WEIGHTS, MDL_PROF_POOL_FWD, MDL_PROF_POOL_BWD, MDL_PROF_SKINNY, MDL_PROF_COUNT
+};
+int mdl_profile_enable(int on);
+int mdl_profile_read(int* tags, float* ms, int max);
+
 /* ---- optimiser (train-step caller) -------------------------------------------------------------- */
 /* Fused multi-tensor AdamW, one launch for all parameters (torch.optim.AdamW semantics; reference:
  * madeleine/utils/setup_components.py:194-196).  host_* are HOST arrays of n_tensors DEVICE pointers / element counts

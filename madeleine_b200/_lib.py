@@ -70,11 +70,22 @@ SIGNATURES = {
     "mdl_got_fwd_bwd": [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "mdl_got_main": [c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p],
     "mdl_got_finish": [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
+    "mdl_encoder_abi": [],
+    "mdl_encoder_fwd_arena_bytes": [c_p],
+    "mdl_encoder_bwd_arena_bytes": [c_p],
+    "mdl_encoder_fwd": [c_p, c_p, c_p],
+    "mdl_encoder_bwd": [c_p, c_p, c_p],
+    "mdl_permute_f32": [c_p, c_p, c_p, c_ll, c_p, c_p],
+    "mdl_executor_launches": [c_i],
+    "mdl_profile_enable": [c_i],
+    "mdl_profile_read": [c_p, c_p, c_i],
 }
-_RESTYPES = {"mdl_got_workspace_bytes": c_ll, "mdl_pool_workspace_bytes": c_ll}
+_RESTYPES = {"mdl_got_workspace_bytes": c_ll, "mdl_pool_workspace_bytes": c_ll, "mdl_encoder_fwd_arena_bytes": c_ll,
+             "mdl_encoder_bwd_arena_bytes": c_ll, "mdl_executor_launches": c_ll}
 # functions that return a value rather than a status code
 _VALUE_FUNCS = {"mdl_version", "mdl_built_arch", "mdl_got_workspace_bytes", "mdl_got_max_tokens", "mdl_pool_tsplit",
-                "mdl_pool_workspace_bytes", "mdl_adamw_max_tensors"}
+                "mdl_pool_workspace_bytes", "mdl_adamw_max_tensors", "mdl_encoder_abi", "mdl_encoder_fwd_arena_bytes",
+                "mdl_encoder_bwd_arena_bytes", "mdl_executor_launches", "mdl_profile_enable", "mdl_profile_read"}
 
 
 def exported_symbols():
@@ -108,6 +119,8 @@ def load():
             fn = getattr(lib, name)
             fn.argtypes = argtypes
             fn.restype = _RESTYPES.get(name, c_i)
+        from . import executor as _executor
+        _executor.check_abi(lib)
         _lib = lib
     return _lib
 
@@ -119,13 +132,53 @@ LAUNCHES = {
     "mdl_ln_gelu_fwd": 1, "mdl_ln_gelu_bwd": 1, "mdl_gate_bwd": 1, "mdl_pool_weights": 1, "mdl_pool_fwd": 1, "mdl_pool_bwd_dlogit": 1,
     "mdl_planes_to_ref_order": 1, "mdl_skinny_linear_fwd": 1, "mdl_skinny_linear_bwd": 2, "mdl_stain_rowbias": 1,
     "mdl_bag_colsum_planes": 1, "mdl_gather_rows_planes": 1, "mdl_stain_rowbias_bwd": 1, "mdl_colsum_f32": 1, "mdl_infonce_fwd": 4, "mdl_infonce_bwd": 2,
-    "mdl_got_extrema": 2, "mdl_got_fwd_bwd": 2, "mdl_got_main": 2, "mdl_got_finish": 1, "mdl_adamw_step": 1, "mdl_sample_gather_f32": 1,
+    "mdl_got_extrema": 2, "mdl_got_fwd_bwd": 2, "mdl_got_main": 2, "mdl_got_finish": 1, "mdl_adamw_step": 1, "mdl_sample_gather_f32": 1, "mdl_permute_f32": 1,
 }
+# mdl_encoder_fwd / mdl_encoder_bwd issue their launches natively; they are counted by the library (mdl_executor_launches)
+
+
+def native_launches(reset: bool = False) -> int:
+    """Kernel entry points issued by the native executor on this thread since the last reset."""
+    return int(load().mdl_executor_launches(1 if reset else 0))
 launch_count = [0]
 # optional per-kernel device timing: {name: [(start_event, end_event), ...]} filled when `timed_kernels` is a set of names
-# (or the string "all")
+# (or the string "all"); the native executor's launches are timed by the library itself (mdl_profile_*)
 timed_kernels = None
 kernel_events = {}
+_PROF_NAMES = ["other", "mdl_gemm_nt", "mdl_gemm_gated", "mdl_gemm_tn_accum", "mdl_ln_gelu_fwd", "mdl_ln_gelu_bwd", "mdl_gate_bwd",
+               "mdl_pool_weights", "mdl_pool_fwd", "mdl_pool_bwd_dlogit", "mdl_skinny_linear"]
+
+
+def start_timing(names="all"):
+    """Time every launch: entry points called from Python whose name is in ``names`` (or all of them), and every launch the
+    native executor issues.  Adds event records around each launch — use for attribution, not for the headline number."""
+    global timed_kernels
+    kernel_events.clear()
+    timed_kernels = names
+    lib = load()
+    lib.mdl_profile_read(None, None, 0)          # drop stale records
+    mask = 1
+    if names != "all":
+        mask = sum(1 << i for i, n in enumerate(_PROF_NAMES) if n in names and i > 0)
+    lib.mdl_profile_enable(mask)
+
+
+def stop_timing():
+    """-> {entry point name: [milliseconds per launch, in launch order]}; synchronises the device."""
+    global timed_kernels
+    lib = load()
+    timed_kernels = None
+    lib.mdl_profile_enable(0)
+    torch.cuda.synchronize()
+    out = {name: [a.elapsed_time(b) for a, b in ev] for name, ev in kernel_events.items()}
+    kernel_events.clear()
+    cap = 1 << 16
+    tags = (ctypes.c_int * cap)()
+    ms = (ctypes.c_float * cap)()
+    n = min(lib.mdl_profile_read(ctypes.cast(tags, ctypes.c_void_p), ctypes.cast(ms, ctypes.c_void_p), cap), cap)
+    for i in range(n):
+        out.setdefault(_PROF_NAMES[tags[i]], []).append(ms[i])
+    return out
 
 
 def _conv(a):
@@ -133,6 +186,8 @@ def _conv(a):
         return None
     if isinstance(a, torch.Tensor):
         return a.data_ptr()
+    if isinstance(a, ctypes.Array):
+        return ctypes.addressof(a)
     return a
 
 

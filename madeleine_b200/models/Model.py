@@ -62,6 +62,7 @@ class ABMILEmbedder(nn.Module):
         self._pack_cache = {}
         self._spec_cache = {}
         self._placeholders = None
+        self._flat = None
 
     # -- parameter containers (checkpoint layout) ---------------------------------------------------------------
     def _build_pre_attention_params(self, params):
@@ -102,6 +103,25 @@ class ABMILEmbedder(nn.Module):
             self._placeholders = [z(ops.TOK, C), z(ops.TOK), z(ops.HID, C), z(ops.HID)]
         return self._placeholders
 
+    def _flat_master(self, params, spec, dev):
+        """Flat fp32 concatenation of ``params`` in ops.PARAM_ORDER.  The first call re-points every parameter's storage at a
+        slice of ONE flat buffer (values unchanged; state_dict / load_state_dict / optimisers keep working on the same
+        Parameter objects), so afterwards the 'concatenation' is that buffer itself — no per-step torch.cat — and the flat
+        gradient the backward pass produces lines up with it for the fused optimiser.  Falls back to a plain copy whenever
+        the parameters cannot be re-pointed (replicas under nn.DataParallel, non-fp32 storage)."""
+        fm = self._flat
+        if fm is not None and fm.device == dev and fm.numel() == spec.master_numel:
+            base = fm.data_ptr()
+            if all(p.data_ptr() == base + 4 * o for p, o in zip(params, spec.param_offsets)):
+                return fm
+        flat = torch.cat([p.detach().reshape(-1).float() for p in params])
+        if all(p.is_leaf and p.dtype == torch.float32 and p.device == dev for p in params):
+            with torch.no_grad():
+                for p, o, n in zip(params, spec.param_offsets, spec.param_numels):
+                    p.data = flat[o:o + n].view(p.shape)
+            self._flat = flat
+        return flat
+
     def run_kernels(self, x, cu, codes, head_params, embedding_weight, *, se_dim, want_tokens, want_projector, want_ref_feats,
                     views=None, precision=None, token_rows=None, token_sel_of_row=None):
         """x [M, d_in] fp32 bag-packed → dict(slide, logits, tokens?, ref_feats?). Differentiable w.r.t. parameters."""
@@ -126,10 +146,12 @@ class ABMILEmbedder(nn.Module):
         if spec is None:
             spec = ops.PackSpec([tuple(p.shape) for p in params], self.n_heads, d_in_total, dev, d_in=d_in)
             self._spec_cache[(str(dev), se_dim)] = spec
-        versions = tuple((p.data_ptr(), p._version) for p in params)
+        master = self._flat_master(params, spec, dev)
+        # one int per parameter: version counters only grow, so their sum changes whenever any parameter was written
+        versions = (master.data_ptr(), sum(p._version for p in params))
         cached = self._pack_cache.get(key)
         if cached is None or cached[0] != versions:
-            pw = ops.PackedWeights(spec, params, 1 if precision == "bf16" else 2)
+            pw = ops.PackedWeights(spec, master, 1 if precision == "bf16" else 2)
             self._pack_cache = {key: (versions, pw)}      # one live pack: weights change every optimiser step
         else:
             pw = cached[1]

@@ -20,6 +20,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
+from . import executor as _ex
 from ._lib import call, stream_ptr
 
 HID = 512          # wsi_encoder_hidden_dim the kernels are built for
@@ -178,6 +179,8 @@ class PackSpec:
         self.gr_dst_late = gr_dst_all[~early].to(torch.int32).to(device)
         self.off = off
         self.P = P
+        self.param_numels = [(offs[i + 1] if i + 1 < len(offs) else self.master_numel) - offs[i] for i in range(len(offs))]
+        self.ip_static = _ex.static_iparams(self)
 
 
 def PARAM_ORDER(n_heads: int) -> List[str]:
@@ -189,13 +192,15 @@ def PARAM_ORDER(n_heads: int) -> List[str]:
 
 
 class PackedWeights:
-    """Kernel-layout copies of the parameters for one precision; rebuilt whenever a parameter changes."""
+    """Kernel-layout copies of the parameters for one precision; rebuilt whenever a parameter changes.
 
-    def __init__(self, spec: PackSpec, params: Sequence[torch.Tensor], nplanes: int):
-        dev = params[0].device
+    ``master`` is the flat fp32 concatenation of the parameters in PARAM_ORDER — normally the very buffer the parameters
+    are views of (ABMILEmbedder flattens them once), so re-packing after an optimiser step is two launches and no copy."""
+
+    def __init__(self, spec: PackSpec, master: torch.Tensor, nplanes: int):
+        dev = master.device
         st = stream_ptr(dev)
         self.spec, self.nplanes = spec, nplanes
-        master = torch.cat([p.detach().reshape(-1).float() for p in params])
         self.master = master
         self.bf = torch.empty(nplanes, spec.bf_numel, dtype=torch.bfloat16, device=dev)
         call("mdl_gather_split", master, spec.bf_idx, spec.bf_numel, self.bf, spec.bf_numel, nplanes, st)
@@ -213,7 +218,7 @@ class PackedWeights:
 
 
 # --------------------------------------------------------------------------------------------------------------
-# thin kernel wrappers
+# thin kernel wrappers (tests, tools and the few callers outside the executor)
 # --------------------------------------------------------------------------------------------------------------
 def _planes_empty(nplanes, M, C, dev):
     return torch.empty(nplanes, M, C, dtype=torch.bfloat16, device=dev)
@@ -294,13 +299,13 @@ def ln_gelu_bwd(z, gamma, beta, mean, rstd, dh_a, dh_b, pool_terms, n_heads, npl
 
 
 # --------------------------------------------------------------------------------------------------------------
-# encoder forward / backward
+# encoder forward / backward: one native call each (csrc/executor.cu)
 # --------------------------------------------------------------------------------------------------------------
 @dataclass
 class EncodeOptions:
     n_heads: int = 4
     activation: str = "softmax"
-    precision: str = "fp32"          # resolved: 'fp32' | 'bf16'
+    precision: str = "fp32"          # resolved: 'fp32' | 'bf16' | 'fp32_fwd'
     training: bool = False           # nn.Module.training → dropout active
     want_tokens: bool = False        # fused token_projector → tokens [M, 128]
     want_projector: bool = False     # fused projector → [R, 512] instead of pooled [R, 512, H]
@@ -334,228 +339,128 @@ class _Saved:
     pass
 
 
+_arena_bytes_cache: Dict[Tuple, int] = {}
+
+
+def _arena_bytes(which: str, ip: List[int], ipa) -> int:
+    """Arena size for this shape/flag combination (asked from the library once per combination)."""
+    I = _ex.I
+    key = (which, ip[I['M']], ip[I['R']], ip[I['D_IN']], ip[I['SE_DIM']], ip[I['NPL_FWD']], ip[I['NPL_BWD']], ip[I['ACT_BF16']],
+           ip[I['KEEP']], ip[I['WANT_TOKENS']], ip[I['N_VIEW_TOK']], ip[I['R2']], ip[I['N_SEL']], ip[I['GR_NUMEL']])
+    n = _arena_bytes_cache.get(key)
+    if n is None:
+        n = call("mdl_encoder_fwd_arena_bytes" if which == "fwd" else "mdl_encoder_bwd_arena_bytes", ipa)
+        if len(_arena_bytes_cache) > 4096:
+            _arena_bytes_cache.clear()
+        _arena_bytes_cache[key] = n
+    return n
+
+
 def encoder_forward(x: torch.Tensor, cu: torch.Tensor, codes: Optional[torch.Tensor], pw: PackedWeights, opt: EncodeOptions,
                     keep_for_backward: bool):
-    """Runs pre_attn → gated attention → pooling (→ projector, token_projector). Returns (outputs dict, saved)."""
+    """pre_attn → gated attention → pooling (→ projector, token_projector) in ONE native call.  Returns (outputs dict, saved)."""
     dev = x.device
-    st = stream_ptr(dev)
+    I = _ex.I
+    spec = pw.spec
     nsplit, npl = _nsplit(opt.precision)
+    nsplit_b, npl_b = _nsplit_bwd(opt.precision)
     H = opt.n_heads
     C = HID * H
     M = x.shape[0]
     R = cu.numel() - 1
     p_pre = 0.1 if opt.training else 0.0      # nn.Dropout(0.1) x3, Model.py:354,358,362
     p_gate = 0.25 if opt.training else 0.0    # nn.Dropout(0.25) on both gates, abmil.py:33-35
-    sv = _Saved()
-    sv.opt, sv.pw, sv.cu, sv.M, sv.R = opt, pw, cu, M, R
-
-    row2bag = torch.empty(M, dtype=torch.int32, device=dev)
-    call("mdl_row2bag", cu, R, row2bag, M, st)
-    sv.row2bag = row2bag
-
-    rowbias = None
-    if opt.se_dim > 0:
-        spec = pw.spec
-        w1 = pw.master[spec.off("pre0.w"):]
-        emb = pw.master[spec.off("emb.w"):]
-        rowbias = torch.empty(R, HID, dtype=torch.float32, device=dev)
-        call("mdl_stain_rowbias", emb, codes, w1, spec.d_in_total, opt.d_in, opt.se_dim, HID, R, rowbias, st)
-    sv.codes = codes
-
-    # bf16 mode: the Linear outputs that feed LayerNorm are stored as bf16, exactly what torch autocast hands LayerNorm in
-    # the reference's --precision bfloat16 runs (trainer.py:108); the fp32-grade modes keep them fp32
-    zdt = _act_dtype(opt.precision)
-    xp = split_planes(x, npl)
-    z1 = gemm_nt(xp, opt.d_in, pw.planes("w1"), HID, nsplit, bias=pw.vec("b1"), rowbias=rowbias, row2bag=row2bag, out_dtype=zdt)
-    h1, mean1, rstd1 = ln_gelu_fwd(z1, pw.vec("g1"), pw.vec("be1"), npl, p_pre, opt.seed, 1)
-    z2 = gemm_nt(h1, HID, pw.planes("w2"), HID, nsplit, bias=pw.vec("b2"), out_dtype=zdt)
-    h2, mean2, rstd2 = ln_gelu_fwd(z2, pw.vec("g2"), pw.vec("be2"), npl, p_pre, opt.seed, 2)
-    z3 = gemm_nt(h2, HID, pw.planes("w3"), C, nsplit, bias=pw.vec("b3"), out_dtype=zdt)
-    h3, mean3, rstd3 = ln_gelu_fwd(z3, pw.vec("g3"), pw.vec("be3"), npl, p_pre, opt.seed, 3)
-    if not keep_for_backward:
-        del z1, z2, z3, h1, h2
-
-    logits = torch.empty(M, H, dtype=torch.float32, device=dev)
-    gate_a = gate_b = None
-    if keep_for_backward:
-        gate_a = torch.empty(M, H * GATE, dtype=torch.float16, device=dev)
-        gate_b = torch.empty(M, H * GATE, dtype=torch.float16, device=dev)
-    wab, _, _, wab_ps = pw.planes("wab")
-    call("mdl_gemm_gated", h3, M, C, C, M * C, wab, wab_ps, M, H, nsplit, pw.vec("ba"), pw.vec("bb"), pw.vec("wc"), pw.vec("bc"),
-         logits, gate_a, gate_b, p_gate, opt.seed, st)
-
-    act = ACT_CODES[opt.activation]
-    pooled = torch.empty(R, C, dtype=torch.float32, device=dev)
-    attn_p = torch.empty(M, H, dtype=torch.float32, device=dev) if keep_for_backward else None
-    pool_fwd(h3, npl, logits, cu, None, R, M, H, HID, pooled, attn_p, act)
-    outs = {"logits": logits}
-    pooled_views = None
+    ip = list(spec.ip_static)
+    ip[I['M']], ip[I['R']], ip[I['D_IN']], ip[I['SE_DIM']] = M, R, opt.d_in, opt.se_dim
+    ip[I['NSPLIT_FWD']], ip[I['NPL_FWD']], ip[I['NSPLIT_BWD']], ip[I['NPL_BWD']] = nsplit, npl, nsplit_b, npl_b
+    ip[I['ACT_BF16']] = int(opt.precision == "bf16")
+    ip[I['ACTIVATION']] = ACT_CODES[opt.activation]
+    ip[I['KEEP']] = int(keep_for_backward)
+    ip[I['WANT_TOKENS']], ip[I['WANT_PROJECTOR']], ip[I['WANT_REF']] = int(opt.want_tokens), int(opt.want_projector), int(opt.want_ref_feats)
+    ip[I['SEED']] = opt.seed & 0x7FFFFFFFFFFFFFFF
+    R2 = 0
+    tok_idx = cu2 = row2seg2 = None
     if opt.views is not None:
         tok_idx, cu2, row2seg2 = opt.views
         R2 = cu2.numel() - 1
-        pooled_views = torch.empty(R2, C, dtype=torch.float32, device=dev)
-        attn_p2 = torch.zeros(M, H, dtype=torch.float32, device=dev) if keep_for_backward else None
-        # the half views are always re-normalised with a softmax over the raw logits, whatever config.activation is
-        # (Model.py:436: F.softmax(attention_weights[:, view_idx], dim=1)); only the whole view uses the configured activation
-        pool_fwd(h3, npl, logits, cu2, tok_idx, R2, tok_idx.numel(), H, HID, pooled_views, attn_p2, ACT_CODES["softmax"])
-        sv.attn_p2, sv.pooled_views = attn_p2, pooled_views
-    # all slide vectors that go through the projector: [whole views | half views]
-    slide_hm = pooled if pooled_views is None else torch.cat([pooled, pooled_views], dim=0)
+        ip[I['N_VIEW_TOK']], ip[I['R2']] = tok_idx.numel(), R2
+    n_sel = 0
+    if opt.want_tokens and opt.token_rows is not None:
+        n_sel = opt.token_rows.numel()
+        ip[I['N_SEL']] = n_sel
+    ipa = _ex.iarr(ip)
+    fpa = _ex.farr(p_pre, p_gate)
+    arena = torch.empty(_arena_bytes("fwd", ip, ipa), dtype=torch.uint8, device=dev)
+    f32 = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)  # noqa: E731
+    n_slide = R + R2
+    logits = f32(M, H)
+    slide_hm = f32(n_slide, C)
+    slide = f32(n_slide, HID) if opt.want_projector else None
+    tokens = f32(n_sel if n_sel else M, TOK) if opt.want_tokens else None
+    ref = f32(M, HID, H) if opt.want_ref_feats else None
+    ptrs = {"STREAM": stream_ptr(dev), "X": x, "CU": cu, "CODES": codes, "MASTER": pw.master, "WBF": pw.bf, "WF32": pw.f32, "ARENA": arena,
+            "SLIDE_HM": slide_hm, "SLIDE": slide, "LOGITS": logits, "TOKENS": tokens, "REF": ref, "VIEW_TOK_IDX": tok_idx, "VIEW_CU": cu2,
+            "VIEW_ROW2SEG": row2seg2, "TOKEN_ROWS": opt.token_rows if n_sel else None,
+            "TOKEN_SEL_OF_ROW": opt.token_sel_of_row if n_sel else None}
+    call("mdl_encoder_fwd", ipa, fpa, _ex.parr(ptrs))
+    outs = {"logits": logits, "tokens": tokens, "ref_feats": ref}
     if opt.want_projector:
-        emb = torch.empty(slide_hm.shape[0], HID, dtype=torch.float32, device=dev)
-        call("mdl_skinny_linear_fwd", slide_hm, pw.vec("wp"), pw.vec("bp"), slide_hm.shape[0], C, HID, emb, st)
-        outs["slide"] = emb
+        outs["slide"] = slide
     else:
         # reference layout [*, E, H] (c = e*H + h) from head-major [*, H, E]
         outs["slide"] = slide_hm.view(-1, H, HID).transpose(1, 2).contiguous()
-    h3_sel = None
-    if opt.want_tokens:
-        if opt.token_rows is not None:
-            n_sel = opt.token_rows.numel()
-            h3_sel = _planes_empty(npl, n_sel, C, dev)
-            call("mdl_gather_rows_planes", h3, M * C, npl, C, opt.token_rows, n_sel, h3_sel, n_sel * C, st)
-            outs["tokens"] = gemm_nt(h3_sel, C, pw.planes("tp"), TOK, nsplit, bias=pw.vec("btp"))
-        else:
-            outs["tokens"] = gemm_nt(h3, C, pw.planes("tp"), TOK, nsplit, bias=pw.vec("btp"))
-    if opt.want_ref_feats:
-        ref = torch.empty(M, HID, H, dtype=torch.float32, device=dev)
-        call("mdl_planes_to_ref_order", h3, M * C, npl, M, H, HID, ref, st)
-        outs["ref_feats"] = ref
+    sv = None
     if keep_for_backward:
-        sv.xp, sv.z1, sv.mean1, sv.rstd1, sv.h1 = xp, z1, mean1, rstd1, h1
-        sv.z2, sv.mean2, sv.rstd2, sv.h2 = z2, mean2, rstd2, h2
-        sv.z3, sv.mean3, sv.rstd3, sv.h3 = z3, mean3, rstd3, h3
-        sv.logits, sv.gate_a, sv.gate_b, sv.attn_p, sv.pooled, sv.slide_hm = logits, gate_a, gate_b, attn_p, pooled, slide_hm
-        sv.p_pre, sv.p_gate = p_pre, p_gate
-        sv.h3_sel = h3_sel
+        sv = _Saved()
+        sv.opt, sv.pw, sv.M, sv.R, sv.n_slide = opt, pw, M, R, n_slide
+        sv.ip, sv.fpa, sv.ptrs = ip, fpa, ptrs          # ptrs keeps every tensor the backward pass reads alive
     return outs, sv
-
-
-def _scatter_grads(gp, pos, dst, gmaster, st):
-    if pos.numel() == 0:
-        return
-    compact = torch.empty(pos.numel(), dtype=torch.float32, device=gp.device)
-    call("mdl_gather_f32", gp, pos, pos.numel(), compact, st)
-    call("mdl_scatter_f32", compact, dst, dst.numel(), gmaster, 0, st)
 
 
 def encoder_backward(sv, d_slide: Optional[torch.Tensor], d_logits: Optional[torch.Tensor], d_tokens: Optional[torch.Tensor],
                      d_ref_feats: Optional[torch.Tensor], early_sync=None) -> torch.Tensor:
-    """Returns the flat master-layout gradient of all parameters.
+    """Returns the flat master-layout gradient of all parameters (ONE native call; two when ``early_sync`` is given).
 
     ``early_sync(gmaster, lo, hi)`` (optional) is called as soon as ``gmaster[lo:hi]`` — everything except the first two
     pre-attention layers and the stain embedding — is final, while the rest of the backward pass is still to be issued."""
     opt, pw = sv.opt, sv.pw
     spec = pw.spec
-    dev = sv.h3.device
-    st = stream_ptr(dev)
-    _, fwd_npl = _nsplit(opt.precision)          # planes of the saved forward activations
-    nsplit, npl = _nsplit_bwd(opt.precision)     # passes / planes of everything the backward pass produces and multiplies
+    I = _ex.I
+    dev = pw.master.device
     H = opt.n_heads
     C = HID * H
-    M, R = sv.M, sv.R
-    act = ACT_CODES[opt.activation]
-
-    gp = torch.zeros(spec.gr_numel, dtype=torch.float32, device=dev)
-
-    def g(name):
-        s = spec.gr_segs[name]
-        v = gp[s.off:s.off + s.numel]
-        return v.view(s.shape) if len(s.shape) > 1 else v
-
-    # ---- projector / pooled gradient (head-major) ----
-    n_slide = sv.slide_hm.shape[0]
-    if d_slide is None:
-        dS_all = torch.zeros(n_slide, C, dtype=torch.float32, device=dev)
-    elif opt.want_projector:
-        d_slide = d_slide.contiguous().float()
-        dS_all = torch.empty(n_slide, C, dtype=torch.float32, device=dev)
-        call("mdl_skinny_linear_bwd", d_slide, sv.slide_hm, pw.vec("wp"), n_slide, C, HID, dS_all, g("wp"), g("bp"), st)
-    else:
-        dS_all = d_slide.float().reshape(n_slide, HID, H).transpose(1, 2).contiguous().view(n_slide, C)
-    dS = dS_all[:R]
-
-    # ---- pooling backward: dlogit ----
-    dlogit = torch.empty(M, H, dtype=torch.float32, device=dev)
-    accumulate = 0
+    M, n_slide = sv.M, sv.n_slide
+    if d_slide is not None:
+        if opt.want_projector:
+            d_slide = d_slide.contiguous().float()
+        else:
+            d_slide = d_slide.float().reshape(n_slide, HID, H).transpose(1, 2).contiguous().view(n_slide, C)
     if d_logits is not None:
-        dlogit.copy_(d_logits.reshape(M, H))
-        accumulate = 1
-    call("mdl_pool_bwd_dlogit", sv.h3, M * C, fwd_npl, dS, sv.pooled, sv.attn_p, sv.cu, None, R, M, H, HID, dlogit, accumulate,
-         sv.logits, act, 0, st)
-    pool_terms = [(sv.attn_p, dS, sv.row2bag)]
-    if opt.views is not None:
-        tok_idx, cu2, row2seg2 = opt.views
-        dS2 = dS_all[R:]
-        call("mdl_pool_bwd_dlogit", sv.h3, M * C, fwd_npl, dS2, sv.pooled_views, sv.attn_p2, cu2, tok_idx, cu2.numel() - 1, tok_idx.numel(),
-             H, HID, dlogit, 1, sv.logits, ACT_CODES["softmax"], 0, st)
-        pool_terms.append((sv.attn_p2, dS2, row2seg2))
-
-    # ---- gated attention backward ----
-    dpre = _planes_empty(npl, M, H * 1024, dev)
-    call("mdl_gate_bwd", sv.gate_a, sv.gate_b, dlogit, pw.vec("wc"), M, H, sv.p_gate, opt.seed, dpre, M * H * 1024, npl,
-         g("ba"), g("bb"), g("wc"), g("bc"), st)
-    zdt = _act_dtype(opt.precision)
-    dh3_attn = gemm_nt(dpre, 1024, pw.planes("wabT"), C, nsplit, grp_n_cols=HID, a_koff=1024, out_dtype=zdt)
-    gemm_tn_accum(dpre, sv.h3, g("wab"), nsplit, grp_m_rows=1024, b_coff=HID)
-    del dpre
-
-    # ---- token projector backward ----
-    dh3_tok = None
-    dh3_tok_rows = None
+        d_logits = d_logits.reshape(M, H).contiguous().float()
     if d_tokens is not None:
-        tok_src = sv.h3 if sv.h3_sel is None else sv.h3_sel           # the rows token_projector saw in forward
-        n_tok = tok_src.shape[1]
-        d_tokens = d_tokens.reshape(n_tok, TOK).contiguous().float()
-        dtp = split_planes(d_tokens, npl)
-        dh3_tok = gemm_nt(dtp, TOK, pw.planes("tpT"), C, nsplit, out_dtype=zdt)   # [n_tok, C]; compact under a token window
-        gemm_tn_accum(dtp, tok_src, g("tp"), nsplit)
-        call("mdl_colsum_f32", d_tokens, n_tok, TOK, g("btp"), st)
-        if sv.h3_sel is not None:
-            dh3_tok_rows = opt.token_sel_of_row
+        d_tokens = d_tokens.reshape(-1, TOK).contiguous().float()
+    d_ref_hm = None
     if d_ref_feats is not None:
         # gradient w.r.t. the reference-order features → head-major, added as a second dh source
-        extra = d_ref_feats.float().reshape(M, HID, H).transpose(1, 2).contiguous().view(M, C).to(zdt)
-        if dh3_tok_rows is not None:
-            raise RuntimeError("madeleine_b200: a token window cannot be combined with gradients through the pre-attention features")
-        dh3_tok = extra if dh3_tok is None else dh3_tok.add_(extra)
-
-    # ---- layer 3 → 2 → 1 ----
-    dz3 = ln_gelu_bwd(sv.z3, pw.vec("g3"), pw.vec("be3"), sv.mean3, sv.rstd3, dh3_attn, dh3_tok, pool_terms, H, npl,
-                      sv.p_pre, opt.seed, 3, g("g3"), g("be3"), g("b3"), dh_b_rows=dh3_tok_rows)
-    del dh3_attn, dh3_tok
-    dh2 = gemm_nt(dz3, C, pw.planes("w3T"), HID, nsplit, out_dtype=zdt)
-    gemm_tn_accum(dz3, sv.h2, g("w3"), nsplit)
-    del dz3
-    gmaster = torch.zeros(spec.master_numel, dtype=torch.float32, device=dev)
-    if early_sync is not None:
-        _scatter_grads(gp, spec.gr_pos_early, spec.gr_dst_early, gmaster, st)
+        d_ref_hm = d_ref_feats.float().reshape(M, HID, H).transpose(1, 2).contiguous().view(M, C).to(_act_dtype(opt.precision))
+    ip = list(sv.ip)
+    ipa = _ex.iarr(ip)
+    barena = torch.empty(_arena_bytes("bwd", ip, ipa), dtype=torch.uint8, device=dev)
+    gmaster = torch.empty(spec.master_numel, dtype=torch.float32, device=dev)
+    ptrs = dict(sv.ptrs)
+    ptrs.update({"STREAM": stream_ptr(dev), "BWD_ARENA": barena, "D_SLIDE": d_slide, "D_LOGITS": d_logits, "D_TOKENS": d_tokens,
+                 "D_REF_HM": d_ref_hm, "GMASTER": gmaster, "GR_POS": spec.gr_pos, "GR_DST": spec.gr_dst,
+                 "GR_POS_EARLY": spec.gr_pos_early, "GR_DST_EARLY": spec.gr_dst_early, "GR_POS_LATE": spec.gr_pos_late,
+                 "GR_DST_LATE": spec.gr_dst_late})
+    pp = _ex.parr(ptrs)
+    if early_sync is None:
+        call("mdl_encoder_bwd", ipa, sv.fpa, pp)
+    else:
+        ip[I['PHASE']] = 1
+        call("mdl_encoder_bwd", _ex.iarr(ip), sv.fpa, pp)
         early_sync(gmaster, spec.early_lo, spec.early_hi)
-    dz2 = ln_gelu_bwd(sv.z2, pw.vec("g2"), pw.vec("be2"), sv.mean2, sv.rstd2, dh2, None, [], 1, npl, sv.p_pre, opt.seed, 2,
-                      g("g2"), g("be2"), g("b2"))
-    dh1 = gemm_nt(dz2, HID, pw.planes("w2T"), HID, nsplit, out_dtype=zdt)
-    gemm_tn_accum(dz2, sv.h1, g("w2"), nsplit)
-    G = torch.zeros(R, HID, dtype=torch.float32, device=dev) if opt.se_dim > 0 else None   # per-bag column sums of dz1
-    dz1 = ln_gelu_bwd(sv.z1, pw.vec("g1"), pw.vec("be1"), sv.mean1, sv.rstd1, dh1, None, [], 1, npl, sv.p_pre, opt.seed, 1,
-                      g("g1"), g("be1"), g("b1"), row2bag=sv.row2bag if G is not None else None, bag_dz=G)
-    if opt.d_in % 256 == 0:
-        gemm_tn_accum(dz1, sv.xp, g("w1"), nsplit)
-    else:
-        # the wgrad tile is 128 x 256: for feature widths that are a multiple of 128 only (384, 640, ...) compute dW1^T
-        w1t = torch.zeros(opt.d_in, HID, dtype=torch.float32, device=dev)
-        gemm_tn_accum(sv.xp, dz1, w1t, nsplit)
-        g("w1").add_(w1t.t())
-
-    # scatter packed grads into parameter layout (gr_pos → gr_dst): gather the compact list, then scatter
-    if early_sync is not None:
-        _scatter_grads(gp, spec.gr_pos_late, spec.gr_dst_late, gmaster, st)
-    else:
-        _scatter_grads(gp, spec.gr_pos, spec.gr_dst, gmaster, st)
-    if opt.se_dim > 0:
-        w1 = pw.master[spec.off("pre0.w"):]
-        emb = pw.master[spec.off("emb.w"):]
-        call("mdl_stain_rowbias_bwd", G, emb, sv.codes, w1, spec.d_in_total, opt.d_in, opt.se_dim, HID, R,
-             gmaster[spec.off("pre0.w"):], gmaster[spec.off("emb.w"):], st)
+        ip[I['PHASE']] = 2
+        call("mdl_encoder_bwd", _ex.iarr(ip), sv.fpa, pp)
     return gmaster
 
 
@@ -616,10 +521,7 @@ class EncodeFn(torch.autograd.Function):
                 grads.append(None)
                 continue
             o = spec.param_offsets[i]
-            n = 1
-            for s in shape:
-                n *= s
-            grads.append(gmaster[o:o + n].view(shape))
+            grads.append(gmaster[o:o + spec.param_numels[i]].view(shape))
         ctx.sv = None
         return (None, None, *grads)
 

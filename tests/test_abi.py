@@ -142,3 +142,52 @@ def test_pack_spec_early_late_gradient_split(se):
     emb = spec.master_numel - spec.early_hi
     assert int((covered == 0).sum()) == stain_cols + emb          # only the stain columns of W1 and the embedding table come later
     assert int(covered.max()) == 1
+
+
+# ---------------------------------------------------------------------------------------------- native step executor
+def _header_enum(name):
+    text = open(HEADER).read()
+    body = re.search(r"enum %s \{(.*?)\};" % name, text, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    return [n.split("=")[0].strip() for n in body.split(",") if n.strip()]
+
+
+def test_executor_enums_mirror_the_header():
+    from madeleine_b200 import executor as ex
+    assert _header_enum("mdl_enc_i") == ["MDL_ENC_I_" + n for n in ex.ENC_I] + ["MDL_ENC_I_COUNT"]
+    assert _header_enum("mdl_enc_f") == ["MDL_ENC_F_" + n for n in ex.ENC_F] + ["MDL_ENC_F_COUNT"]
+    assert _header_enum("mdl_enc_p") == ["MDL_ENC_P_" + n for n in ex.ENC_P] + ["MDL_ENC_P_COUNT"]
+    assert len(_header_enum("mdl_prof_tag")) - 1 == len(ex.PROF_TAGS) == len(_lib._PROF_NAMES)
+    assert _lib.load().mdl_encoder_abi() == ex.ABI
+
+
+def test_executor_arena_plan_is_a_dry_run_of_the_launch_sequence():
+    """mdl_encoder_{fwd,bwd}_arena_bytes walk the same code as the real pass with a null arena (no GPU needed): sizes grow
+    with the token count, keep-for-backward costs the two fp16 gate buffers, bf16 mode halves the activation planes, and
+    the backward scratch covers the 16 KB/token gate-gradient planes."""
+    from madeleine_b200 import executor as ex
+    _, ps = _params()
+    spec = ops.PackSpec([tuple(p.shape) for p in ps], 4, 544, "cpu", d_in=512)
+    I = ex.I
+
+    def ip(M, R, keep=1, npl=2, want_tokens=1, n_sel=0, act_bf16=0):
+        v = list(spec.ip_static)
+        v[I["M"]], v[I["R"]], v[I["D_IN"]], v[I["SE_DIM"]] = M, R, 512, 32
+        v[I["NSPLIT_FWD"]], v[I["NPL_FWD"]], v[I["NSPLIT_BWD"]], v[I["NPL_BWD"]] = 3 if npl == 2 else 1, npl, 3 if npl == 2 else 1, npl
+        v[I["KEEP"]], v[I["WANT_TOKENS"]], v[I["WANT_PROJECTOR"]], v[I["N_SEL"]], v[I["ACT_BF16"]] = keep, want_tokens, 1, n_sel, act_bf16
+        return ex.iarr(v)
+
+    fwd = lambda *a, **k: _lib.call("mdl_encoder_fwd_arena_bytes", ip(*a, **k))  # noqa: E731
+    bwd = lambda *a, **k: _lib.call("mdl_encoder_bwd_arena_bytes", ip(*a, **k))  # noqa: E731
+    M = 64000
+    full = fwd(M, 32)
+    # per token, fp32-grade: x planes 2 KB, z1/z2 2 KB each, h1/h2 2 KB each, z3 8 KB, h3 8 KB, gates 2 x 4 KB, + small
+    per_token = 2048 + 2 * 2048 + 2 * 2048 + 8192 + 8192 + 2 * 4096
+    assert per_token * M <= full <= (per_token + 256) * M
+    assert fwd(M, 32, keep=0) == pytest.approx(full - 2 * 4096 * M, rel=1e-3)
+    assert fwd(2 * M, 32) > 1.9 * full
+    assert fwd(M, 32, npl=1, act_bf16=1) < 0.65 * full          # the fp16 gate buffers do not shrink
+    assert fwd(M, 32, n_sel=1024) - full == pytest.approx(2 * 1024 * 2048 * 2, rel=1e-2)     # gathered rows for the token window
+    b = bwd(M, 32)
+    assert 16384 * M + 8192 * M <= b <= 56 * 1024 * M
+    assert bwd(M, 32, n_sel=1024) <= b                                                        # compact token_projector gradient

@@ -55,17 +55,15 @@ def config3(precision, steps, warmup, skip=True, bs=32, tag="BASELINE configs[2]
     for _ in range(warmup):
         step()
     torch.cuda.synchronize()
-    _lib.kernel_events.clear()
-    _lib.timed_kernels = "all" if breakdown else {"mdl_got_fwd_bwd", "mdl_got_extrema", "mdl_infonce_fwd", "mdl_infonce_bwd"}
+    _lib.start_timing("all" if breakdown else {"mdl_got_fwd_bwd", "mdl_got_extrema", "mdl_infonce_fwd", "mdl_infonce_bwd"})
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
         loss = step()
     e1.record()
     torch.cuda.synchronize()
-    _lib.timed_kernels = None
     ms = e0.elapsed_time(e1) / steps
-    kt = {k: round(sum(a.elapsed_time(b) for a, b in v) / steps, 4) for k, v in _lib.kernel_events.items()}
+    kt = {k: round(sum(v) / steps, 4) for k, v in _lib.stop_timing().items()}
     bags = bs * 5
     print(json.dumps({"config": tag + ", 5 stains, T=2048, stain encodings, InfoNCE + GOT, fwd+bwd, train mode",
                       "missing_bags_encoded_from_one_token": skip, "token_window": token_window, "missing_bag_fraction": float(1 - labels.mean()),

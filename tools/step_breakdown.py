@@ -50,12 +50,9 @@ for _ in range(a.steps):
 e1.record()
 torch.cuda.synchronize()
 ms_plain = e0.elapsed_time(e1) / a.steps
-_lib.kernel_events.clear()
-_lib.timed_kernels = "all"
+_lib.start_timing("all")
 for _ in range(a.steps):
     step()
-torch.cuda.synchronize()
-_lib.timed_kernels = None
-kt = {k: round(sum(x.elapsed_time(y) for x, y in v) / a.steps, 4) for k, v in _lib.kernel_events.items()}
+kt = {k: round(sum(v) / a.steps, 4) for k, v in _lib.stop_timing().items()}
 print(json.dumps({"precision": a.precision, "ms_per_step": round(ms_plain, 3), "sum_of_entry_points_ms": round(sum(kt.values()), 3),
                   "entry_point_ms_per_step": dict(sorted(kt.items(), key=lambda kv: -kv[1]))}))

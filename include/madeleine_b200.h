@@ -149,6 +149,16 @@ int mdl_infonce_fwd(const float* q, const float* k, int m, int D, float temperat
 int mdl_infonce_bwd(const float* q, const float* k, int m, int D, float temperature,
                     const float* qn, const float* kn, const float* L, const float* lse_r, const float* lse_c,
                     const float* w_r, const float* w_c, float* G, float* dq, float* dk, void* stream);
+/* The same loss on rows picked out of one matrix: q_i = base + q_rows[i] * ld, k_i = base + k_rows[i] * ld (the boolean-mask
+ * row selection of calculate_losses, madeleine/utils/trainer.py:28-33, fused into the kernels — no gathered copies, no
+ * index_put in backward).  reduction = mean.  `workspace`: mdl_infonce_rows_workspace_floats(m) floats, kept by the caller
+ * from forward to backward.  loss: this term; total (optional): running sum over the terms of a step (+=, stream-ordered).
+ * Backward ADDS (*go) * d loss / d row into dbase (same layout as base; the caller zero-fills it once per step). */
+long long mdl_infonce_rows_workspace_floats(int m);
+int mdl_infonce_rows_fwd(const float* base, long long ld, const int* q_rows, const int* k_rows, int m, int D, float temperature,
+                         int symmetric, float* workspace, float* loss, float* total, void* stream);
+int mdl_infonce_rows_bwd(const float* base, long long ld, const int* q_rows, const int* k_rows, int m, int D, float temperature,
+                         int symmetric, float* workspace, const float* go, float* dbase, void* stream);
 /* Graph-OT local loss, forward and backward in one call (GOT, madeleine/utils/loss.py:278-301 with
  * cost_matrix_batch_torch :162-176, IPOT :179-207, cos_batch_torch :210-233, GW :236-275).
  * v, q [m, n, D] (already token-subsampled); loss = sum_b (wd_b + gwd_b); dv, dq = d loss / d v, q.

@@ -60,6 +60,9 @@ SIGNATURES = {
     "mdl_colsum_f32": [c_p, c_ll, c_i, c_p, c_p],
     "mdl_infonce_fwd": [c_p, c_p, c_i, c_i, c_f, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "mdl_infonce_bwd": [c_p, c_p, c_i, c_i, c_f, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
+    "mdl_infonce_rows_workspace_floats": [c_i],
+    "mdl_infonce_rows_fwd": [c_p, c_ll, c_p, c_p, c_i, c_i, c_f, c_i, c_p, c_p, c_p, c_p],
+    "mdl_infonce_rows_bwd": [c_p, c_ll, c_p, c_p, c_i, c_i, c_f, c_i, c_p, c_p, c_p, c_p],
     "mdl_adamw_max_tensors": [],
     "mdl_adamw_step": [c_i, c_p, c_p, c_p, c_p, c_p, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_p],
     "mdl_sample_gather_f32": [c_p, c_p, c_p, c_i, c_i, c_i, c_ull, c_p, c_p, c_p],
@@ -81,11 +84,12 @@ SIGNATURES = {
     "mdl_profile_read": [c_p, c_p, c_i],
 }
 _RESTYPES = {"mdl_got_workspace_bytes": c_ll, "mdl_pool_workspace_bytes": c_ll, "mdl_encoder_fwd_arena_bytes": c_ll,
-             "mdl_encoder_bwd_arena_bytes": c_ll, "mdl_executor_launches": c_ll}
+             "mdl_encoder_bwd_arena_bytes": c_ll, "mdl_executor_launches": c_ll, "mdl_infonce_rows_workspace_floats": c_ll}
 # functions that return a value rather than a status code
 _VALUE_FUNCS = {"mdl_version", "mdl_built_arch", "mdl_got_workspace_bytes", "mdl_got_max_tokens", "mdl_pool_tsplit",
                 "mdl_pool_workspace_bytes", "mdl_adamw_max_tensors", "mdl_encoder_abi", "mdl_encoder_fwd_arena_bytes",
-                "mdl_encoder_bwd_arena_bytes", "mdl_executor_launches", "mdl_profile_enable", "mdl_profile_read"}
+                "mdl_encoder_bwd_arena_bytes", "mdl_executor_launches", "mdl_profile_enable", "mdl_profile_read",
+                "mdl_infonce_rows_workspace_floats"}
 
 
 def exported_symbols():
@@ -131,7 +135,7 @@ LAUNCHES = {
     "mdl_gemm_nt": 1, "mdl_gemm_gated": 1, "mdl_gemm_tn_accum": 1, "mdl_gemm_nt_simt": 1, "mdl_gemm_tn_simt": 1,
     "mdl_ln_gelu_fwd": 1, "mdl_ln_gelu_bwd": 1, "mdl_gate_bwd": 1, "mdl_pool_weights": 1, "mdl_pool_fwd": 1, "mdl_pool_bwd_dlogit": 1,
     "mdl_planes_to_ref_order": 1, "mdl_skinny_linear_fwd": 1, "mdl_skinny_linear_bwd": 2, "mdl_stain_rowbias": 1,
-    "mdl_bag_colsum_planes": 1, "mdl_gather_rows_planes": 1, "mdl_stain_rowbias_bwd": 1, "mdl_colsum_f32": 1, "mdl_infonce_fwd": 4, "mdl_infonce_bwd": 2,
+    "mdl_bag_colsum_planes": 1, "mdl_gather_rows_planes": 1, "mdl_stain_rowbias_bwd": 1, "mdl_colsum_f32": 1, "mdl_infonce_fwd": 4, "mdl_infonce_bwd": 2, "mdl_infonce_rows_fwd": 4, "mdl_infonce_rows_bwd": 2,
     "mdl_got_extrema": 2, "mdl_got_fwd_bwd": 2, "mdl_got_main": 2, "mdl_got_finish": 1, "mdl_adamw_step": 1, "mdl_sample_gather_f32": 1, "mdl_permute_f32": 1,
 }
 # mdl_encoder_fwd / mdl_encoder_bwd issue their launches natively; they are counted by the library (mdl_executor_launches)

@@ -357,7 +357,7 @@ class MADELEINE(nn.Module):
 
     def forward(self, data, device, train=True, n_views=1, custom_stain_idx=None, return_attention=False):
         all_wsi_feats = data["feats"].to(device)
-        all_embeddings, all_token_embeddings = {}, {}
+        all_embeddings, all_token_embeddings = ops.EmbeddingDict(), {}
 
         if train:
             bs, n_mod, n_tokens, d_in = all_wsi_feats.shape
@@ -411,6 +411,8 @@ class MADELEINE(nn.Module):
                 whole, halves = slide[:R], slide[R:].view(2, R, d_out).transpose(0, 1)
                 slide_embeddings = torch.cat([whole.unsqueeze(1), halves], dim=1).view(bs, n_mod, 3, d_out)
             token_embeddings = out["tokens"].view(bs, n_mod, n_tokens, -1)
+            # the loss glue may address the slide embeddings by row of this matrix instead of through the per-modality views
+            all_embeddings.b200_set(slide, bs, n_mod, 1 if n_views == 1 else 3)
             for idx, modality in enumerate(self.modalities):
                 slide_emb = slide_embeddings[:, idx, :, :]
                 token_emb = token_embeddings[:, idx, :]

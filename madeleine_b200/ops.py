@@ -577,6 +577,84 @@ def info_nce(query, positive_key, temperature=0.1, reduction="mean", symmetric=F
         return InfoNCEFn.apply(query, positive_key, temperature, symmetric, reduction)
 
 
+class EmbeddingDict(dict):
+    """The ``{modality: tensor}`` dict MADELEINE.forward(train=True) returns (Model.py:147-159) plus a handle on the matrix
+    all of its entries are views of, so that the loss glue can hand row INDEX LISTS to the kernels instead of materialising
+    boolean-mask selections (trainer.py:28-33).
+
+    ``b200_base`` [n_rows, 512]: the encoder's slide embeddings; ``b200_row(case, modality, view)`` -> row of that matrix
+    (works on LongTensors / ints)."""
+
+    b200_base: Optional[torch.Tensor] = None
+
+    def b200_set(self, base, bs, n_mod, n_views, world=1):
+        self.b200_base, self.b200_bs, self.b200_n_mod, self.b200_n_views, self.b200_world = base, bs, n_mod, n_views, world
+        return self
+
+    def b200_row(self, case, modality, view):
+        # encoder output order: [whole views of all (case, modality) rows | half view 1 | half view 2]; under case sharding
+        # every rank contributes one such block, rank-major (parallel.all_gather_rows)
+        R = self.b200_bs * self.b200_n_mod
+        rank, local = case // self.b200_bs, case % self.b200_bs
+        return rank * (R * self.b200_n_views) + view * R + local * self.b200_n_mod + modality
+
+
+class InfoNCERowsFn(torch.autograd.Function):
+    """Sum of mean-reduced (optionally symmetric) InfoNCE terms whose operands are ROWS of one matrix; one autograd node for
+    all stains / views of a step, no gathered copies, no index_put in backward.  ``plan``: dict(idx=int32 device tensor with
+    all row lists back to back, terms=[(q_offset, k_offset, m, temperature, symmetric), ...])."""
+
+    @staticmethod
+    def forward(ctx, base, plan):
+        dev = base.device
+        base_c = base.contiguous().float()
+        n_rows, D = base_c.shape
+        st = stream_ptr(dev)
+        terms, idx = plan["terms"], plan["idx"]
+        sizes = [int(call("mdl_infonce_rows_workspace_floats", m)) for _, _, m, _, _ in terms]
+        ws = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+        out = torch.zeros(len(terms) + 1, dtype=torch.float32, device=dev)          # [total | per-term losses]
+        o = 0
+        offs = []
+        for t, ((qo, ko, m, tau, sym), n) in enumerate(zip(terms, sizes)):
+            call("mdl_infonce_rows_fwd", base_c, D, idx[qo:], idx[ko:], m, D, float(tau), int(bool(sym)), ws[o:], out[t + 1:], out, st)
+            offs.append(o)
+            o += n
+        ctx.save_for_backward(base_c, idx, ws)
+        ctx.meta = (terms, offs)
+        ctx.per_term = out[1:]
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, go):
+        base_c, idx, ws = ctx.saved_tensors
+        terms, offs = ctx.meta
+        dev = base_c.device
+        D = base_c.shape[1]
+        go = go.contiguous().float()
+        dbase = torch.zeros_like(base_c)
+        st = stream_ptr(dev)
+        for (qo, ko, m, tau, sym), o in zip(terms, offs):
+            call("mdl_infonce_rows_bwd", base_c, D, idx[qo:], idx[ko:], m, D, float(tau), int(bool(sym)), ws[o:], go, dbase, st)
+        return dbase, None
+
+
+def info_nce_rows(base: torch.Tensor, row_lists, temperatures, symmetric):
+    """row_lists: [(q_rows, k_rows)] CPU int tensors/lists of equal length per pair; returns the SUM of the terms' losses."""
+    _lib.require_cuda(base, "slide embeddings")
+    flat, terms, o = [], [], 0
+    for (q_rows, k_rows), tau, sym in zip(row_lists, temperatures, symmetric):
+        q_rows = torch.as_tensor(q_rows, dtype=torch.int32)
+        k_rows = torch.as_tensor(k_rows, dtype=torch.int32)
+        m = q_rows.numel()
+        terms.append((o, o + m, m, tau, sym))
+        flat += [q_rows, k_rows]
+        o += 2 * m
+    idx = torch.cat(flat).pin_memory().to(base.device, non_blocking=True)          # ONE small upload for all terms
+    with torch.cuda.device(base.device):
+        return InfoNCERowsFn.apply(base, {"idx": idx, "terms": terms})
+
+
 # --------------------------------------------------------------------------------------------------------------
 # Graph-OT local loss
 # --------------------------------------------------------------------------------------------------------------

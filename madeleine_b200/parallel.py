@@ -15,6 +15,8 @@ from typing import Dict
 import torch
 import torch.distributed as dist
 
+from . import ops
+
 
 class _AllGatherRows(torch.autograd.Function):
     """[B_local, ...] → [world * B_local, ...] (rank-major). Backward: this rank's slice of the incoming gradient."""
@@ -54,15 +56,39 @@ def gradient_sync_enabled() -> bool:
     return _GRAD_SYNC[0] and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
 
+class _GatheredEmbeddings(ops.EmbeddingDict):
+    """Per-modality views of the all-gathered slide-embedding matrix, built only if somebody asks for them (the fused loss
+    glue addresses the matrix by row and never does)."""
+
+    def __init__(self, modalities, n_mod):
+        super().__init__()
+        self._modalities, self._n_mod = list(modalities), n_mod
+
+    def __missing__(self, key):
+        i = self._modalities.index(key)                       # KeyError semantics for unknown names
+        world, v, bs, n_mod = self.b200_world, self.b200_n_views, self.b200_bs, self.b200_n_mod
+        t = self.b200_base.view(world, v, bs, n_mod, -1)[:, :, :, i].permute(0, 2, 1, 3).reshape(world * bs, v, -1)
+        if key == "HE":
+            t = t.unsqueeze(-1).expand(*t.shape, n_mod - 1)
+        self[key] = t
+        return t
+
+
 def gather_slide_embeddings(wsi_embs: Dict[str, torch.Tensor], modality_labels: torch.Tensor, global_labels_host=None):
     """All-gather the per-modality slide embeddings ([B_local, n_views, 512(, n_mod-1)]) and the availability mask in a
     single collective: everything is packed into one [B_local, F] fp32 buffer, gathered once, and unpacked.
 
     ``global_labels_host`` (optional, CPU tensor [B_global, n_mod]): the availability mask of the whole batch when the
     loader already knows it (it comes from the case list); it is returned instead of the gathered device copy so the loss
-    glue needs no device->host sync."""
+    glue needs no device->host sync.  In that case, and when ``wsi_embs`` comes from this package's MADELEINE.forward, the
+    encoder's slide-embedding matrix itself is gathered (no packing copies) and the result addresses it by row."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
         return wsi_embs, (modality_labels if global_labels_host is None else global_labels_host)
+    base = getattr(wsi_embs, "b200_base", None)
+    if base is not None and global_labels_host is not None and getattr(wsi_embs, "b200_world", 1) == 1:
+        out = _GatheredEmbeddings(list(wsi_embs.keys()), wsi_embs.b200_n_mod)
+        out.b200_set(all_gather_rows(base), wsi_embs.b200_bs, wsi_embs.b200_n_mod, wsi_embs.b200_n_views, world=dist.get_world_size())
+        return out, global_labels_host
     keys = list(wsi_embs.keys())
     B = modality_labels.shape[0]
     dev = wsi_embs[keys[0]].device

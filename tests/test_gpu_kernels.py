@@ -479,3 +479,32 @@ def test_pool_empty_and_single_token_bags():
     call("mdl_pool_bwd_dlogit", xp, M * C, 2, dS, out, attn, cu, None, len(lens), M, H, E, dlogit, 0, logits, 0, 1, _st())
     assert torch.isfinite(dlogit).all()
     assert float(dlogit[0].abs().max()) < 1e-3          # a one-token bag has a constant softmax: zero logit gradient (up to fp32 rounding of two 512-term dots)
+
+
+def test_infonce_rows_equals_gathered_operands():
+    """mdl_infonce_rows_fwd/bwd (operands = indexed rows of one matrix, several terms accumulated into one gradient) against
+    the dense entry points on explicitly gathered copies, and against torch autograd through the index ops."""
+    from madeleine_b200 import ops
+    from madeleine_b200.utils.loss import InfoNCE
+    g = torch.Generator().manual_seed(3)
+    base = torch.randn(40, 512, generator=g).to(DEV).requires_grad_(True)
+    pairs = [(torch.tensor([0, 2, 4, 6, 8, 10]), torch.tensor([1, 3, 5, 7, 9, 11])),
+             (torch.tensor([0, 4, 8, 20, 30]), torch.tensor([13, 15, 17, 19, 39]))]        # H&E rows shared between the terms
+    for tau, sym in ((0.1, True), (0.001, True), (0.07, False)):
+        base.grad = None
+        total = ops.info_nce_rows(base, pairs, [tau] * len(pairs), [sym] * len(pairs))
+        total.backward()
+        got = base.grad.clone()
+        base.grad = None
+        fn = InfoNCE(temperature=tau)
+        ref = sum(fn(base[q.to(DEV)], base[k.to(DEV)], symmetric=sym) for q, k in pairs)
+        ref.backward()
+        torch.testing.assert_close(total.detach(), ref.detach(), rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(got, base.grad, rtol=1e-5, atol=1e-7)
+    # upstream scaling
+    base.grad = None
+    (ops.info_nce_rows(base, pairs, [0.1, 0.1], [True, True]) * 3.0).backward()
+    g3 = base.grad.clone()
+    base.grad = None
+    ops.info_nce_rows(base, pairs, [0.1, 0.1], [True, True]).backward()
+    torch.testing.assert_close(g3, 3.0 * base.grad, rtol=1e-6, atol=1e-8)

@@ -59,6 +59,32 @@ def _worker(rank, world, port, q):
         ref_loss.backward()
         torch.testing.assert_close(loss.detach(), ref_loss.detach(), rtol=1e-5, atol=1e-6)
         torch.testing.assert_close(lin.weight.grad, ref.weight.grad, rtol=1e-4, atol=1e-6)
+        # the row-addressed path: the encoder's slide-embedding matrix itself is gathered (rank-major blocks of
+        # [view][case][modality] rows) and the per-modality tensors are rebuilt from it on demand
+        from madeleine_b200 import ops
+        for n_views in (1, 3):
+            lin.weight.grad = None
+            base = lin(torch.randn(world * n_views * B * 2, 16, generator=torch.Generator().manual_seed(5))[rank * n_views * B * 2:
+                                                                                                       (rank + 1) * n_views * B * 2])
+            local = ops.EmbeddingDict()
+            blk = base.view(n_views, B, 2, 8)
+            local["HE"] = blk[:, :, 0].permute(1, 0, 2).unsqueeze(-1)
+            local["IHC"] = blk[:, :, 1].permute(1, 0, 2)
+            local.b200_set(base, B, 2, n_views)
+            g2, lab2 = parallel.gather_slide_embeddings(local, labels_all[rank * B:(rank + 1) * B], global_labels_host=labels_all)
+            assert lab2 is labels_all and g2.b200_world == world and g2.b200_base.shape == (world * n_views * B * 2, 8)
+            # same tensors as gathering the per-modality entries one by one
+            plain, _ = parallel.gather_slide_embeddings(dict(local), labels_all[rank * B:(rank + 1) * B])
+            torch.testing.assert_close(g2["HE"], plain["HE"])
+            torch.testing.assert_close(g2["IHC"], plain["IHC"])
+            for case in (0, B - 1, B, world * B - 1):
+                for mod in (0, 1):
+                    for view in range(n_views):
+                        row = g2.b200_row(case, mod, view)
+                        want = (g2["HE"][case, view, :, 0] if mod == 0 else g2["IHC"][case, view])
+                        assert torch.equal(g2.b200_base[row], want)
+            g2.b200_base.square().sum().backward()          # all-gather backward = this rank's slice
+            assert lin.weight.grad is not None
         q.put((rank, "ok"))
     except Exception as e:  # noqa: BLE001
         q.put((rank, f"{type(e).__name__}: {e}"))

@@ -159,7 +159,7 @@ def run_reference(args, rank, world):
     from weights import make_state_dict, make_feats
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cases = 2                                                     # bounded sample: 2 cases x 2 stains x 2000 tokens per step
+    cases = CASES_PER_GPU                                         # the GPU arm's own batch: 16 cases x 2 stains x 2000 tokens per step
     sd = {k: v.clone().requires_grad_(True) for k, v in make_state_dict(0, n_mod=2).items()}
     feats = make_feats(1, cases, N_STAINS, N_TOKENS, D_IN)
     labels = torch.ones(cases, 1)
@@ -174,7 +174,7 @@ def run_reference(args, rank, world):
 
     for _ in range(max(1, min(args.warmup, 2))):
         step()
-    steps = max(1, min(args.steps, 5))
+    steps = max(1, min(args.steps, 5))                            # bounded: ~2 s per step on 16 host cores
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
@@ -185,7 +185,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "slides/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1] at fixed N=2000 (bounded CPU sample)", "bags_per_step": cases * N_STAINS,
+        "config": {"workload": "BASELINE configs[1] at the metric's fixed N=2000: 16 cases x 2 stains per step (the GPU arm's batch; bounded number of steps)",
+                   "bags_per_step": cases * N_STAINS, "bags_per_gpu": cases * N_STAINS,
                    "tokens_per_bag": N_TOKENS, "d_in": D_IN, "loss": "symmetric InfoNCE tau=0.001"},
         "cpu_baseline": {"value": value, "unit": "slides/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "slides/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -197,12 +198,12 @@ def cpu_baseline_quick():
     from weights import make_state_dict, make_feats
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cases = 2
+    cases = CASES_PER_GPU
     sd = {k: v.clone().requires_grad_(True) for k, v in make_state_dict(0, n_mod=2).items()}
     feats = make_feats(1, cases, N_STAINS, N_TOKENS, D_IN)
     labels = torch.ones(cases, 1)
     times = []
-    for it in range(4):
+    for it in range(3):
         for v in sd.values():
             v.grad = None
         t0 = time.perf_counter()
@@ -212,7 +213,60 @@ def cpu_baseline_quick():
         times.append(time.perf_counter() - t0)
     dt = statistics.median(times[1:])
     return {"value": cases * N_STAINS / dt, "unit": "slides/s", "cores": cores, "kind": "port",
-            "sample": f"{cases} cases x {N_STAINS} stains x {N_TOKENS} tokens, fwd+bwd, median of 3 after 1 warm-up (oracle port, torch CPU fp32)"}
+            "sample": f"{cases} cases x {N_STAINS} stains x {N_TOKENS} tokens (the bench batch), fwd+bwd, median of 2 after 1 warm-up (oracle port, torch CPU fp32)"}
+
+
+def canonical_block(precision, dev, steps):
+    """The reference's shipped pre-training configuration (scripts/launch_pretrain_withStainEncodings.sh; the one BASELINE.md's
+    only published number — 38.4 cases/s on 3 x 3090 Ti — is quoted on): batch 65 cases x 5 stains x 2048 tokens, stain
+    encodings, ACROBAT availability, InfoNCE (tau 0.001) + Graph-OT, fwd+bwd+AdamW, train mode; token window off and on."""
+    from madeleine.models.Model import MADELEINE
+    from madeleine.utils.loss import InfoNCE, GOT
+    from madeleine.utils.trainer import calculate_losses
+    from madeleine_b200.optim import FusedAdamW
+    from weights import make_state_dict
+    mods = ["HE", "HER2", "PGR", "KI67", "ER"]
+    bs, T = 65, 2048
+    gen = torch.Generator().manual_seed(0)
+    labels = (torch.rand(bs, 5, generator=gen) < torch.tensor([1.0, 0.46, 0.73, 0.73, 0.73])).float()
+    labels[:, 0] = 1
+    feats = torch.randn(bs, 5, T, D_IN, device=dev) * labels.to(dev)[:, :, None, None]
+    largs = Namespace(global_loss="info-nce", symmetric_cl=True, local_loss_weight=1.0)
+    loss_fn = InfoNCE(temperature=TAU)
+    res = {"workload": "65 cases x 5 stains x 2048 x 512, stain encodings, 28 % of the stain slots missing, InfoNCE + GOT, "
+                       "fwd+bwd+AdamW, train mode", "published_reference_cases_per_s_3x3090Ti": 38.4}
+    for window in ("off", "batch"):
+        cfg = Namespace(MODALITIES=mods, wsi_encoder="abmil", patch_embedding_dim=D_IN, wsi_encoder_hidden_dim=512, activation="softmax",
+                        n_heads=4, b200_precision=precision, b200_token_window=window)
+        model = MADELEINE(cfg, stain_encoding=True)
+        model.load_state_dict(make_state_dict(3, n_mod=5, stain_encoding=True))
+        model.to(dev).train()
+        opt = FusedAdamW(model.parameters(), lr=1e-4)
+
+        def step():
+            model.zero_grad(set_to_none=True)
+            embs, toks = model({"feats": feats, "modality_labels": labels}, device=dev, n_views=1)
+            loss, _ = calculate_losses(mods[1:], loss_fn, GOT, None, embs, toks, labels[:, 1:], largs)
+            loss.backward()
+            opt.step()
+            return loss
+
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        res[f"token_window_{window}"] = {"ms_per_step": ms, "cases_per_s": bs / (ms * 1e-3), "slides_per_s": float(labels.sum()) / (ms * 1e-3),
+                                         "loss": float(loss.detach())}
+        del model, opt
+        torch.cuda.empty_cache()
+    res["peak_mem_gb"] = torch.cuda.max_memory_allocated() / 1e9
+    return res
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -226,6 +280,7 @@ def main():
     ap.add_argument("--eval-mode", action="store_true", help="model.eval(): dropout off")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-canonical", action="store_true", help="skip the reference's canonical 65 x 5 x 2048 configuration block")
     ap.add_argument("--no-optimizer", action="store_true",
                     help="time forward + backward only; by default every timed step also runs the fused AdamW update, so the "
                          "kernel-layout copies of the weights are re-packed every step as in real training (nothing is cached "
@@ -287,26 +342,69 @@ def main():
         from madeleine_b200.optim import FusedAdamW
         optimizer = FusedAdamW(model.parameters(), lr=1e-4)       # reference: optim.AdamW(lr=args.lr), lr 1e-4 in the scripts
 
-    def step(feats):
+    def step(feats, ctx=None, update=True):
+        lab, lab_dev, lab_global = ctx or (labels, labels_dev, labels_global)
         model.zero_grad(set_to_none=True)
         embs, toks = model({"feats": feats}, device=dev, n_views=1)
-        lab = labels                      # availability mask stays on the host (as the reference's dataloader delivers it)
+        # the availability mask stays on the host (as the reference's dataloader delivers it)
         if world > 1:
-            embs, lab = parallel.gather_slide_embeddings(embs, labels_dev, global_labels_host=labels_global)
+            embs, lab = parallel.gather_slide_embeddings(embs, lab_dev, global_labels_host=lab_global)
         loss, ok = calculate_losses(MODS[1:], loss_fn, None, None, embs, toks, lab[:, 1:], largs)
         loss.backward()               # world > 1: the encoder backward all-reduces its flat gradient buffer (enable_gradient_sync)
-        if optimizer is not None:
+        if optimizer is not None and update:
             optimizer.step()
         return loss
 
-    def timed(n_steps, feats_fn, read_loss):
+    def sharded_parity():
+        """N > 1 only, once, before anything is timed: the sharded step (cases split over the ranks, ONE all-gather of the
+        slide embeddings, gradients summed by the encoder's all-reduce) against the same global batch evaluated by rank 0
+        alone — loss and parameter gradients.  Dropout off (model.eval()) so that both evaluations are deterministic."""
+        was_training = model.training
+        model.eval()
+        loss_sh = step(feats_dev, update=False).detach().clone()
+        named = [(n, p) for n, p in model.named_parameters() if p.grad is not None]
+        g_sh = torch.cat([p.grad.reshape(-1) for _, p in named]).clone()
+        feats_all = torch.empty((world * B,) + tuple(feats_dev.shape[1:]), device=dev)
+        dist.all_gather_into_tensor(feats_all, feats_dev)
+        out = None
+        if rank == 0:
+            parallel.enable_gradient_sync(False)
+            model.zero_grad(set_to_none=True)
+            embs, toks = model({"feats": feats_all}, device=dev, n_views=1)
+            loss_1, _ = calculate_losses(MODS[1:], loss_fn, None, None, embs, toks, labels_global[:, 1:], largs)
+            loss_1.backward()
+            g_1 = torch.cat([p.grad.reshape(-1) for _, p in named])
+            worst, worst_name, o = 0.0, "", 0
+            total = float(g_1.double().norm())
+            for n, p in named:
+                k = p.numel()
+                ref = g_1[o:o + k].double()
+                err = float((g_sh[o:o + k].double() - ref).norm()) / max(float(ref.norm()), 1e-6 * total)
+                if err > worst:
+                    worst, worst_name = err, n
+                o += k
+            out = {"what": f"sharded step on {world} ranks vs the same global batch ({world * B} cases) on rank 0 alone, eval mode",
+                   "loss_sharded": float(loss_sh), "loss_single": float(loss_1),
+                   "loss_rel": abs(float(loss_sh) - float(loss_1)) / max(abs(float(loss_1)), 1e-12),
+                   "grad_rel": float((g_sh.double() - g_1.double()).norm()) / total,
+                   "grad_rel_worst_param": worst, "worst_param": worst_name}
+            parallel.enable_gradient_sync(True)
+            model.zero_grad(set_to_none=True)
+        del feats_all
+        dist.barrier()
+        model.train(was_training)
+        return out
+
+    parity = sharded_parity() if world > 1 else None
+
+    def timed(n_steps, feats_fn, read_loss, ctx=None):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(n_steps):
-            loss = step(feats_fn(i))
+            loss = step(feats_fn(i), ctx)
             if read_loss:
                 loss.item()
         e1.record()
@@ -336,6 +434,19 @@ def main():
     bags_per_step = B * N_STAINS * world
     value = bags_per_step / (ms_step * 1e-3)
 
+    # ---- BASELINE configs[3]: batch = 64 cases sharded over 8 ranks = 8 cases per rank (timed for any N > 1) ----
+    config3 = None
+    if world > 1:
+        b3 = 8
+        ctx3 = (torch.ones(b3, N_STAINS), torch.ones(b3, N_STAINS, device=dev), torch.ones(b3 * world, N_STAINS))
+        feats3 = feats_dev[:b3].contiguous()
+        for _ in range(3):
+            step(feats3, ctx3)
+        ms3 = timed(args.steps, lambda i: feats3, read_loss=False, ctx=ctx3)
+        config3 = {"workload": f"BASELINE configs[3]: {b3} cases x {N_STAINS} stains x {N_TOKENS} per rank, global batch {b3 * world} cases "
+                               "sharded, one all-gather of slide embeddings before InfoNCE", "cases_per_gpu": b3, "global_batch_cases": b3 * world,
+                   "ms_per_step": ms3, "slides_per_s": b3 * N_STAINS * world / (ms3 * 1e-3)}
+
     # ---- end to end: every step's features come from pinned HOST memory (H2D inside the timed region, staged one batch
     # ahead on a copy stream by DevicePrefetcher) and every step's loss is read back to the host (async D2H into a pinned
     # buffer, consumed one step later so the host keeps one step of launches queued) ----
@@ -345,7 +456,7 @@ def main():
 
         def run_e2e(n_steps):
             batches = ({"feats": feats_host[i % 2]} for i in range(n_steps))
-            LAG = 4                                    # the host reads the loss of step i-4 while step i is being queued
+            LAG = 2                                    # the host reads the loss of step i-2 while step i is being queued (tools/e2e_probe.py)
             host_loss = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(LAG + 1)]
             events = [torch.cuda.Event() for _ in range(LAG + 1)]
             seen = []
@@ -391,7 +502,7 @@ def main():
                "h2d_bytes_per_step": feats_host[0].numel() * 4, "d2h_bytes_per_step": 4,
                "h2d_gbs_alone": h2d_gbs, "runs_ms_per_step": e2e_runs,
                "note": "pinned host features staged one batch ahead on a copy stream; every step's loss is read back inside the "
-                       "timed region, four steps deferred so the host stays ahead of the device (tools/e2e_probe.py); "
+                       "timed region, two steps deferred so the host stays ahead of the device (tools/e2e_probe.py); "
                        "h2d_gbs_alone = this box's pinned H2D rate for one batch with the GPU otherwise idle"}
 
     if rank != 0:
@@ -446,6 +557,22 @@ def main():
         "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "roofline_gemm": roofline_gemm,
         "kernel_ms_per_step": {k: sum(v) / args.steps for k, v in kt.items()}, "pool_bwd_avg_launch_ms": pool_bwd_ms,
     }
+    # whole step against the tensor roofline: algorithmic (1x, fp32-equivalent) FLOPs of everything a step computes per
+    # second of step time, over the measured sustained bf16 rate (46.2 GFLOP/bag fwd+bwd with the token
+    # projector's backward; this step has no local loss, so 44.0 GFLOP/bag)
+    step_tf = (flops_fwd + flops_bwd) * world / (ms_step * 1e-3) / 1e12
+    out["roofline_step"] = {"bound": "tensor", "achieved": step_tf / world, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                            "frac": step_tf / world / peaks["bf16_tflops_sustained"], "per_gpu": True,
+                            "algorithmic_gflop_per_bag": (flops_fwd + flops_bwd) / bags_local / 1e9,
+                            "frac_bf16_issue": step_tf * issued / world / peaks["bf16_tflops_sustained"],
+                            "note": "algorithmic FLOPs x bags/s over the sustained bf16 rate; x3 issued in the fp32-grade mode"}
+    out["parity"] = parity
+    if config3 is not None:
+        out["config3"] = config3
+    if world == 1 and not args.no_canonical:
+        del feats_dev, feats_host
+        torch.cuda.empty_cache()
+        out["canonical"] = canonical_block(args.precision, dev, 5)
     if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_baseline_quick()
     print(json.dumps(out))

@@ -240,6 +240,9 @@ int mdl_encoder_fwd(const long long* ip, const double* fp, void* const* pp);
 int mdl_encoder_bwd(const long long* ip, const double* fp, void* const* pp);
 /* out[dst[i]] = src[pos[i]] — packed gradient buffer -> parameter layout in one pass. */
 int mdl_permute_f32(const float* src, const int* pos, const int* dst, long long n, float* out, void* stream);
+/* G [D, D] fp64 = E^T E for E fp32 [n, D]: the Gram matrix whose eigenvalues are the squared singular values that
+ * smooth_rank_measure needs (madeleine/utils/utils.py:180-201: torch.svd of the [n, 512] H&E embedding matrix on the CPU). */
+int mdl_gram_f64(const float* E, long long n, int D, double* G, void* stream);
 /* Number of C-ABI kernel entry points mdl_encoder_fwd / mdl_encoder_bwd called (all threads) since the last reset. */
 long long mdl_executor_launches(int reset);
 

@@ -43,6 +43,33 @@ __global__ void add_transposed_kernel(float* __restrict__ dst, const float* __re
     }
 }
 
+// G[i, j] = sum_n E[n, i] * E[n, j] accumulated in fp64 (E fp32 [n, D]); one 32 x 32 tile of G per block, upper triangle
+// only (mirrored on the way out).  The singular values the rank metric needs (smooth_rank_measure, utils.py:180-201) are
+// the square roots of this matrix's eigenvalues, so the [n, 512] embedding matrix never leaves the device.
+__global__ void __launch_bounds__(1024)
+gram_f64_kernel(const float* __restrict__ E, long long n, int D, double* __restrict__ G) {
+    const int ti = blockIdx.y, tj = blockIdx.x;
+    if (tj < ti) return;
+    __shared__ float a[32][33], b[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    double acc = 0.0;
+    for (long long r0 = 0; r0 < n; r0 += 32) {
+        const long long r = r0 + ty;
+        const int ci = ti * 32 + tx, cj = tj * 32 + tx;
+        a[ty][tx] = (r < n && ci < D) ? __ldg(E + r * D + ci) : 0.f;
+        b[ty][tx] = (r < n && cj < D) ? __ldg(E + r * D + cj) : 0.f;
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) acc = fma((double)a[k][ty], (double)b[k][tx], acc);
+        __syncthreads();
+    }
+    const int i = ti * 32 + ty, j = tj * 32 + tx;
+    if (i < D && j < D) {
+        G[(long long)i * D + j] = acc;
+        G[(long long)j * D + i] = acc;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // process-wide launch profiler (bench.py's live roofline); forward runs on the caller's thread, backward on autograd's
 // ------------------------------------------------------------------------------------------------------------------
@@ -485,6 +512,14 @@ int mdl_encoder_bwd(const long long* ip, const double* fp, void* const* pp) {
 int mdl_permute_f32(const float* src, const int* pos, const int* dst, long long n, float* out, void* stream) {
     if (n <= 0) return 0;
     permute_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, pos, dst, n, out);
+    MDL_CHECK_LAUNCH();
+    return 0;
+}
+
+int mdl_gram_f64(const float* E, long long n, int D, double* G, void* stream) {
+    MDL_REQUIRE(E && G && n > 0 && D > 0, "gram: empty input");
+    dim3 grid((D + 31) / 32, (D + 31) / 32);
+    gram_f64_kernel<<<grid, 1024, 0, (cudaStream_t)stream>>>(E, n, D, G);
     MDL_CHECK_LAUNCH();
     return 0;
 }

@@ -166,5 +166,5 @@ def train_loop(args, loss_fn_interMod, loss_fn_interMod_local, loss_fn_intraMod,
             print(f"Loss for batch: {step} = {loss:.3f}")
         running += loss.detach()
         busy += time.time() - t0
-    rank = smooth_rank_measure(torch.cat(he_embeddings, dim=0).cpu())
+    rank = smooth_rank_measure(torch.cat(he_embeddings, dim=0))          # on the device: Gram matrix + eigenvalues, one scalar back
     return float(running), rank

@@ -18,11 +18,26 @@ def set_model_precision(precision):
 
 
 def smooth_rank_measure(embedding_matrix, eps=1e-7):
-    """exp(entropy of the normalised singular values) — the model-selection metric (utils.py:180-201)."""
-    _, s, _ = torch.svd(embedding_matrix.float())
+    """exp(entropy of the normalised singular values), rounded to two decimals — the model-selection metric
+    (utils.py:180-201).
+
+    A CUDA matrix stays on the device: its singular values are the square roots of the eigenvalues of the [D, D] Gram
+    matrix, accumulated in fp64 by ``mdl_gram_f64`` (one kernel over the [n, D] embeddings) and diagonalised in fp64; a
+    single scalar comes back.  fp64 keeps singular values down to 1e-8 of the largest, far below what moves the entropy.
+    CPU input takes the reference's ``torch.svd`` route."""
+    if embedding_matrix.is_cuda:
+        from .._lib import call, stream_ptr
+        e = embedding_matrix.detach().float().contiguous()
+        n, d = e.shape
+        gram = torch.empty(d, d, dtype=torch.float64, device=e.device)
+        with torch.cuda.device(e.device):
+            call("mdl_gram_f64", e, n, d, gram, stream_ptr(e.device))
+        s = torch.linalg.eigvalsh(gram).clamp_min(0).sqrt().flip(0)[: min(n, d)].float()
+    else:
+        _, s, _ = torch.svd(embedding_matrix.float())
     p = s / torch.sum(s, dim=0) + eps
-    p = p[: min(embedding_matrix.shape)]
-    return float(torch.exp(-torch.sum(p * torch.log(p))))
+    p = p[: embedding_matrix.shape[1]]
+    return round(float(torch.exp(-torch.sum(p * torch.log(p)))), 2)
 
 
 def run_inference(ssl_model, val_dataloader, config=None, torch_precision=None):

@@ -20,7 +20,7 @@ def test_reference_arm_json_line():
     assert d["impl"] == "reference" and d["metric"].startswith("slides/sec") and d["unit"] == "slides/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == os.cpu_count() and cb["value"] == d["value"] and "2 cases x 2 stains" in cb["sample"]
+    assert cb["kind"] == "port" and cb["cores"] == os.cpu_count() and cb["value"] == d["value"] and "16 cases x 2 stains" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "slides/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
 

@@ -158,3 +158,20 @@ def test_resident_loader_feeds_a_training_step(tmp_path):
     assert flag
     loss.backward()
     assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+
+
+def test_load_features_reads_the_reference_hdf5_layout(tmp_path):
+    """The reference stores patch embeddings as an HDF5 dataset ``features`` [1, N, D] or [N, D] fp32
+    (madeleine/preprocessing/conch_patch_embedder.py:127-131, read by wsi_dataset.py:14-19).  Needs h5py, which this image
+    does not ship: skipped there, exercised wherever the reference's own loader can run."""
+    h5py = pytest.importorskip("h5py")
+    import numpy as np
+    from madeleine_b200.datasets.wsi_dataset import load_features
+    arr = np.random.default_rng(0).standard_normal((1, 37, 512)).astype(np.float32)
+    path = tmp_path / "slide.h5"
+    with h5py.File(path, "w") as f:
+        f.create_dataset("features", data=arr)
+        f.create_dataset("coords", data=np.zeros((37, 2), dtype=np.int64))
+    out = load_features(str(path))
+    assert out.dtype == torch.float32 and tuple(out.shape) == (37, 512)
+    assert torch.equal(out, torch.from_numpy(arr[0]))

@@ -1,4 +1,5 @@
 """CPU tests of host-side logic that needs no GPU."""
+import pytest
 import torch
 
 from madeleine_b200.utils.inference import plan_batches
@@ -22,6 +23,30 @@ def test_precision_resolution(monkeypatch):
     monkeypatch.setenv("MADELEINE_B200_PRECISION", "bf16")
     assert ops.resolve_precision(None) == "bf16"
     assert set_model_precision("bfloat16") is torch.bfloat16
+
+
+# values printed by the reference's own smooth_rank_measure (madeleine/utils/utils.py:180-201, executed from /root/reference
+# in the build container) on make_feats(1, n, d) * linspace(0.1, 2.0, d)
+SMOOTH_RANK_REFERENCE = {(300, 512): 255.13, (40, 512): 39.35, (700, 64): 54.15}
+
+
+def _rank_input(n, d):
+    from weights import make_feats
+    return make_feats(1, n, d) * torch.linspace(0.1, 2.0, d)
+
+
+def test_smooth_rank_measure_matches_reference_values():
+    for (n, d), want in SMOOTH_RANK_REFERENCE.items():
+        assert smooth_rank_measure(_rank_input(n, d)) == pytest.approx(want, abs=0.011)
+
+
+@pytest.mark.gpu
+def test_smooth_rank_measure_on_device_matches_reference_values():
+    """CUDA input: Gram matrix in fp64 on the device (mdl_gram_f64) + eigenvalues instead of a CPU SVD; same numbers."""
+    for (n, d), want in SMOOTH_RANK_REFERENCE.items():
+        x = _rank_input(n, d).cuda()
+        assert smooth_rank_measure(x) == pytest.approx(want, abs=0.011)
+        assert smooth_rank_measure(x) == pytest.approx(smooth_rank_measure(x.cpu()), abs=0.011)
 
 
 def test_smooth_rank_measure():

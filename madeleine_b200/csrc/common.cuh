@@ -199,6 +199,23 @@ __device__ __forceinline__ void dropout_scale4(const DropCfg& c, uint64_t seed, 
     m[2] = (hi << 16) >= c.thresh_hi ? c.keep : 0.f;
     m[3] = hi >= c.thresh_hi ? c.keep : 0.f;
 }
+// Two mask vectors (elements 4*idx4 .. +3 of stream `stream` and of stream `stream + 1`) from ONE hash, 8-bit fields: exact
+// whenever p * 256 is an integer (the gates' nn.Dropout(0.25), abmil.py:33-35).  Used where only one kernel ever needs
+// the masks (the gated-attention epilogue; its backward reads them off the stored gates).
+__device__ __forceinline__ bool drop_p_is_8bit(float p) { const float t = p * 256.f; return t == floorf(t); }
+__device__ __forceinline__ void dropout_scale4x2_8bit(uint32_t thresh24, float keep, uint64_t seed, uint32_t stream, uint64_t idx4,
+                                                      float (&ma)[4], float (&mb)[4]) {
+    const uint64_t h = hash_u64(seed, stream, idx4);
+    const uint32_t lo = (uint32_t)h, hi = (uint32_t)(h >> 32);
+    ma[0] = (lo << 24) >= thresh24 ? keep : 0.f;
+    ma[1] = (lo << 16) >= thresh24 ? keep : 0.f;
+    ma[2] = (lo << 8) >= thresh24 ? keep : 0.f;
+    ma[3] = lo >= thresh24 ? keep : 0.f;
+    mb[0] = (hi << 24) >= thresh24 ? keep : 0.f;
+    mb[1] = (hi << 16) >= thresh24 ? keep : 0.f;
+    mb[2] = (hi << 8) >= thresh24 ? keep : 0.f;
+    mb[3] = hi >= thresh24 ? keep : 0.f;
+}
 __device__ __forceinline__ void dropout_scale4(float p, uint64_t seed, uint32_t stream, uint64_t idx4, float (&m)[4]) {
     dropout_scale4(make_drop_cfg(p), seed, stream, idx4, m);
 }
@@ -289,6 +306,16 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
           "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+// TMEM -> registers: 32 lanes x 16 consecutive fp32 columns (half of the above; lets an epilogue software-pipeline its loads).
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
 }

@@ -7,6 +7,13 @@
 
 namespace mdl {
 
+// streaming 16-byte load that does not allocate in L1 (data touched once)
+__device__ __forceinline__ uint4 ld_nc_na(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
 static inline int grid_for(long long work_items, int per_block, int max_blocks_per_sm = 8) {
     long long b = (work_items + per_block - 1) / per_block;
     long long cap = (long long)kNumSMs * max_blocks_per_sm;
@@ -389,32 +396,42 @@ ln_gelu_bwd_kernel(const void* __restrict__ z, int M, const float* __restrict__ 
 // Gated-attention backward (elementwise part).  gate_a/gate_b hold the (dropout-scaled) tanh / sigmoid outputs
 // as fp16 [M, H*512].  Produces d(pre-activation) as bf16 planes in the packed column order of the gated GEMM
 // (per head: 4 groups of [128 a-cols | 128 b-cols]) and the column sums d(ba), d(bb), d(wc), d(bc).
-// Thread t owns gate columns [8t, 8t+8) for the whole kernel; a block sweeps rows two at a time.
+// Thread t owns gate columns [8t, 8t+8) for the whole kernel; a block sweeps rows R at a time.
+//
+// The dropout masks are NOT regenerated: a dropped gate was stored as an exact zero, and every product below that must
+// vanish for a dropped gate does so by itself except the tanh branch's own derivative, which one select on `a == 0`
+// handles.  (A KEPT tanh output that underflows fp16 — |tanh| < 3e-8, < 1e-7 of the elements — is thereby treated as
+// dropped; the gates themselves carry 2^-11 per element, so this is far inside the precision of what was saved.)
+//   dpre_a = dl wc (b mb) ma (1 - a^2),  dpre_b = dl wc (a ma) mb b (1 - b),  ma, mb in {0, 1/(1-p)}
 // ---------------------------------------------------------------------------------------------------
+#ifndef GATE_BWD_ROWS
+#define GATE_BWD_ROWS 4
+#endif
+template <int R>
 __global__ void __launch_bounds__(256, 3)
 gate_bwd_kernel(const __half* __restrict__ gate_a, const __half* __restrict__ gate_b, const float* __restrict__ dlogit,
-                const float* __restrict__ wc, long long M, int n_heads, float drop_p, unsigned long long seed,
+                const float* __restrict__ wc, long long M, int n_heads, float drop_p,
                 __nv_bfloat16* __restrict__ dpre, long long plane_stride, int nplanes,
                 float* __restrict__ dba, float* __restrict__ dbb, float* __restrict__ dwc, float* __restrict__ dbc) {
     const int HC = n_heads * 512;            // gate columns per row
     const int j0 = threadIdx.x * 8;          // requires HC == blockDim.x * 8  (n_heads = 4 -> 256 threads)
     const int head = j0 / 512, jh = j0 % 512;
     const int packed0 = head * 1024 + (jh / 128) * 256 + (jh % 128);  // a-part; b-part is +128
-    float w[8], s_a[8], s_b[8], s_w[8];
+    const bool drop = drop_p > 0.f;
+    const float keep_inv = drop ? (1.f - drop_p) : 1.f;               // undoes the 1/(1-p) scaling of a stored gate
+    const float keep = drop ? __fdividef(1.f, 1.f - drop_p) : 1.f;
+    float kw[8], s_a[8], s_b[8], s_w[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { w[i] = __ldg(wc + j0 + i); s_a[i] = 0.f; s_b[i] = 0.f; s_w[i] = 0.f; }
+    for (int i = 0; i < 8; ++i) { kw[i] = __ldg(wc + j0 + i) * keep; s_a[i] = 0.f; s_b[i] = 0.f; s_w[i] = 0.f; }
     float s_c = 0.f;
-    const float keep_inv = drop_p > 0.f ? (1.f - drop_p) : 1.f;
-    const DropCfg dcfg = make_drop_cfg(drop_p);
-    constexpr int R = 2;
     for (long long m0 = (long long)blockIdx.x * R; m0 < M; m0 += (long long)gridDim.x * R) {
         uint4 ua[R], ub[R];
         float dl[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const long long m = m0 + r < M ? m0 + r : m0;
-            ua[r] = __ldg(reinterpret_cast<const uint4*>(gate_a + m * HC + j0));
-            ub[r] = __ldg(reinterpret_cast<const uint4*>(gate_b + m * HC + j0));
+            ua[r] = ld_nc_na(reinterpret_cast<const uint4*>(gate_a + m * HC + j0));
+            ub[r] = ld_nc_na(reinterpret_cast<const uint4*>(gate_b + m * HC + j0));
             dl[r] = m0 + r < M ? __ldg(dlogit + m * n_heads + head) : 0.f;
         }
 #pragma unroll
@@ -423,15 +440,6 @@ gate_bwd_kernel(const __half* __restrict__ gate_a, const __half* __restrict__ ga
             const long long m = m0 + r;
             const __half2* ha = reinterpret_cast<const __half2*>(&ua[r]);
             const __half2* hb = reinterpret_cast<const __half2*>(&ub[r]);
-            float sa[8], sb[8];
-            {
-                float t[4];
-                const uint64_t idx4 = ((uint64_t)m * (uint64_t)HC + (uint64_t)j0) >> 2;
-                dropout_scale4(dcfg, seed, 10u, idx4, t); sa[0] = t[0]; sa[1] = t[1]; sa[2] = t[2]; sa[3] = t[3];
-                dropout_scale4(dcfg, seed, 10u, idx4 + 1, t); sa[4] = t[0]; sa[5] = t[1]; sa[6] = t[2]; sa[7] = t[3];
-                dropout_scale4(dcfg, seed, 11u, idx4, t); sb[0] = t[0]; sb[1] = t[1]; sb[2] = t[2]; sb[3] = t[3];
-                dropout_scale4(dcfg, seed, 11u, idx4 + 1, t); sb[4] = t[0]; sb[5] = t[1]; sb[6] = t[2]; sb[7] = t[3];
-            }
             float dpa[8], dpb[8];
 #pragma unroll
             for (int i2 = 0; i2 < 4; ++i2) {
@@ -442,11 +450,11 @@ gate_bwd_kernel(const __half* __restrict__ gate_a, const __half* __restrict__ ga
                 for (int k = 0; k < 2; ++k) {
                     const int i = 2 * i2 + k;
                     const float ad = adv[k], bd = bdv[k];               // dropout-scaled gates (0 where dropped)
-                    const float a = ad * keep_inv;                      // undo the 1/(1-p) scaling; dropped gates stay 0 and
-                    const float b = bd * keep_inv;                      // their gradients are zeroed by sa / sb below
-                    const float dA = dl[r] * w[i];
-                    dpa[i] = dA * bd * sa[i] * (1.f - a * a);
-                    dpb[i] = dA * ad * sb[i] * b * (1.f - b);
+                    const float a = ad * keep_inv, b = bd * keep_inv;
+                    const float t = dl[r] * kw[i];                      // dl wc / (1-p): the surviving mask factor of either branch
+                    const float da = (t * bd) * fmaf(-a, a, 1.f);
+                    dpa[i] = (drop && ad == 0.f) ? 0.f : da;
+                    dpb[i] = (t * ad) * fmaf(-b, b, b);
                     s_a[i] += dpa[i]; s_b[i] += dpb[i]; s_w[i] = fmaf(dl[r], ad * bd, s_w[i]);
                 }
             }
@@ -685,9 +693,10 @@ int mdl_gate_bwd(const void* gate_a, const void* gate_b, const float* dlogit, co
                  float* dba, float* dbb, float* dwc, float* dbc, void* stream) {
     MDL_REQUIRE(n_heads == 4, "gate_bwd: only n_heads == 4 is built (got %d)", n_heads);
     if (M == 0) return 0;
+    (void)seed;      // the masks are read off the stored gates (a dropped gate is an exact zero), not regenerated
     const int grid = grid_for(M, 32, 3);
-    gate_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)gate_a, (const __half*)gate_b, dlogit, wc, M, n_heads, drop_p, seed,
-                                                           (__nv_bfloat16*)dpre_planes, plane_stride, nplanes, dba, dbb, dwc, dbc);
+    gate_bwd_kernel<GATE_BWD_ROWS><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)gate_a, (const __half*)gate_b, dlogit, wc, M, n_heads, drop_p,
+                                                                          (__nv_bfloat16*)dpre_planes, plane_stride, nplanes, dba, dbb, dwc, dbc);
     MDL_CHECK_LAUNCH();
     return 0;
 }

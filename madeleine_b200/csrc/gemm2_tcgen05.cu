@@ -98,7 +98,7 @@ gemm2_kf_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     if constexpr (EPI == EPI_GATED) {
         const int hc = p.n_heads * 512;
         for (int i = threadIdx.x; i < hc; i += GEMM_THREADS) {
-            aux[i] = __ldg(p.ba + i); aux[2048 + i] = __ldg(p.bb + i); aux[4096 + i] = __ldg(p.wc + i);
+            aux[i] = -2.885390081777927f * __ldg(p.ba + i); aux[2048 + i] = -1.4426950408889634f * __ldg(p.bb + i); aux[4096 + i] = __ldg(p.wc + i);   // pre-scaled: see EPI_GATED
         }
     }
     tc_fence_before();

@@ -122,21 +122,34 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, float* aux, uin
             __syncwarp();
         }
     } else {  // EPI_GATED
+        // aux holds ba' = -2 log2(e) ba, bb' = -log2(e) bb (pre-scaled by the caller) and wc: tanh(x + ba) = 2 / (1 + 2^(c2 x + ba')) - 1
+        // and sigmoid(y + bb) = 1 / (1 + 2^(c1 y + bb')) each start with ONE fma.  The 64 accumulator columns a warp owns per
+        // gate branch are drained in four 16-column pieces, the load of piece k + 1 in flight while piece k is evaluated
+        // (tcgen05.wait::ld waits for everything issued before it, so: wait, issue the next load, then compute).
         const int head = n_group;          // one work unit = (m_tile, head); inner = 128-wide gate group
-        const int j_base = head * 512 + inner * 128;
+        const int j_base = head * 512 + inner * 128 + half * 64;
         const int HC = p.n_heads * 512;
         const DropCfg dcfg = make_drop_cfg(p.drop_p);
-#pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-            const int c = half * 2 + cc;
-            uint32_t ra[32], rb[32];
-            tmem_ld_32x32(t_row + c * 32, ra);
-            tmem_ld_32x32(t_row + 128 + c * 32, rb);
-            tmem_ld_wait();
-            const int j0 = j_base + c * 32;
-            uint32_t ha[16], hb[16];
+        const bool drop8 = dcfg.on && drop_p_is_8bit(p.drop_p);
+        const uint32_t thresh24 = ((uint32_t)(p.drop_p * 256.f)) << 24;
+        constexpr float C2 = -2.885390081777927f, C1 = -1.4426950408889634f;
+        uint32_t ra[2][16], rb[2][16];
+        const uint32_t t_a = t_row + half * 64, t_b = t_row + 128 + half * 64;
+        tmem_ld_32x16(t_a, ra[0]);
+        tmem_ld_32x16(t_b, rb[0]);
 #pragma unroll
-            for (int i4 = 0; i4 < 8; ++i4) {
+        for (int k = 0; k < 4; ++k) {
+            tmem_ld_wait();
+            if (k < 3) {
+                tmem_ld_32x16(t_a + (k + 1) * 16, ra[(k + 1) & 1]);
+                tmem_ld_32x16(t_b + (k + 1) * 16, rb[(k + 1) & 1]);
+            }
+            const uint32_t (&xa)[16] = ra[k & 1];
+            const uint32_t (&xb)[16] = rb[k & 1];
+            const int j0 = j_base + k * 16;
+            uint32_t ha[8], hb[8];
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
                 const float4 vba = *reinterpret_cast<const float4*>(aux + j0 + 4 * i4);
                 const float4 vbb = *reinterpret_cast<const float4*>(aux + 2048 + j0 + 4 * i4);
                 const float4 vwc = *reinterpret_cast<const float4*>(aux + 4096 + j0 + 4 * i4);
@@ -144,13 +157,19 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, float* aux, uin
                 const float fwc[4] = {vwc.x, vwc.y, vwc.z, vwc.w};
                 float ma[4], mb[4];
                 const uint64_t idx4 = ((uint64_t)m * (uint64_t)HC + (uint64_t)(j0 + 4 * i4)) >> 2;
-                dropout_scale4(dcfg, p.seed, 10u, idx4, ma);
-                dropout_scale4(dcfg, p.seed, 11u, idx4, mb);
+                if (drop8) {
+                    dropout_scale4x2_8bit(thresh24, dcfg.keep, p.seed, 12u, idx4, ma, mb);
+                } else {
+                    dropout_scale4(dcfg, p.seed, 10u, idx4, ma);
+                    dropout_scale4(dcfg, p.seed, 11u, idx4, mb);
+                }
                 float av[4], bv[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    av[i] = tanh_acc(__uint_as_float(ra[4 * i4 + i]) + fba[i]) * ma[i];
-                    bv[i] = sigmoid_acc(__uint_as_float(rb[4 * i4 + i]) + fbb[i]) * mb[i];
+                    const float ea = ex2_approx(fmaf(__uint_as_float(xa[4 * i4 + i]), C2, fba[i]));
+                    const float eb = ex2_approx(fmaf(__uint_as_float(xb[4 * i4 + i]), C1, fbb[i]));
+                    av[i] = fmaf(2.f, rcp_approx(1.f + ea), -1.f) * ma[i];
+                    bv[i] = rcp_approx(1.f + eb) * mb[i];
                     gated_partial = fmaf(av[i] * bv[i], fwc[i], gated_partial);
                 }
                 if (p.gate_a != nullptr) {
@@ -163,11 +182,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, float* aux, uin
             if (p.gate_a != nullptr && row_ok) {
                 uint4* da = reinterpret_cast<uint4*>(p.gate_a + (size_t)m * HC + j0);
                 uint4* db = reinterpret_cast<uint4*>(p.gate_b + (size_t)m * HC + j0);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    da[i] = make_uint4(ha[4 * i], ha[4 * i + 1], ha[4 * i + 2], ha[4 * i + 3]);
-                    db[i] = make_uint4(hb[4 * i], hb[4 * i + 1], hb[4 * i + 2], hb[4 * i + 3]);
-                }
+                da[0] = make_uint4(ha[0], ha[1], ha[2], ha[3]); da[1] = make_uint4(ha[4], ha[5], ha[6], ha[7]);
+                db[0] = make_uint4(hb[0], hb[1], hb[2], hb[3]); db[1] = make_uint4(hb[4], hb[5], hb[6], hb[7]);
             }
         }
         if (inner == p.n_inner - 1) {

@@ -31,6 +31,17 @@ ACT_CODES = {"softmax": 0, "leaky_relu": 1, "relu": 2, "sigmoid": 3}
 
 _step_counter = [0]
 
+# Optional phase timeline (bench.py --timeline): when this is a list, the encoder's backward appends (label, cuda event)
+# pairs at its phase boundaries so that the multi-GPU cost of the two gradient all-reduces can be read off the device clock.
+timeline = None
+
+
+def _mark(label):
+    if timeline is not None:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        timeline.append((label, ev))
+
 
 def resolve_precision(requested: Optional[str]) -> str:
     """'fp32' (3-pass split-bf16 tcgen05, fp32-grade, forward and backward), 'bf16' (1 pass) or 'fp32_fwd' (fp32-grade
@@ -497,13 +508,17 @@ class EncodeFn(torch.autograd.Function):
             def early(gm, lo, hi):
                 pending.append(dist.all_reduce(gm[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
 
+            _mark("bwd_begin")
             gmaster = encoder_backward(sv, d_slide, d_logits, d_tokens, d_ref, early_sync=early)
+            _mark("bwd_kernels_done")
             if spec.early_lo > 0:
                 dist.all_reduce(gmaster[:spec.early_lo], op=dist.ReduceOp.SUM)
             if spec.early_hi < spec.master_numel:
                 dist.all_reduce(gmaster[spec.early_hi:], op=dist.ReduceOp.SUM)
+            _mark("late_allreduce_done")
             for work in pending:
                 work.wait()
+            _mark("early_allreduce_joined")
         else:
             gmaster = encoder_backward(sv, d_slide, d_logits, d_tokens, d_ref)
         # parameters that no incoming gradient can reach keep grad = None, as in the reference (AdamW then skips them: no

@@ -159,3 +159,64 @@ def test_gemm_gated(M, nsplit):
     call("mdl_gemm_gated", xp, M, H * 512, H * 512, M * H * 512, wp, wp.shape[1] * wp.shape[2], M, H, nsplit, ba, bb, wc, bc,
          logits2, None, None, 0.0, 0, _st())
     assert torch.equal(logits, logits2)
+
+
+@pytest.mark.parametrize("p", [0.25, 0.1])
+def test_gemm_gated_dropout_forward_and_gate_bwd_consistency(p):
+    """Train mode (nn.Dropout on both gates, abmil.py:33-35): the saved gates are the dropout-scaled activations with exact
+    zeros where dropped (keep rate ~ 1 - p, masks of the two branches independent, reproducible per seed, different per
+    seed), the logits are those gates' weighted sum, and mdl_gate_bwd — which reads the masks off the saved gates instead
+    of regenerating them — returns the gradient of exactly that masked function.  p = 0.25 takes the 8-bit-field mask path
+    (p * 256 integral), p = 0.1 the 16-bit one."""
+    M, H, nsplit, npl = 640, 4, 3, 2
+    g = torch.Generator().manual_seed(17)
+    X = torch.randn(M, H * 512, generator=g).to(DEV)
+    packed = (torch.randn(H * 1024, 512, generator=g) / 22.6).to(DEV)
+    ba, bb, wc = (torch.randn(H * 512, generator=g).to(DEV) * 0.1 for _ in range(3))
+    bc = torch.randn(H, generator=g).to(DEV)
+    xp, wp = ops.split_planes(X, npl), ops.split_planes(packed, npl)
+
+    def run(seed, drop):
+        logits = torch.empty(M, H, device=DEV)
+        ga = torch.empty(M, H * 512, dtype=torch.float16, device=DEV)
+        gb = torch.empty_like(ga)
+        call("mdl_gemm_gated", xp, M, H * 512, H * 512, M * H * 512, wp, wp.shape[1] * wp.shape[2], M, H, nsplit, ba, bb, wc, bc,
+             logits, ga, gb, drop, seed, _st())
+        return logits, ga, gb
+
+    l0, a0, b0 = run(5, 0.0)
+    l1, a1, b1 = run(5, p)
+    l1b, a1b, b1b = run(5, p)
+    l2, a2, b2 = run(6, p)
+    assert torch.equal(l1, l1b) and torch.equal(a1, a1b) and torch.equal(b1, b1b)          # same seed, same masks
+    keep = 1.0 / (1.0 - p)
+    for kept_vals, full in ((a1, a0), (b1, b0)):
+        kept = kept_vals != 0
+        frac = float(kept.float().mean())
+        assert abs(frac - (1 - p)) < 5e-3, frac
+        # kept entries are the undropped activations times 1 / (1 - p)
+        torch.testing.assert_close(kept_vals[kept].float(), full[kept].float() * keep, rtol=2e-3, atol=1e-3)
+    ka, kb = (a1 != 0), (b1 != 0)
+    joint = float((ka & kb).float().mean())
+    assert abs(joint - (1 - p) ** 2) < 5e-3, joint                                             # the two branches' masks are independent
+    assert float(((a2 != 0) == ka).float().mean()) < 0.9                                        # another seed, other masks
+    ref_logits = (a1.double() * b1.double() * wc.double()).view(M, H, 512).sum(-1) + bc.double()
+    torch.testing.assert_close(l1.double(), ref_logits, rtol=1e-3, atol=2e-3)                   # fp16 rounding of the saved gates only
+
+    # backward of the masked function, masks taken from the saved gates
+    dlogit = torch.randn(M, H, generator=g).to(DEV)
+    dpre = torch.empty(2, M, H * 1024, dtype=torch.bfloat16, device=DEV)
+    dba, dbb, dwc = (torch.zeros(H * 512, device=DEV) for _ in range(3))
+    dbc = torch.zeros(H, device=DEV)
+    call("mdl_gate_bwd", a1, b1, dlogit, wc, M, H, p, 5, dpre, M * H * 1024, 2, dba, dbb, dwc, dbc, _st())
+    d = (dpre[0].float() + dpre[1].float()).view(M, H, 4, 2, 128)
+    d_a, d_b = d[:, :, :, 0].reshape(M, H * 512), d[:, :, :, 1].reshape(M, H * 512)
+    a = a1.float() / keep                       # tanh / sigmoid values where kept, 0 where dropped
+    b = b1.float() / keep
+    dl = dlogit.repeat_interleave(512, 1)
+    ref_a = dl * wc * b1.float() * keep * ka.float() * (1 - a * a)
+    ref_b = dl * wc * a1.float() * keep * kb.float() * b * (1 - b)
+    torch.testing.assert_close(d_a, ref_a, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(d_b, ref_b, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(dwc, (dl * a1.float() * b1.float()).sum(0), rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(dbc, dlogit.sum(0), rtol=1e-4, atol=1e-4)

@@ -52,7 +52,10 @@ int mdl_gemm_nt(const void* a_planes, long long a_rows, long long a_cols, long l
                 const float* bias, const float* rowbias, const int* row2bag, int out_bf16, void* stream);
 /* Gated-attention scores of all heads in one launch (BatchedABMIL.forward, abmil.py:49-52; head loop Model.py:406-409):
  * logits[m,h] = sum_j tanh(x_h Wa_h^T + ba)_j * sigmoid(x_h Wb_h^T + bb)_j * wc_hj + bc_h, x_h = A[:, h*512:(h+1)*512].
- * b_planes = packed [n_heads*4][128 Wa rows | 128 Wb rows][512].  gate_a/gate_b (fp16 [M, n_heads*512]) may be NULL. */
+ * b_planes = packed [n_heads*4][128 Wa rows | 128 Wb rows][512].  gate_a/gate_b (optional, may be NULL): fp16 scratch for
+ * mdl_gate_bwd, ceil(M/32)*32 * n_heads*512 elements each, holding the dropout-scaled tanh / sigmoid outputs in a TILED
+ * layout — element (row m, gate column j) at ((((m/32) * (n_heads*32) + j/16) * 2 + (j%16)/8) * 32 + m%32) * 8 + j%8, i.e.
+ * blocks of 32 rows x 8 columns are contiguous (full-line stores from the epilogue's row-per-lane registers). */
 int mdl_gemm_gated(const void* a_planes, long long a_rows, long long a_cols, long long lda, long long a_plane_stride,
                    const void* b_planes, long long b_plane_stride, int M, int n_heads, int nsplit,
                    const float* ba, const float* bb, const float* wc, const float* bc,
@@ -93,7 +96,9 @@ int mdl_ln_gelu_bwd(const void* z, long long M, int C, const float* gamma, const
                     float drop_p, unsigned long long seed, unsigned stream_id,
                     void* dz_planes, long long plane_stride, int nplanes,
                     float* dgamma, float* dbeta, float* dbias, const int* row2bag, float* bag_dz, int in_bf16, void* stream);
-/* Backward of the gate nonlinearities of mdl_gemm_gated; dpre planes [M, n_heads*1024] in packed gate order. */
+/* Backward of the gate nonlinearities of mdl_gemm_gated; gate_a / gate_b in the tiled scratch layout described there;
+ * dpre planes [M, n_heads*1024] row-major in packed gate order.  `seed` is unused: the dropout masks are read off the saved
+ * gates (a dropped gate is an exact zero). */
 int mdl_gate_bwd(const void* gate_a, const void* gate_b, const float* dlogit, const float* wc, long long M, int n_heads,
                  float drop_p, unsigned long long seed, void* dpre_planes, long long plane_stride, int nplanes,
                  float* dba, float* dbb, float* dwc, float* dbc, void* stream);

@@ -393,10 +393,16 @@ ln_gelu_bwd_kernel(const void* __restrict__ z, int M, const float* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Gated-attention backward (elementwise part).  gate_a/gate_b hold the (dropout-scaled) tanh / sigmoid outputs
-// as fp16 [M, H*512].  Produces d(pre-activation) as bf16 planes in the packed column order of the gated GEMM
-// (per head: 4 groups of [128 a-cols | 128 b-cols]) and the column sums d(ba), d(bb), d(wc), d(bc).
-// Thread t owns gate columns [8t, 8t+8) for the whole kernel; a block sweeps rows R at a time.
+// Gated-attention backward (elementwise part).  gate_a/gate_b hold the (dropout-scaled) tanh / sigmoid outputs as fp16 in
+// the TILED scratch layout the gated GEMM's epilogue writes (32 rows x 8 columns contiguous, see gate_tile_offset).
+// Produces d(pre-activation) as bf16 planes in the packed column order of the gated GEMM (per head: 4 groups of
+// [128 a-cols | 128 b-cols]) and the column sums d(ba), d(bb), d(wc), d(bc).
+//
+// A block owns ONE 64-column slice of the gate columns (grid.x % 32) and sweeps 32-row blocks; warp w owns the slice's
+// 8-column slab w and lane = row, so a warp's load is one contiguous 512-byte slab of the tiled layout and every thread keeps
+// the same 8 columns — and their 24 column-sum accumulators — for the whole kernel (one shuffle reduction over the rows at the
+// end).  The results of a row block are transposed through (double-buffered) shared memory so that the row-major dpre planes
+// are written in 128-byte row segments.
 //
 // The dropout masks are NOT regenerated: a dropped gate was stored as an exact zero, and every product below that must
 // vanish for a dropped gate does so by itself except the tanh branch's own derivative, which one select on `a == 0`
@@ -404,83 +410,139 @@ ln_gelu_bwd_kernel(const void* __restrict__ z, int M, const float* __restrict__ 
 // dropped; the gates themselves carry 2^-11 per element, so this is far inside the precision of what was saved.)
 //   dpre_a = dl wc (b mb) ma (1 - a^2),  dpre_b = dl wc (a ma) mb b (1 - b),  ma, mb in {0, 1/(1-p)}
 // ---------------------------------------------------------------------------------------------------
-#ifndef GATE_BWD_ROWS
-#define GATE_BWD_ROWS 4
-#endif
-template <int R>
-__global__ void __launch_bounds__(256, 3)
+constexpr int GB_COLS = 32;                 // gate columns per block (4 warps x 8 columns)
+constexpr int GB_THREADS = GB_COLS * 4;
+constexpr int GB_PITCH = GB_COLS + 8;       // bf16 elements per staged row (144 bytes: 16-byte accesses of consecutive rows hit distinct banks)
+template <int NPL>
+__global__ void __launch_bounds__(GB_THREADS, 6)
 gate_bwd_kernel(const __half* __restrict__ gate_a, const __half* __restrict__ gate_b, const float* __restrict__ dlogit,
                 const float* __restrict__ wc, long long M, int n_heads, float drop_p,
-                __nv_bfloat16* __restrict__ dpre, long long plane_stride, int nplanes,
+                __nv_bfloat16* __restrict__ dpre, long long plane_stride,
                 float* __restrict__ dba, float* __restrict__ dbb, float* __restrict__ dwc, float* __restrict__ dbc) {
-    const int HC = n_heads * 512;            // gate columns per row
-    const int j0 = threadIdx.x * 8;          // requires HC == blockDim.x * 8  (n_heads = 4 -> 256 threads)
-    const int head = j0 / 512, jh = j0 % 512;
-    const int packed0 = head * 1024 + (jh / 128) * 256 + (jh % 128);  // a-part; b-part is +128
+    __shared__ __align__(16) __nv_bfloat16 stage[2][NPL][2][32][GB_PITCH];     // double-buffered: one barrier per row block
+    const int HC = n_heads * 512;
+    const int groups = HC / GB_COLS;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cg = blockIdx.x % groups;                      // GB_COLS-column slice of a 128-column gate group
+    const int jg = cg * GB_COLS;                             // first gate column of the slice
+    const int head = jg >> 9, grp = (jg >> 7) & 3;
+    const int j0 = jg + warp * 8;                            // this thread's 8 gate columns (one 32 x 8 slab of the tiled layout per row block)
+    const int pcol_a = head * 1024 + grp * 256 + (jg & 127); // packed column of the slice's a-part; b-part is +128
     const bool drop = drop_p > 0.f;
-    const float keep_inv = drop ? (1.f - drop_p) : 1.f;               // undoes the 1/(1-p) scaling of a stored gate
+    const float keep_inv = drop ? (1.f - drop_p) : 1.f;      // undoes the 1/(1-p) scaling of a stored gate
     const float keep = drop ? __fdividef(1.f, 1.f - drop_p) : 1.f;
     float kw[8], s_a[8], s_b[8], s_w[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { kw[i] = __ldg(wc + j0 + i) * keep; s_a[i] = 0.f; s_b[i] = 0.f; s_w[i] = 0.f; }
     float s_c = 0.f;
-    for (long long m0 = (long long)blockIdx.x * R; m0 < M; m0 += (long long)gridDim.x * R) {
-        uint4 ua[R], ub[R];
-        float dl[R];
+    const bool count_c = warp == 0 && (jg & 511) == 0;      // one warp per head sums dlogit
+    const long long n_rb = (M + 31) >> 5;
+    const int chunks = gridDim.x / groups, chunk = blockIdx.x / groups;
+    // slab of row block rb: ((rb * (HC/16) + j0/16) * 2 + (j0%16)/8) * 32 rows * 8 halfs, + lane * 8
+    const size_t slab0 = ((size_t)(j0 >> 4) * 2 + (size_t)((j0 >> 3) & 1)) * 256 + (size_t)lane * 8;
+    const size_t rb_stride = (size_t)(HC / 16) * 512;
+    // software pipeline: the loads of the next two row blocks are in flight while one is evaluated
+    constexpr int PF = 2;
+    uint4 qa[PF], qb[PF];
+    float qdl[PF];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const long long m = m0 + r < M ? m0 + r : m0;
-            ua[r] = ld_nc_na(reinterpret_cast<const uint4*>(gate_a + m * HC + j0));
-            ub[r] = ld_nc_na(reinterpret_cast<const uint4*>(gate_b + m * HC + j0));
-            dl[r] = m0 + r < M ? __ldg(dlogit + m * n_heads + head) : 0.f;
+    for (int f = 0; f < PF; ++f) {
+        const long long rb = chunk + (long long)f * chunks;
+        qa[f] = make_uint4(0, 0, 0, 0); qb[f] = make_uint4(0, 0, 0, 0); qdl[f] = 0.f;
+        if (rb < n_rb) {
+            qa[f] = ld_nc_na(reinterpret_cast<const uint4*>(gate_a + rb * rb_stride + slab0));
+            qb[f] = ld_nc_na(reinterpret_cast<const uint4*>(gate_b + rb * rb_stride + slab0));
+            const long long mm = rb * 32 + lane;
+            qdl[f] = mm < M ? __ldg(dlogit + mm * n_heads + head) : 0.f;
         }
+    }
+    int buf = 0;
+    for (long long rb = chunk; rb < n_rb; rb += chunks) {
+        const long long m = rb * 32 + lane;
+        const bool ok = m < M;
+        const uint4 ua = qa[0], ub = qb[0];
+        const float dl = qdl[0];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (m0 + r >= M) break;
-            const long long m = m0 + r;
-            const __half2* ha = reinterpret_cast<const __half2*>(&ua[r]);
-            const __half2* hb = reinterpret_cast<const __half2*>(&ub[r]);
-            float dpa[8], dpb[8];
-#pragma unroll
-            for (int i2 = 0; i2 < 4; ++i2) {
-                const float2 fa = __half22float2(ha[i2]);
-                const float2 fb = __half22float2(hb[i2]);
-                const float adv[2] = {fa.x, fa.y}, bdv[2] = {fb.x, fb.y};
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const int i = 2 * i2 + k;
-                    const float ad = adv[k], bd = bdv[k];               // dropout-scaled gates (0 where dropped)
-                    const float a = ad * keep_inv, b = bd * keep_inv;
-                    const float t = dl[r] * kw[i];                      // dl wc / (1-p): the surviving mask factor of either branch
-                    const float da = (t * bd) * fmaf(-a, a, 1.f);
-                    dpa[i] = (drop && ad == 0.f) ? 0.f : da;
-                    dpb[i] = (t * ad) * fmaf(-b, b, b);
-                    s_a[i] += dpa[i]; s_b[i] += dpb[i]; s_w[i] = fmaf(dl[r], ad * bd, s_w[i]);
-                }
+        for (int f = 0; f + 1 < PF; ++f) { qa[f] = qa[f + 1]; qb[f] = qb[f + 1]; qdl[f] = qdl[f + 1]; }
+        {
+            const long long rn = rb + (long long)PF * chunks;
+            if (rn < n_rb) {
+                qa[PF - 1] = ld_nc_na(reinterpret_cast<const uint4*>(gate_a + rn * rb_stride + slab0));
+                qb[PF - 1] = ld_nc_na(reinterpret_cast<const uint4*>(gate_b + rn * rb_stride + slab0));
+                const long long mm = rn * 32 + lane;
+                qdl[PF - 1] = mm < M ? __ldg(dlogit + mm * n_heads + head) : 0.f;
             }
-            if (threadIdx.x % 64 == 0) s_c += dl[r];  // one thread per head
+        }
+        if (count_c) s_c += dl;
+        float dpa[8], dpb[8];
+        const __half2* ha = reinterpret_cast<const __half2*>(&ua);
+        const __half2* hb = reinterpret_cast<const __half2*>(&ub);
+#pragma unroll
+        for (int i2 = 0; i2 < 4; ++i2) {
+            const float2 fa = __half22float2(ha[i2]);
+            const float2 fb = __half22float2(hb[i2]);
+            const float adv[2] = {fa.x, fa.y}, bdv[2] = {fb.x, fb.y};
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int i = 2 * i2 + k;
+                const float ad = ok ? adv[k] : 0.f, bd = ok ? bdv[k] : 0.f;   // dropout-scaled gates (0 where dropped); padding rows contribute nothing
+                const float a = ad * keep_inv, b = bd * keep_inv;
+                const float t = dl * kw[i];                                   // dl wc / (1-p): the surviving mask factor of either branch
+                const float da = (t * bd) * fmaf(-a, a, 1.f);
+                dpa[i] = (drop && ad == 0.f) ? 0.f : da;
+                dpb[i] = (t * ad) * fmaf(-b, b, b);
+                s_a[i] += dpa[i]; s_b[i] += dpb[i]; s_w[i] = fmaf(dl, ad * bd, s_w[i]);
+            }
+        }
+        // registers -> shared (this thread: row `lane`, columns warp*8 .. +7 of the slice), hi / lo planes
+        {
             uint32_t ah[4], al[4], bh[4], bl[4];
 #pragma unroll
             for (int i2 = 0; i2 < 4; ++i2) {
                 split_bf16x2(dpa[2 * i2], dpa[2 * i2 + 1], ah[i2], al[i2]);
                 split_bf16x2(dpb[2 * i2], dpb[2 * i2 + 1], bh[i2], bl[i2]);
             }
-            __nv_bfloat16* o = dpre + (size_t)m * (size_t)(n_heads * 1024) + packed0;
-            *reinterpret_cast<uint4*>(o) = make_uint4(ah[0], ah[1], ah[2], ah[3]);
-            *reinterpret_cast<uint4*>(o + 128) = make_uint4(bh[0], bh[1], bh[2], bh[3]);
-            if (nplanes > 1) {
-                *reinterpret_cast<uint4*>(o + plane_stride) = make_uint4(al[0], al[1], al[2], al[3]);
-                *reinterpret_cast<uint4*>(o + plane_stride + 128) = make_uint4(bl[0], bl[1], bl[2], bl[3]);
+            const int c = warp * 8;
+            *reinterpret_cast<uint4*>(&stage[buf][0][0][lane][c]) = make_uint4(ah[0], ah[1], ah[2], ah[3]);
+            *reinterpret_cast<uint4*>(&stage[buf][0][1][lane][c]) = make_uint4(bh[0], bh[1], bh[2], bh[3]);
+            if (NPL > 1) {
+                *reinterpret_cast<uint4*>(&stage[buf][NPL - 1][0][lane][c]) = make_uint4(al[0], al[1], al[2], al[3]);
+                *reinterpret_cast<uint4*>(&stage[buf][NPL - 1][1][lane][c]) = make_uint4(bl[0], bl[1], bl[2], bl[3]);
             }
         }
+        __syncthreads();     // the only barrier of a row block: the other buffer is rewritten one iteration later, after every thread
+                             // has passed this barrier again, i.e. finished reading it
+        // shared -> global: GB_COLS / 8 lanes cover one row segment; the block's threads = all 32 rows
+        {
+            const int row = tid / (GB_COLS / 8), c = (tid % (GB_COLS / 8)) * 8;
+            const long long mr = rb * 32 + row;
+            if (mr < M) {
+#pragma unroll
+                for (int pl = 0; pl < NPL; ++pl)
+#pragma unroll
+                    for (int br = 0; br < 2; ++br) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(&stage[buf][pl][br][row][c]);
+                        __nv_bfloat16* o = dpre + (size_t)pl * (size_t)plane_stride + (size_t)mr * (size_t)(n_heads * 1024) + pcol_a + br * 128 + c;
+                        *reinterpret_cast<uint4*>(o) = v;
+                    }
+            }
+        }
+        buf ^= 1;
     }
+    // column sums over the rows (lanes) of this warp's 8 columns
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        atomicAdd(dba + j0 + i, s_a[i]);
-        atomicAdd(dbb + j0 + i, s_b[i]);
-        atomicAdd(dwc + j0 + i, s_w[i]);
+        const float va = warp_sum(s_a[i]), vb = warp_sum(s_b[i]), vw = warp_sum(s_w[i]);
+        if (lane == 0) {
+            atomicAdd(dba + j0 + i, va);
+            atomicAdd(dbb + j0 + i, vb);
+            atomicAdd(dwc + j0 + i, vw);
+        }
     }
-    if (threadIdx.x % 64 == 0) atomicAdd(dbc + head, s_c);
+    if (count_c) {
+        s_c = warp_sum(s_c);
+        if (lane == 0) atomicAdd(dbc + head, s_c);
+    }
 }
 
 // out[p][s, :] = planes[p][rows[s], :]  — row gather of a bf16 planes tensor (token window of the local loss: only the
@@ -694,9 +756,18 @@ int mdl_gate_bwd(const void* gate_a, const void* gate_b, const float* dlogit, co
     MDL_REQUIRE(n_heads == 4, "gate_bwd: only n_heads == 4 is built (got %d)", n_heads);
     if (M == 0) return 0;
     (void)seed;      // the masks are read off the stored gates (a dropped gate is an exact zero), not regenerated
-    const int grid = grid_for(M, 32, 3);
-    gate_bwd_kernel<GATE_BWD_ROWS><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)gate_a, (const __half*)gate_b, dlogit, wc, M, n_heads, drop_p,
-                                                                          (__nv_bfloat16*)dpre_planes, plane_stride, nplanes, dba, dbb, dwc, dbc);
+    const int groups = n_heads * 512 / GB_COLS;            // 64-column slices
+    const long long n_rb = (M + 31) / 32;
+    long long chunks = (long long)kNumSMs * 6 / groups;    // ~6 resident blocks per SM
+    if (chunks > n_rb) chunks = n_rb;
+    if (chunks < 1) chunks = 1;
+    const int grid = (int)(chunks * groups);
+    if (nplanes > 1)
+        gate_bwd_kernel<2><<<grid, GB_THREADS, 0, (cudaStream_t)stream>>>((const __half*)gate_a, (const __half*)gate_b, dlogit, wc, M, n_heads, drop_p,
+                                                                  (__nv_bfloat16*)dpre_planes, plane_stride, dba, dbb, dwc, dbc);
+    else
+        gate_bwd_kernel<1><<<grid, GB_THREADS, 0, (cudaStream_t)stream>>>((const __half*)gate_a, (const __half*)gate_b, dlogit, wc, M, n_heads, drop_p,
+                                                                  (__nv_bfloat16*)dpre_planes, plane_stride, dba, dbb, dwc, dbc);
     MDL_CHECK_LAUNCH();
     return 0;
 }

@@ -190,8 +190,9 @@ static void layout_fwd(Arena& a, const Desc& d, FwdState& s) {
     s.h2 = a.get<__nv_bfloat16>((size_t)npl * M * HID);
     s.z3 = a.raw((size_t)M * C * d.act_size); s.mean3 = a.get<float>(M); s.rstd3 = a.get<float>(M);
     s.h3 = a.get<__nv_bfloat16>((size_t)npl * M * C);
-    s.gate_a = d.keep ? a.get<__half>((size_t)M * d.H * GATE) : nullptr;
-    s.gate_b = d.keep ? a.get<__half>((size_t)M * d.H * GATE) : nullptr;
+    const size_t gate_rows = ((size_t)M + 31) / 32 * 32;     // tiled scratch layout: whole 32-row blocks (gemm_common.cuh::gate_tile_offset)
+    s.gate_a = d.keep ? a.get<__half>(gate_rows * d.H * GATE) : nullptr;
+    s.gate_b = d.keep ? a.get<__half>(gate_rows * d.H * GATE) : nullptr;
     s.attn_p = a.get<float>((size_t)M * d.H);
     s.tsplit = mdl_pool_tsplit(d.R, M, d.H, HID);
     s.pool_ws = s.tsplit > 1 ? a.raw((size_t)mdl_pool_workspace_bytes(d.R, d.H, HID, s.tsplit)) : nullptr;

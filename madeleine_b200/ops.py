@@ -267,6 +267,26 @@ def gemm_tn_accum(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, nsplit: i
     return out
 
 
+def gate_buffer(M: int, HC: int, device) -> torch.Tensor:
+    """fp16 scratch for the saved gates of mdl_gemm_gated / mdl_gate_bwd (tiled layout, whole 32-row blocks)."""
+    return torch.empty((M + 31) // 32 * 32 * HC, dtype=torch.float16, device=device)
+
+
+def gate_untile(buf: torch.Tensor, M: int, HC: int) -> torch.Tensor:
+    """Tiled gate scratch -> row-major [M, HC] (tests / debugging): blocks of 32 rows x 8 columns are contiguous."""
+    n_rb = (M + 31) // 32
+    return buf.view(n_rb, HC // 16, 2, 32, 8).permute(0, 3, 1, 2, 4).reshape(n_rb * 32, HC)[:M]
+
+
+def gate_tile(x: torch.Tensor) -> torch.Tensor:
+    """Row-major [M, HC] fp16 -> tiled gate scratch (inverse of gate_untile; padding rows are zero)."""
+    M, HC = x.shape
+    n_rb = (M + 31) // 32
+    pad = torch.zeros(n_rb * 32, HC, dtype=x.dtype, device=x.device)
+    pad[:M] = x
+    return pad.view(n_rb, 32, HC // 16, 2, 8).permute(0, 2, 3, 1, 4).contiguous().view(-1)
+
+
 def pool_fwd(h3, npl, logits, cu, tok_idx, R, total_tokens, H, E, out, attn_p, act, tsplit=0):
     """Attention pooling; picks the token split and provides the (deterministic) partial-sum workspace."""
     M, C = h3.shape[1], h3.shape[2]

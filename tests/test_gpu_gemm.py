@@ -133,10 +133,11 @@ def test_gemm_gated(M, nsplit):
     packed = torch.cat([torch.cat([Wa[h, g * 128:(g + 1) * 128], Wb[h, g * 128:(g + 1) * 128]]) for h in range(H) for g in range(4)])
     xp, wp = ops.split_planes(X, npl), ops.split_planes(packed.contiguous(), npl)
     logits = torch.empty(M, H, device=DEV)
-    ga = torch.empty(M, H * 512, dtype=torch.float16, device=DEV)
-    gb = torch.empty(M, H * 512, dtype=torch.float16, device=DEV)
+    ga = ops.gate_buffer(M, H * 512, DEV)                    # tiled scratch layout
+    gb = ops.gate_buffer(M, H * 512, DEV)
     call("mdl_gemm_gated", xp, M, H * 512, H * 512, M * H * 512, wp, wp.shape[1] * wp.shape[2], M, H, nsplit, ba, bb, wc, bc,
          logits, ga, gb, 0.0, 0, _st())
+    ga, gb = ops.gate_untile(ga, M, H * 512), ops.gate_untile(gb, M, H * 512)
     x64 = xp.double().sum(0) if nsplit == 3 else xp[0].double()
     ref_l, ref_a, ref_b = [], [], []
     for h in range(H):
@@ -168,7 +169,7 @@ def test_gemm_gated_dropout_forward_and_gate_bwd_consistency(p):
     seed), the logits are those gates' weighted sum, and mdl_gate_bwd — which reads the masks off the saved gates instead
     of regenerating them — returns the gradient of exactly that masked function.  p = 0.25 takes the 8-bit-field mask path
     (p * 256 integral), p = 0.1 the 16-bit one."""
-    M, H, nsplit, npl = 640, 4, 3, 2
+    M, H, nsplit, npl = 650, 4, 3, 2                      # not a multiple of 32: the tiled gate scratch has padding rows
     g = torch.Generator().manual_seed(17)
     X = torch.randn(M, H * 512, generator=g).to(DEV)
     packed = (torch.randn(H * 1024, 512, generator=g) / 22.6).to(DEV)
@@ -178,11 +179,11 @@ def test_gemm_gated_dropout_forward_and_gate_bwd_consistency(p):
 
     def run(seed, drop):
         logits = torch.empty(M, H, device=DEV)
-        ga = torch.empty(M, H * 512, dtype=torch.float16, device=DEV)
-        gb = torch.empty_like(ga)
+        ga = ops.gate_buffer(M, H * 512, DEV)
+        gb = ops.gate_buffer(M, H * 512, DEV)
         call("mdl_gemm_gated", xp, M, H * 512, H * 512, M * H * 512, wp, wp.shape[1] * wp.shape[2], M, H, nsplit, ba, bb, wc, bc,
              logits, ga, gb, drop, seed, _st())
-        return logits, ga, gb
+        return logits, ops.gate_untile(ga, M, H * 512).contiguous(), ops.gate_untile(gb, M, H * 512).contiguous()
 
     l0, a0, b0 = run(5, 0.0)
     l1, a1, b1 = run(5, p)
@@ -208,7 +209,7 @@ def test_gemm_gated_dropout_forward_and_gate_bwd_consistency(p):
     dpre = torch.empty(2, M, H * 1024, dtype=torch.bfloat16, device=DEV)
     dba, dbb, dwc = (torch.zeros(H * 512, device=DEV) for _ in range(3))
     dbc = torch.zeros(H, device=DEV)
-    call("mdl_gate_bwd", a1, b1, dlogit, wc, M, H, p, 5, dpre, M * H * 1024, 2, dba, dbb, dwc, dbc, _st())
+    call("mdl_gate_bwd", ops.gate_tile(a1), ops.gate_tile(b1), dlogit, wc, M, H, p, 5, dpre, M * H * 1024, 2, dba, dbb, dwc, dbc, _st())
     d = (dpre[0].float() + dpre[1].float()).view(M, H, 4, 2, 128)
     d_a, d_b = d[:, :, :, 0].reshape(M, H * 512), d[:, :, :, 1].reshape(M, H * 512)
     a = a1.float() / keep                       # tanh / sigmoid values where kept, 0 where dropped

@@ -380,7 +380,8 @@ def test_gate_bwd():
     dpre = torch.empty(2, M, H * 1024, dtype=torch.bfloat16, device=DEV)
     dba, dbb, dwc = (torch.zeros(H * 512, device=DEV) for _ in range(3))
     dbc = torch.zeros(H, device=DEV)
-    call("mdl_gate_bwd", ga, gb, dlogit, wc.detach(), M, H, 0.0, 0, dpre, M * H * 1024, 2, dba, dbb, dwc, dbc, _st())
+    call("mdl_gate_bwd", ops.gate_tile(ga), ops.gate_tile(gb), dlogit, wc.detach(), M, H, 0.0, 0, dpre, M * H * 1024, 2, dba, dbb, dwc, dbc,
+         _st())
     d = planes_f32(dpre).view(M, H, 4, 2, 128)               # [m, h, group, a|b, i]
     d_a = d[:, :, :, 0].reshape(M, H * 512)
     d_b = d[:, :, :, 1].reshape(M, H * 512)

@@ -21,8 +21,8 @@ for nsplit, npl in ((3, 2), (1, 1)):
     vec = lambda n: torch.randn(n, device=dev) * 0.04  # noqa: E731
     ba, bb, wc, bc = vec(H * 512), vec(H * 512), vec(H * 512), vec(H)
     logits = torch.empty(M, H, device=dev)
-    ga = torch.empty(M, H * 512, dtype=torch.float16, device=dev)
-    gb = torch.empty_like(ga)
+    ga = ops.gate_buffer(M, H * 512, dev)
+    gb = ops.gate_buffer(M, H * 512, dev)
     st = stream_ptr(dev)
     for p in (0.0, 0.25):
         for keep in (False, True):

@@ -543,6 +543,8 @@ def main():
         # what the link alone gives on this box (the e2e number is bounded by it on hosts with slow pinned copies)
         scratch = torch.empty_like(feats_dev)
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()              # all ranks copy at the same time: the rate a rank sees when the host serves N GPUs
         torch.cuda.synchronize()
         c0.record()
         for _ in range(4):
@@ -551,12 +553,16 @@ def main():
         torch.cuda.synchronize()
         h2d_gbs = 4 * feats_host[0].numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
         del scratch
-        e2e = {"value": bags_per_step / (ms_e2e * 1e-3), "unit": "slides/s", "ms_per_step": ms_e2e,
+        h2d_ms = feats_host[0].numel() * 4 / (h2d_gbs * 1e9) * 1e3
+        bound = ("host h2d: one 131 MB batch takes %.2f ms at the %.1f GB/s a rank gets while all %d ranks copy, the step itself %.2f ms"
+                 % (h2d_ms, h2d_gbs, world, ms_step)) if h2d_ms > 0.9 * ms_step else "device (the copy hides under the step)"
+        e2e = {"value": bags_per_step / (ms_e2e * 1e-3), "unit": "slides/s", "ms_per_step": ms_e2e, "bound": bound,
                "h2d_bytes_per_step": feats_host[0].numel() * 4, "d2h_bytes_per_step": 4,
                "h2d_gbs_alone": h2d_gbs, "runs_ms_per_step": e2e_runs,
                "note": "pinned host features staged one batch ahead on a copy stream; every step's loss is read back inside the "
                        "timed region, two steps deferred so the host stays ahead of the device (tools/e2e_probe.py); "
-                       "h2d_gbs_alone = this box's pinned H2D rate for one batch with the GPU otherwise idle"}
+                       "h2d_gbs_alone = this box's pinned H2D rate for one batch with the GPU otherwise idle (N > 1: all ranks copying "
+                       "at the same time)"}
 
     if rank != 0:
         if world > 1:

@@ -4,6 +4,7 @@
 // All are coalesced, 16-byte vectorised, grid-stride over rows with grids sized as a multiple of the SM count.
 #include "common.cuh"
 #include "madeleine_b200.h"
+#include <stdlib.h>
 
 namespace mdl {
 

@@ -13,6 +13,12 @@
  *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, nothing synchronises;
  *   - "planes": an fp32 matrix held as bf16 hi plane followed (plane_stride elements later) by a bf16 lo plane,
  *     x ~= hi + lo.  nplanes/nsplit = 2/3 gives fp32-grade products on the bf16 tensor pipe, 1/1 plain bf16;
+ *   - MDL_PLANES_F16 OR-ed into an `nplanes` or `nsplit` argument selects fp16 hi/lo planes instead (x ~= hi + lo with
+ *     2 x 11 mantissa bits, 2^-22 per element instead of 2^-17): the fp32-grade INFERENCE format.  Supported by
+ *     mdl_split_planes, mdl_gather_split (weights: values are multiplied by 64 before the split so that the lo plane
+ *     stays in fp16's normal range), mdl_ln_gelu_fwd, mdl_gemm_nt and mdl_gemm_gated (both operands fp16, B planes from
+ *     mdl_gather_split; the accumulator is multiplied by 1/64), mdl_pool_fwd and mdl_planes_to_ref_order.  Conversions
+ *     saturate at +-65504.  Backward entry points take bf16 planes only;
  *   - token rows are bag-packed: bag r owns rows [cu_seqlens[r], cu_seqlens[r+1]).
  */
 #ifndef MADELEINE_B200_H
@@ -21,6 +27,8 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+
+#define MDL_PLANES_F16 0x100
 
 const char* mdl_last_error(void);
 /* Library/ABI version and the compute capability the kernels were built for (100 = sm_100a). */
@@ -217,7 +225,7 @@ enum mdl_enc_i {
     MDL_ENC_I_GR_B3, MDL_ENC_I_GR_G3, MDL_ENC_I_GR_BE3, MDL_ENC_I_GR_BA, MDL_ENC_I_GR_BB, MDL_ENC_I_GR_WC,
     MDL_ENC_I_GR_BC, MDL_ENC_I_GR_BTP, MDL_ENC_I_GR_WP, MDL_ENC_I_GR_BP,
     MDL_ENC_I_MASTER_NUMEL, MDL_ENC_I_MASTER_PRE0W, MDL_ENC_I_MASTER_EMB,
-    MDL_ENC_I_GR_N, MDL_ENC_I_GR_N_EARLY, MDL_ENC_I_GR_N_LATE,
+    MDL_ENC_I_GR_N, MDL_ENC_I_GR_N_EARLY, MDL_ENC_I_GR_N_LATE, MDL_ENC_I_PLANES_F16,
     MDL_ENC_I_COUNT
 };
 enum mdl_enc_f { MDL_ENC_F_P_PRE = 0, MDL_ENC_F_P_GATE, MDL_ENC_F_COUNT };

@@ -119,6 +119,31 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uin
     __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
     lo = *reinterpret_cast<uint32_t*>(&l);
 }
+// fp16 operand planes (inference): x ~= hi + lo with 11 + 11 mantissa bits (|err| <= 2^-22 |x| for |x| within fp16's normal range;
+// the absolute floor is fp16's subnormal spacing 6e-8).  Conversions saturate (+-65504) instead of producing infinities.
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));        // low half <- a, high half <- b
+    const __half2 h = *reinterpret_cast<const __half2*>(&hi);
+    const float2 hf = __half22float2(h);
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - hf.y), "f"(a - hf.x));
+}
+// one packed pair of planes values -> two floats
+__device__ __forceinline__ float2 f16x2_to_f32(uint32_t packed) { return __half22float2(*reinterpret_cast<const __half2*>(&packed)); }
+// PLANE FORMAT: 0 = bf16 hi/lo, 1 = fp16 hi/lo.  `nplanes` / `nsplit` arguments of the C ABI carry it as a flag bit.
+constexpr int kPlanesF16 = 0x100;
+template <bool F16>
+__device__ __forceinline__ void split_planes2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    if (F16) split_f16x2(a, b, hi, lo); else split_bf16x2(a, b, hi, lo);
+}
+template <bool F16>
+__device__ __forceinline__ float2 planes2_to_f32(uint32_t packed) {
+    if (F16) return f16x2_to_f32(packed);
+    return make_float2(__uint_as_float(packed << 16), __uint_as_float(packed & 0xffff0000u));
+}
+// weights are multiplied by this power of two before the fp16 split (|w| ~ 0.04 would put the lo plane into fp16's
+// subnormal range); the GEMM epilogues multiply the accumulator by its inverse
+#define MDL_F16_WEIGHT_SCALE 64.0f
+
 __device__ __forceinline__ float bf16_lo_of(uint32_t packed) { return __uint_as_float(packed << 16); }
 __device__ __forceinline__ float bf16_hi_of(uint32_t packed) { return __uint_as_float(packed & 0xffff0000u); }
 
@@ -344,6 +369,8 @@ __device__ __forceinline__ uint64_t make_umma_desc_sw64(uint32_t smem_addr, uint
     return d;
 }
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 D.
+// kind::f16 operand formats live in bits [7,10) (A) and [10,13) (B): 1 = BF16, 0 = F16
+__host__ __device__ constexpr uint32_t idesc_as_f16(uint32_t idesc_bf16) { return idesc_bf16 & ~((7u << 7) | (7u << 10)); }
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, bool a_mn_major, bool b_mn_major) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);

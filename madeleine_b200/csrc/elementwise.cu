@@ -26,6 +26,7 @@ static inline int grid_for(long long work_items, int per_block, int max_blocks_p
 // ---------------------------------------------------------------------------------------------------
 // fp32 [rows, cols] (row stride ld) -> bf16 planes [nplanes][rows][cols]
 // ---------------------------------------------------------------------------------------------------
+template <bool F16>
 __global__ void split_planes_kernel(const float* __restrict__ x, long long rows, int cols, long long ld,
                                     __nv_bfloat16* __restrict__ planes, long long plane_stride, int nplanes) {
     const int vec_per_row = cols >> 2;
@@ -34,23 +35,34 @@ __global__ void split_planes_kernel(const float* __restrict__ x, long long rows,
         const long long r = i / vec_per_row;
         const int c = (int)(i - r * vec_per_row) << 2;
         const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ld + c));
-        __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-        split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1); split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
+        uint32_t h01, l01, h23, l23;
+        split_planes2<F16>(v.x, v.y, h01, l01);
+        split_planes2<F16>(v.z, v.w, h23, l23);
         const long long o = r * cols + c;
-        *reinterpret_cast<uint2*>(planes + o) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+        *reinterpret_cast<uint2*>(planes + o) = make_uint2(h01, h23);
         if (nplanes > 1)
-            *reinterpret_cast<uint2*>(planes + plane_stride + o) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+            *reinterpret_cast<uint2*>(planes + plane_stride + o) = make_uint2(l01, l23);
     }
 }
 
 // packed[i] = split(src[idx[i]])  (weight packing: permutations / transposes expressed as an index map)
+template <bool F16>
 __global__ void gather_split_kernel(const float* __restrict__ src, const int* __restrict__ idx, long long n,
                                     __nv_bfloat16* __restrict__ planes, long long plane_stride, int nplanes) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        __nv_bfloat16 h, l;
-        split_bf16(__ldg(src + __ldg(idx + i)), h, l);
-        planes[i] = h;
-        if (nplanes > 1) planes[plane_stride + i] = l;
+        const float w = __ldg(src + __ldg(idx + i));
+        if (F16) {
+            // weights: scaled by a power of two so that the lo plane stays in fp16's normal range (undone in the GEMM epilogue)
+            uint32_t hi, lo;
+            split_f16x2(w * MDL_F16_WEIGHT_SCALE, 0.f, hi, lo);
+            reinterpret_cast<unsigned short*>(planes)[i] = (unsigned short)(hi & 0xffffu);
+            if (nplanes > 1) reinterpret_cast<unsigned short*>(planes)[plane_stride + i] = (unsigned short)(lo & 0xffffu);
+        } else {
+            __nv_bfloat16 h, l;
+            split_bf16(w, h, l);
+            planes[i] = h;
+            if (nplanes > 1) planes[plane_stride + i] = l;
+        }
     }
 }
 __global__ void gather_f32_kernel(const float* __restrict__ src, const int* __restrict__ idx, long long n, float* __restrict__ dst) {
@@ -97,7 +109,7 @@ __device__ __forceinline__ void prefetch_act(const void* base, size_t off) {
 // columns j*128 + lane*4), so the two row reductions are shuffles only and RPW*C/128 16-byte loads are in flight
 // per lane.  No shared memory, no block barriers.
 // ---------------------------------------------------------------------------------------------------
-template <int C, int RPW, bool ZBF16>
+template <int C, int RPW, bool ZBF16, bool F16>
 __global__ void __launch_bounds__(256, 2)
 ln_gelu_fwd_kernel(const void* __restrict__ z, int M, const float* __restrict__ gamma, const float* __restrict__ beta,
                    float eps, float drop_p, unsigned long long seed, unsigned stream_id,
@@ -160,8 +172,8 @@ ln_gelu_fwd_kernel(const void* __restrict__ z, int M, const float* __restrict__ 
                     y0 *= msk[0]; y1 *= msk[1]; y2 *= msk[2]; y3 *= msk[3];
                 }
                 uint32_t h01, l01, h23, l23;
-                split_bf16x2(y0, y1, h01, l01);
-                split_bf16x2(y2, y3, h23, l23);
+                split_planes2<F16>(y0, y1, h01, l01);
+                split_planes2<F16>(y2, y3, h23, l23);
                 __nv_bfloat16* o = planes + row_off + j * 128;
                 *reinterpret_cast<uint2*>(o) = make_uint2(h01, h23);
                 if (nplanes > 1) *reinterpret_cast<uint2*>(o + plane_stride) = make_uint2(l01, l23);
@@ -633,14 +645,20 @@ int mdl_split_planes(const float* x, long long rows, int cols, long long ld, voi
     MDL_REQUIRE(cols % 4 == 0 && ld % 4 == 0, "split_planes: cols and ld must be multiples of 4");
     if (rows == 0) return 0;
     const long long total = rows * (cols / 4);
-    split_planes_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ld, (__nv_bfloat16*)planes, plane_stride, nplanes);
+    const bool f16 = (nplanes & kPlanesF16) != 0;
+    nplanes &= 0xff;
+    if (f16) split_planes_kernel<true><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ld, (__nv_bfloat16*)planes, plane_stride, nplanes);
+    else split_planes_kernel<false><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ld, (__nv_bfloat16*)planes, plane_stride, nplanes);
     MDL_CHECK_LAUNCH();
     return 0;
 }
 
 int mdl_gather_split(const float* src, const int* idx, long long n, void* planes, long long plane_stride, int nplanes, void* stream) {
     if (n == 0) return 0;
-    gather_split_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, idx, n, (__nv_bfloat16*)planes, plane_stride, nplanes);
+    const bool f16 = (nplanes & kPlanesF16) != 0;
+    nplanes &= 0xff;
+    if (f16) gather_split_kernel<true><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, idx, n, (__nv_bfloat16*)planes, plane_stride, nplanes);
+    else gather_split_kernel<false><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, idx, n, (__nv_bfloat16*)planes, plane_stride, nplanes);
     MDL_CHECK_LAUNCH();
     return 0;
 }
@@ -673,15 +691,23 @@ int mdl_ln_gelu_fwd(const void* z, long long M, int C, const float* gamma, const
     MDL_REQUIRE(M < (1LL << 31), "ln_gelu_fwd: too many rows");
     if (M == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
+    const bool f16 = (nplanes & kPlanesF16) != 0;
+    nplanes &= 0xff;
+    MDL_REQUIRE(!(f16 && z_bf16), "ln_gelu_fwd: fp16 planes are the fp32-grade inference format (z must be fp32)");
+#define MDL_LNF(CC, RPW, grid) \
+    do { \
+        if (z_bf16) ln_gelu_fwd_kernel<CC, RPW, true, false><<<grid, 256, 0, st>>>(z, (int)M, gamma, beta, eps, drop_p, seed, stream_id, (__nv_bfloat16*)planes, plane_stride, nplanes, mean, rstd); \
+        else if (f16) ln_gelu_fwd_kernel<CC, RPW, false, true><<<grid, 256, 0, st>>>(z, (int)M, gamma, beta, eps, drop_p, seed, stream_id, (__nv_bfloat16*)planes, plane_stride, nplanes, mean, rstd); \
+        else ln_gelu_fwd_kernel<CC, RPW, false, false><<<grid, 256, 0, st>>>(z, (int)M, gamma, beta, eps, drop_p, seed, stream_id, (__nv_bfloat16*)planes, plane_stride, nplanes, mean, rstd); \
+    } while (0)
     if (C == 512) {
         const int grid = grid_for(M, 8 * 2, 6);
-        if (z_bf16) ln_gelu_fwd_kernel<512, 2, true><<<grid, 256, 0, st>>>(z, (int)M, gamma, beta, eps, drop_p, seed, stream_id, (__nv_bfloat16*)planes, plane_stride, nplanes, mean, rstd);
-        else ln_gelu_fwd_kernel<512, 2, false><<<grid, 256, 0, st>>>(z, (int)M, gamma, beta, eps, drop_p, seed, stream_id, (__nv_bfloat16*)planes, plane_stride, nplanes, mean, rstd);
+        MDL_LNF(512, 2, grid);
     } else {
         const int grid = grid_for(M, 8, 4);
-        if (z_bf16) ln_gelu_fwd_kernel<2048, 1, true><<<grid, 256, 0, st>>>(z, (int)M, gamma, beta, eps, drop_p, seed, stream_id, (__nv_bfloat16*)planes, plane_stride, nplanes, mean, rstd);
-        else ln_gelu_fwd_kernel<2048, 1, false><<<grid, 256, 0, st>>>(z, (int)M, gamma, beta, eps, drop_p, seed, stream_id, (__nv_bfloat16*)planes, plane_stride, nplanes, mean, rstd);
+        MDL_LNF(2048, 1, grid);
     }
+#undef MDL_LNF
     MDL_CHECK_LAUNCH();
     return 0;
 }
@@ -775,6 +801,7 @@ int mdl_gate_bwd(const void* gate_a, const void* gate_b, const float* dlogit, co
 
 int mdl_gather_rows_planes(const void* planes, long long plane_stride_in, int nplanes, int C, const int* rows, long long n_sel,
                            void* out, long long plane_stride_out, void* stream) {
+    nplanes &= 0xff;      // a byte copy: the plane format flag does not matter
     MDL_REQUIRE(C % 8 == 0, "gather_rows_planes: C must be a multiple of 8 (got %d)", C);
     if (n_sel == 0) return 0;
     gather_rows_planes_kernel<<<grid_for(n_sel * nplanes, 8, 8), 256, 0, (cudaStream_t)stream>>>(

@@ -213,7 +213,11 @@ static int run_fwd(const Desc& d, bool dry, size_t* bytes_out) {
     if (dry) return 0;
     cudaStream_t st = d.st;
     void* stv = (void*)st;
-    const long long M = d.M; const int C = d.C, H = d.H, R = d.R, npl = d.npl_f, nsplit = d.nsplit_f;
+    const long long M = d.M; const int C = d.C, H = d.H, R = d.R;
+    // MDL_ENC_I_PLANES_F16: the operand planes (activations and the packed weights handed in) are fp16 hi/lo — the
+    // inference format of the fp32-grade mode; the flag rides on the nplanes / nsplit arguments of the entry points
+    const int f16 = d.ip[MDL_ENC_I_PLANES_F16] ? kPlanesF16 : 0;
+    const int npl = d.npl_f | f16, nsplit = d.nsplit_f | f16;
     const long long bfn = d.ip[MDL_ENC_I_BF_NUMEL];
     const float* x = d.ptr<const float>(MDL_ENC_P_X);
     const int* cu = d.ptr<const int>(MDL_ENC_P_CU);
@@ -221,6 +225,7 @@ static int run_fwd(const Desc& d, bool dry, size_t* bytes_out) {
     float* logits = d.ptr<float>(MDL_ENC_P_LOGITS);
     float* slide_hm = d.ptr<float>(MDL_ENC_P_SLIDE_HM);
     MDL_REQUIRE(x && cu && logits && slide_hm && d.ptr<void>(MDL_ENC_P_WBF) && d.ptr<void>(MDL_ENC_P_WF32), "mdl_encoder_fwd: null input");
+    MDL_REQUIRE(!(f16 && (d.keep || d.act_bf16 || d.nsplit_f != 3)), "mdl_encoder_fwd: fp16 planes are the fp32-grade INFERENCE format (keep = 0, 3-pass)");
 
     RUN(MDL_PROF_OTHER, mdl_row2bag(cu, R, s.row2bag, M, stv));
     if (d.se > 0) {

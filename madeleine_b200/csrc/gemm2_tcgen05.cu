@@ -171,7 +171,7 @@ gemm2_kf_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
         if (lane == 0 && rank == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N, kMN, kMN);
+            const uint32_t idesc = p.ab_f16 ? idesc_as_f16(make_idesc_bf16(256, BLOCK_N, kMN, kMN)) : make_idesc_bf16(256, BLOCK_N, kMN, kMN);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int unit = pair; unit < num_units; unit += num_pairs) {

@@ -39,6 +39,8 @@ struct GemmArgs {
     float drop_p; unsigned long long seed;
     int n_heads;
     int debug_flags;          // tools/gemm_bounds.py only: 1 = skip TMA loads, 2 = skip epilogue global writes
+    int ab_f16;               // operand planes are fp16 hi/lo (inference format) instead of bf16 hi/lo
+    float acc_scale;          // the accumulator is multiplied by this before bias / activations (1, or 1/MDL_F16_WEIGHT_SCALE)
 };
 
 template <int BLOCK_N>
@@ -92,9 +94,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, float* aux, uin
                 float4 v;
                 v.x = __uint_as_float(r[i]); v.y = __uint_as_float(r[i + 1]);
                 v.z = __uint_as_float(r[i + 2]); v.w = __uint_as_float(r[i + 3]);
-                if (EPI == EPI_STORE && p.bias != nullptr) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
-                    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                if (EPI == EPI_STORE) {
+                    // x * 1 and fma(x, 1, b) round exactly like x and x + b: the bf16-plane path is bit-for-bit what it was
+                    const float sc = p.acc_scale;
+                    if (p.bias != nullptr) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
+                        v.x = fmaf(v.x, sc, b.x); v.y = fmaf(v.y, sc, b.y); v.z = fmaf(v.z, sc, b.z); v.w = fmaf(v.w, sc, b.w);
+                    } else {
+                        v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+                    }
                 }
                 if (EPI == EPI_STORE && p.rowbias != nullptr) {
                     const float4 b = __ldg(reinterpret_cast<const float4*>(p.rowbias + (size_t)bag * p.N + n0 + i));
@@ -139,7 +147,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, float* aux, uin
         const DropCfg dcfg = make_drop_cfg(p.drop_p);
         const bool drop8 = dcfg.on && drop_p_is_8bit(p.drop_p);
         const uint32_t thresh24 = ((uint32_t)(p.drop_p * 256.f)) << 24;
-        constexpr float C2 = -2.885390081777927f, C1 = -1.4426950408889634f;
+        const float C2 = -2.885390081777927f * p.acc_scale, C1 = -1.4426950408889634f * p.acc_scale;
         uint32_t ra[2][16], rb[2][16];
         const uint32_t t_a = t_row + half * 64, t_b = t_row + 128 + half * 64;
         tmem_ld_32x16(t_a, ra[0]);

@@ -142,7 +142,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, kMNMajor, kMNMajor);
+            const uint32_t idesc = p.ab_f16 ? idesc_as_f16(make_idesc_bf16(BLOCK_M, BLOCK_N, kMNMajor, kMNMajor))
+                                            : make_idesc_bf16(BLOCK_M, BLOCK_N, kMNMajor, kMNMajor);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
@@ -353,6 +354,8 @@ int mdl_gemm_nt(const void* a_planes, long long a_rows, long long a_cols, long l
                 void* out, long long ldc, int M, int N, int K, int nsplit,
                 int grp_n_cols, int a_koff,
                 const float* bias, const float* rowbias, const int* row2bag, int out_bf16, void* stream) {
+    const bool f16 = (nsplit & kPlanesF16) != 0;     // operands are fp16 hi/lo planes, the B planes scaled by MDL_F16_WEIGHT_SCALE
+    nsplit &= 0xff;
     MDL_REQUIRE(nsplit == 1 || nsplit == 3, "nsplit must be 1 or 3");
     MDL_REQUIRE(K % BLOCK_K == 0, "K (%d) must be a multiple of %d", K, BLOCK_K);
     MDL_REQUIRE(N % 128 == 0, "N (%d) must be a multiple of 128", N);
@@ -377,6 +380,7 @@ int mdl_gemm_nt(const void* a_planes, long long a_rows, long long a_cols, long l
     g.grp_m_tiles = 1 << 30; g.b_coff = 0;
     g.out = (float*)out; g.ldc = (int)ldc; g.out_bf16 = out_bf16 ? 1 : 0; g.bias = bias; g.rowbias = rowbias; g.row2bag = row2bag;
     g.debug_flags = g_debug_flags;
+    g.ab_f16 = f16 ? 1 : 0; g.acc_scale = f16 ? 1.f / MDL_F16_WEIGHT_SCALE : 1.f;
     if (two_cta) {
         g.num_m_tiles = (M + 255) / 256;
         return launch_gemm2_kf(ta, tb, g, EPI_STORE, (cudaStream_t)stream);
@@ -397,6 +401,8 @@ int mdl_gemm_gated(const void* a_planes, long long a_rows, long long a_cols, lon
                    int M, int n_heads, int nsplit,
                    const float* ba, const float* bb, const float* wc, const float* bc,
                    float* logits, void* gate_a, void* gate_b, float drop_p, unsigned long long seed, void* stream) {
+    const bool f16 = (nsplit & kPlanesF16) != 0;
+    nsplit &= 0xff;
     MDL_REQUIRE(nsplit == 1 || nsplit == 3, "nsplit must be 1 or 3");
     MDL_REQUIRE(M > 0 && n_heads > 0, "bad sizes");
     const int planes = nsplit == 3 ? 2 : 1;
@@ -416,6 +422,7 @@ int mdl_gemm_gated(const void* a_planes, long long a_rows, long long a_cols, lon
     g.ba = ba; g.bb = bb; g.wc = wc; g.bc = bc; g.logits = logits;
     g.gate_a = reinterpret_cast<__half*>(gate_a); g.gate_b = reinterpret_cast<__half*>(gate_b);
     g.drop_p = drop_p; g.seed = seed; g.n_heads = n_heads;
+    g.ab_f16 = f16 ? 1 : 0; g.acc_scale = f16 ? 1.f / MDL_F16_WEIGHT_SCALE : 1.f;
     if (two_cta) {
         g.num_m_tiles = (M + 255) / 256;
         return launch_gemm2_kf(ta, tb, g, EPI_GATED, (cudaStream_t)stream);

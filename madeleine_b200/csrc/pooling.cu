@@ -28,6 +28,14 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p) {
     return r;
 }
 
+// fp16 planes (inference format): same accumulation, half2 -> float2 conversions
+__device__ __forceinline__ void fma8_f16(float (&acc)[8], float w, const uint4& v) {
+    const float2 a = f16x2_to_f32(v.x), b = f16x2_to_f32(v.y), c = f16x2_to_f32(v.z), d = f16x2_to_f32(v.w);
+    acc[0] = fmaf(w, a.x, acc[0]); acc[1] = fmaf(w, a.y, acc[1]);
+    acc[2] = fmaf(w, b.x, acc[2]); acc[3] = fmaf(w, b.y, acc[3]);
+    acc[4] = fmaf(w, c.x, acc[4]); acc[5] = fmaf(w, c.y, acc[5]);
+    acc[6] = fmaf(w, d.x, acc[6]); acc[7] = fmaf(w, d.y, acc[7]);
+}
 __device__ __forceinline__ void fma8(float (&acc)[8], float w, const uint4& v) {
     acc[0] = fmaf(w, bf16_lo_of(v.x), acc[0]); acc[1] = fmaf(w, bf16_hi_of(v.x), acc[1]);
     acc[2] = fmaf(w, bf16_lo_of(v.y), acc[2]); acc[3] = fmaf(w, bf16_hi_of(v.y), acc[3]);
@@ -94,7 +102,7 @@ pool_weights_kernel(const float* __restrict__ logits, const int* __restrict__ cu
     }
 }
 
-template <int NPLANES>
+template <int NPLANES, bool F16>
 __global__ void __launch_bounds__(POOL_THREADS, 4)
 pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long plane_stride, const float* __restrict__ attn_p,
                 const int* __restrict__ cu, const int* __restrict__ tok_idx, int H, int E, int tsplit,
@@ -131,8 +139,13 @@ pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long plane_stride, con
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            fma8(acc, w[u], vh[u]);
-            if (NPLANES > 1) fma8(acc, w[u], vl[u]);
+            if (F16) {
+                fma8_f16(acc, w[u], vh[u]);
+                if (NPLANES > 1) fma8_f16(acc, w[u], vl[u]);
+            } else {
+                fma8(acc, w[u], vh[u]);
+                if (NPLANES > 1) fma8(acc, w[u], vl[u]);
+            }
         }
     }
 #pragma unroll
@@ -236,7 +249,7 @@ pool_bwd_dlogit_kernel(const __nv_bfloat16* __restrict__ x, long long plane_stri
 
 // Head-major [M, H*E] planes -> reference channel order fp32 [M, E, H] (c_ref = e*H + h); only for
 // ABMILEmbedder(return_preattn_feats=True) called on its own.
-__global__ void planes_to_ref_order_kernel(const __nv_bfloat16* __restrict__ x, long long plane_stride, int nplanes,
+__global__ void planes_to_ref_order_kernel(const __nv_bfloat16* __restrict__ x, long long plane_stride, int nplanes, int f16,
                                            long long M, int H, int E, float* __restrict__ out) {
     const long long total = M * H * E;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -244,8 +257,15 @@ __global__ void planes_to_ref_order_kernel(const __nv_bfloat16* __restrict__ x, 
         const int cr = (int)(i - m * H * E);
         const int e = cr / H, h = cr % H;
         const long long src = m * H * E + h * E + e;
-        float v = __bfloat162float(x[src]);
-        if (nplanes > 1) v += __bfloat162float(x[plane_stride + src]);
+        float v;
+        if (f16) {
+            const __half* xh = reinterpret_cast<const __half*>(x);
+            v = __half2float(xh[src]);
+            if (nplanes > 1) v += __half2float(xh[plane_stride + src]);
+        } else {
+            v = __bfloat162float(x[src]);
+            if (nplanes > 1) v += __bfloat162float(x[plane_stride + src]);
+        }
         out[i] = v;
     }
 }
@@ -288,6 +308,8 @@ int mdl_pool_weights(const float* logits, const int* cu_seqlens, const int* tok_
 int mdl_pool_fwd(const void* x_planes, long long plane_stride, int nplanes, const float* attn_p, const int* cu_seqlens,
                  const int* tok_idx, int n_bags, long long total_tokens, int n_heads, int head_dim,
                  float* out, int tsplit, void* workspace, void* stream) {
+    const bool f16 = (nplanes & kPlanesF16) != 0;       // fp16 hi/lo planes (the fp32-grade inference format)
+    nplanes &= 0xff;
     MDL_REQUIRE(head_dim % 256 == 0, "pool_fwd: head_dim must be a multiple of 256 (got %d)", head_dim);
     MDL_REQUIRE(nplanes == 1 || nplanes == 2, "pool_fwd: nplanes must be 1 or 2");
     MDL_REQUIRE(attn_p != nullptr, "pool_fwd: attn_p (from mdl_pool_weights) is required");
@@ -300,10 +322,14 @@ int mdl_pool_fwd(const void* x_planes, long long plane_stride, int nplanes, cons
     float* partial = reinterpret_cast<float*>(workspace);
     int* tickets = pool_tickets(workspace, tsplit, n_bags, n_heads, head_dim);
     dim3 grid(halves * tsplit, n_heads, n_bags);
-    if (nplanes == 2)
-        pool_fwd_kernel<2><<<grid, POOL_THREADS, 0, st>>>((const __nv_bfloat16*)x_planes, plane_stride, attn_p, cu_seqlens, tok_idx, n_heads, head_dim, tsplit, out, partial, tickets);
+    if (nplanes == 2 && f16)
+        pool_fwd_kernel<2, true><<<grid, POOL_THREADS, 0, st>>>((const __nv_bfloat16*)x_planes, plane_stride, attn_p, cu_seqlens, tok_idx, n_heads, head_dim, tsplit, out, partial, tickets);
+    else if (nplanes == 2)
+        pool_fwd_kernel<2, false><<<grid, POOL_THREADS, 0, st>>>((const __nv_bfloat16*)x_planes, plane_stride, attn_p, cu_seqlens, tok_idx, n_heads, head_dim, tsplit, out, partial, tickets);
+    else if (f16)
+        pool_fwd_kernel<1, true><<<grid, POOL_THREADS, 0, st>>>((const __nv_bfloat16*)x_planes, plane_stride, attn_p, cu_seqlens, tok_idx, n_heads, head_dim, tsplit, out, partial, tickets);
     else
-        pool_fwd_kernel<1><<<grid, POOL_THREADS, 0, st>>>((const __nv_bfloat16*)x_planes, plane_stride, attn_p, cu_seqlens, tok_idx, n_heads, head_dim, tsplit, out, partial, tickets);
+        pool_fwd_kernel<1, false><<<grid, POOL_THREADS, 0, st>>>((const __nv_bfloat16*)x_planes, plane_stride, attn_p, cu_seqlens, tok_idx, n_heads, head_dim, tsplit, out, partial, tickets);
     MDL_CHECK_LAUNCH();
     return 0;
 }
@@ -337,10 +363,12 @@ int mdl_pool_bwd_dlogit(const void* x_planes, long long plane_stride, int nplane
 
 int mdl_planes_to_ref_order(const void* x_planes, long long plane_stride, int nplanes, long long M, int n_heads, int head_dim, float* out, void* stream) {
     if (M == 0) return 0;
+    const int f16 = (nplanes & kPlanesF16) != 0;
+    nplanes &= 0xff;
     const long long total = M * n_heads * head_dim;
     long long blocks = (total + 255) / 256;
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-    planes_to_ref_order_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x_planes, plane_stride, nplanes, M, n_heads, head_dim, out);
+    planes_to_ref_order_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x_planes, plane_stride, nplanes, f16, M, n_heads, head_dim, out);
     MDL_CHECK_LAUNCH();
     return 0;
 }

@@ -18,7 +18,7 @@ ENC_I = ['M', 'R', 'D_IN', 'D_IN_TOTAL', 'SE_DIM', 'N_HEADS', 'NSPLIT_FWD', 'NPL
          'F32_WC', 'F32_BC', 'F32_BTP', 'F32_WP', 'F32_BP',
          'GR_NUMEL', 'GR_W1', 'GR_W2', 'GR_W3', 'GR_WAB', 'GR_TP', 'GR_B1', 'GR_G1', 'GR_BE1', 'GR_B2', 'GR_G2', 'GR_BE2',
          'GR_B3', 'GR_G3', 'GR_BE3', 'GR_BA', 'GR_BB', 'GR_WC', 'GR_BC', 'GR_BTP', 'GR_WP', 'GR_BP',
-         'MASTER_NUMEL', 'MASTER_PRE0W', 'MASTER_EMB', 'GR_N', 'GR_N_EARLY', 'GR_N_LATE']
+         'MASTER_NUMEL', 'MASTER_PRE0W', 'MASTER_EMB', 'GR_N', 'GR_N_EARLY', 'GR_N_LATE', 'PLANES_F16']
 ENC_F = ['P_PRE', 'P_GATE']
 ENC_P = ['STREAM', 'X', 'CU', 'CODES', 'MASTER', 'WBF', 'WF32', 'ARENA', 'SLIDE_HM', 'SLIDE', 'LOGITS', 'TOKENS', 'REF',
          'VIEW_TOK_IDX', 'VIEW_CU', 'VIEW_ROW2SEG', 'TOKEN_ROWS', 'TOKEN_SEL_OF_ROW', 'BWD_ARENA', 'D_SLIDE', 'D_LOGITS',

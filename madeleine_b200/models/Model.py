@@ -141,7 +141,12 @@ class ABMILEmbedder(nn.Module):
         if se_dim > 0:
             params.append(embedding_weight)
         precision = ops.resolve_precision(precision)
-        key = (precision, str(dev), se_dim)
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        # fp32-grade inference runs on fp16 hi/lo operand planes (2^-22 per element instead of the training format's 2^-17:
+        # embeddings and attention logits at the accuracy of the reference's own fp32 evaluation); MADELEINE_B200_INFER_F16=0
+        # keeps the bf16 hi/lo planes of the training forward
+        f16 = (not need_grad) and precision in ("fp32", "fp32_fwd") and os.environ.get("MADELEINE_B200_INFER_F16", "1") != "0"
+        key = (precision, str(dev), se_dim, f16)
         spec = self._spec_cache.get((str(dev), se_dim))
         if spec is None:
             spec = ops.PackSpec([tuple(p.shape) for p in params], self.n_heads, d_in_total, dev, d_in=d_in)
@@ -151,11 +156,12 @@ class ABMILEmbedder(nn.Module):
         versions = (master.data_ptr(), sum(p._version for p in params))
         cached = self._pack_cache.get(key)
         if cached is None or cached[0] != versions:
-            pw = ops.PackedWeights(spec, master, 1 if precision == "bf16" else 2)
-            self._pack_cache = {key: (versions, pw)}      # one live pack: weights change every optimiser step
+            pw = ops.PackedWeights(spec, master, 1 if precision == "bf16" else 2, f16=f16)
+            # one live pack per operand format: weights change every optimiser step, evaluation alternates with training
+            self._pack_cache = {k: v for k, v in self._pack_cache.items() if v[0] == versions}
+            self._pack_cache[key] = (versions, pw)
         else:
             pw = cached[1]
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         if need_grad and d_in % 128 != 0:
             raise NotImplementedError(f"training needs a feature width that is a multiple of 128 (got {d_in}); "
                                       "inference works for any multiple of 64")

@@ -30,6 +30,7 @@ LN_EPS = 1e-5
 ACT_CODES = {"softmax": 0, "leaky_relu": 1, "relu": 2, "sigmoid": 3}
 
 _step_counter = [0]
+PLANES_F16 = 0x100      # MDL_PLANES_F16: flag on nplanes / nsplit arguments selecting fp16 hi/lo planes (fp32-grade inference)
 
 # Optional phase timeline (bench.py --timeline): when this is a list, the encoder's backward appends (label, cuda event)
 # pairs at its phase boundaries so that the multi-GPU cost of the two gradient all-reduces can be read off the device clock.
@@ -208,13 +209,15 @@ class PackedWeights:
     ``master`` is the flat fp32 concatenation of the parameters in PARAM_ORDER — normally the very buffer the parameters
     are views of (ABMILEmbedder flattens them once), so re-packing after an optimiser step is two launches and no copy."""
 
-    def __init__(self, spec: PackSpec, master: torch.Tensor, nplanes: int):
+    def __init__(self, spec: PackSpec, master: torch.Tensor, nplanes: int, f16: bool = False):
+        """f16: fp16 hi/lo operand planes (weights scaled by 64) — the inference format of the fp32-grade mode, see
+        include/madeleine_b200.h MDL_PLANES_F16; training packs bf16 planes."""
         dev = master.device
         st = stream_ptr(dev)
-        self.spec, self.nplanes = spec, nplanes
+        self.spec, self.nplanes, self.f16 = spec, nplanes, f16
         self.master = master
-        self.bf = torch.empty(nplanes, spec.bf_numel, dtype=torch.bfloat16, device=dev)
-        call("mdl_gather_split", master, spec.bf_idx, spec.bf_numel, self.bf, spec.bf_numel, nplanes, st)
+        self.bf = torch.empty(nplanes, spec.bf_numel, dtype=torch.float16 if f16 else torch.bfloat16, device=dev)
+        call("mdl_gather_split", master, spec.bf_idx, spec.bf_numel, self.bf, spec.bf_numel, nplanes | (PLANES_F16 if f16 else 0), st)
         self.f32 = torch.empty(spec.f32_numel, dtype=torch.float32, device=dev)
         call("mdl_gather_f32", master, spec.f32_idx, spec.f32_numel, self.f32, st)
 
@@ -409,6 +412,10 @@ def encoder_forward(x: torch.Tensor, cu: torch.Tensor, codes: Optional[torch.Ten
     ip[I['KEEP']] = int(keep_for_backward)
     ip[I['WANT_TOKENS']], ip[I['WANT_PROJECTOR']], ip[I['WANT_REF']] = int(opt.want_tokens), int(opt.want_projector), int(opt.want_ref_feats)
     ip[I['SEED']] = opt.seed & 0x7FFFFFFFFFFFFFFF
+    if pw.f16:
+        if keep_for_backward or opt.precision == "bf16":
+            raise RuntimeError("madeleine_b200: fp16 operand planes are the fp32-grade inference format (no backward state)")
+        ip[I['PLANES_F16']] = 1
     R2 = 0
     tok_idx = cu2 = row2seg2 = None
     if opt.views is not None:

@@ -626,6 +626,8 @@ def main():
                             "frac_bf16_issue": step_tf * issued / world / peaks["bf16_tflops_sustained"],
                             "note": "algorithmic FLOPs x bags/s over the sustained bf16 rate; x3 issued in the fp32-grade mode"}
     out["parity"] = parity
+    if world > 1:
+        out["small_collectives"] = parallel.PeerExchange.status()
     if timeline is not None:
         out["timeline"] = timeline
     if config3 is not None:

@@ -271,6 +271,20 @@ enum mdl_prof_tag {
 int mdl_profile_enable(int on);
 int mdl_profile_read(int* tags, float* ms, int max);
 
+/* ---- small exchanges over NVLink peer memory (case-sharded runs) -------------------------------------- */
+/* One-kernel all-reduce (sum) / all-gather of small fp32 messages over symmetric peer buffers, replacing NCCL where the
+ * message is latency-bound: the slide-embedding all-gather before the contrastive loss and the all-reduce of the 2 MB of
+ * gradients that only become final at the end of backward.  host_bufs / host_sigs: HOST arrays of `world` DEVICE pointers
+ * to every rank's symmetric buffer and uint32 signal pad (peer-mapped; this rank's own at [rank]).  The caller has put its
+ * contribution at buf[rank] + buf_off_bytes (stream-ordered before the call) and alternates between two buffer halves from
+ * call to call (epoch parity); `epoch` increases by one per call on a channel and is the same on every rank; slots
+ * [slot_base, slot_base + world) of the signal pad belong to the channel.  out: [n] (all-reduce, may alias nothing in the
+ * symmetric buffers) or [world * n_per_rank] rank-major (all-gather).  Sums are taken in rank order on every rank. */
+int mdl_peer_allreduce_f32(void* const* host_bufs, void* const* host_sigs, int rank, int world, long long buf_off_bytes, long long n,
+                           float* out, unsigned epoch, int slot_base, void* stream);
+int mdl_peer_allgather_f32(void* const* host_bufs, void* const* host_sigs, int rank, int world, long long buf_off_bytes,
+                           long long n_per_rank, float* out, unsigned epoch, int slot_base, void* stream);
+
 /* ---- optimiser (train-step caller) -------------------------------------------------------------- */
 /* Fused multi-tensor AdamW, one launch for all parameters (torch.optim.AdamW semantics; reference:
  * madeleine/utils/setup_components.py:194-196).  host_* are HOST arrays of n_tensors DEVICE pointers / element counts

@@ -80,6 +80,8 @@ SIGNATURES = {
     "mdl_encoder_bwd": [c_p, c_p, c_p],
     "mdl_permute_f32": [c_p, c_p, c_p, c_ll, c_p, c_p],
     "mdl_gram_f64": [c_p, c_ll, c_i, c_p, c_p],
+    "mdl_peer_allreduce_f32": [c_p, c_p, c_i, c_i, c_ll, c_ll, c_p, c_u, c_i, c_p],
+    "mdl_peer_allgather_f32": [c_p, c_p, c_i, c_i, c_ll, c_ll, c_p, c_u, c_i, c_p],
     "mdl_executor_launches": [c_i],
     "mdl_profile_enable": [c_i],
     "mdl_profile_read": [c_p, c_p, c_i],
@@ -137,7 +139,7 @@ LAUNCHES = {
     "mdl_ln_gelu_fwd": 1, "mdl_ln_gelu_bwd": 1, "mdl_gate_bwd": 1, "mdl_pool_weights": 1, "mdl_pool_fwd": 1, "mdl_pool_bwd_dlogit": 1,
     "mdl_planes_to_ref_order": 1, "mdl_skinny_linear_fwd": 1, "mdl_skinny_linear_bwd": 2, "mdl_stain_rowbias": 1,
     "mdl_bag_colsum_planes": 1, "mdl_gather_rows_planes": 1, "mdl_stain_rowbias_bwd": 1, "mdl_colsum_f32": 1, "mdl_infonce_fwd": 4, "mdl_infonce_bwd": 2, "mdl_infonce_rows_fwd": 4, "mdl_infonce_rows_bwd": 2,
-    "mdl_got_extrema": 2, "mdl_got_fwd_bwd": 2, "mdl_got_main": 2, "mdl_got_finish": 1, "mdl_adamw_step": 1, "mdl_sample_gather_f32": 1, "mdl_permute_f32": 1, "mdl_gram_f64": 1,
+    "mdl_got_extrema": 2, "mdl_got_fwd_bwd": 2, "mdl_got_main": 2, "mdl_got_finish": 1, "mdl_adamw_step": 1, "mdl_sample_gather_f32": 1, "mdl_permute_f32": 1, "mdl_gram_f64": 1, "mdl_peer_allreduce_f32": 1, "mdl_peer_allgather_f32": 1,
 }
 # mdl_encoder_fwd / mdl_encoder_bwd issue their launches natively; they are counted by the library (mdl_executor_launches)
 

@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libmadeleine_b200.so")
 STAMP = os.path.join(HERE, ".build_stamp")
-SOURCES = ["misc.cu", "gemm_tcgen05.cu", "gemm2_tcgen05.cu", "elementwise.cu", "pooling.cu", "skinny.cu", "infonce.cu", "got.cu", "got_big.cu", "optim.cu", "sampler.cu", "executor.cu"]
+SOURCES = ["misc.cu", "gemm_tcgen05.cu", "gemm2_tcgen05.cu", "elementwise.cu", "pooling.cu", "skinny.cu", "infonce.cu", "got.cu", "got_big.cu", "optim.cu", "sampler.cu", "executor.cu", "peer.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

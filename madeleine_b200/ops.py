@@ -538,10 +538,12 @@ class EncodeFn(torch.autograd.Function):
             _mark("bwd_begin")
             gmaster = encoder_backward(sv, d_slide, d_logits, d_tokens, d_ref, early_sync=early)
             _mark("bwd_kernels_done")
+            # the gradients that only became final now (first two layers, stain embedding: 2 MB) — latency-bound, nothing
+            # left to hide them under: one peer-memory kernel each instead of NCCL's protocol
             if spec.early_lo > 0:
-                dist.all_reduce(gmaster[:spec.early_lo], op=dist.ReduceOp.SUM)
+                parallel.small_all_reduce_(gmaster[:spec.early_lo])
             if spec.early_hi < spec.master_numel:
-                dist.all_reduce(gmaster[spec.early_hi:], op=dist.ReduceOp.SUM)
+                parallel.small_all_reduce_(gmaster[spec.early_hi:])
             _mark("late_allreduce_done")
             for work in pending:
                 work.wait()

@@ -182,6 +182,14 @@ ln_gelu_fwd_kernel(const void* __restrict__ z, int M, const float* __restrict__ 
     }
 }
 
+// cp.async (LDGSTS): 16 bytes global -> shared without passing through registers; completion tracked per thread in groups
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ---------------------------------------------------------------------------------------------------
 // LayerNorm + GELU (+dropout) backward.
 //   dh = dh_a + dh_b + sum_v p_v[m, head(c)] * dS_v[seg_v(m), c]     (the last term fuses the pooling backward)
@@ -208,7 +216,12 @@ struct PoolTerm {
 // row of token m (or -1): the token-projector gradient exists only for the token window the local loss can read.
 // BAGSUM: additionally accumulate per-bag column sums of dz into bag_dz[row2bag[m], c] (the stain-encoding backward needs
 // them); a thread flushes its bag accumulator only when the bag id changes.
-template <int C, int HAS_B, int NPOOL, bool BAGSUM, bool INBF16>
+// ASYNC (fp32 activations, no dense second gradient): the two row streams (z, dh_a) are staged by cp.async into a warp-private
+// double buffer one row ahead — every lane copies exactly the 2 x 64 bytes it will read itself, so there is no cross-lane
+// synchronisation, only cp.async.wait_group — instead of being requested into registers when they are needed (with an L2
+// prefetch two rows ahead).  The loads then overlap the previous row's arithmetic without holding 32 registers per thread.
+constexpr int LNB_ASYNC_STAGES = 2;
+template <int C, int HAS_B, int NPOOL, bool BAGSUM, bool INBF16, bool ASYNC>
 __global__ void __launch_bounds__(256, 2)
 ln_gelu_bwd_kernel(const void* __restrict__ z, int M, const float* __restrict__ gamma, const float* __restrict__ beta,
                    const float* __restrict__ mean, const float* __restrict__ rstd_in,
@@ -222,11 +235,13 @@ ln_gelu_bwd_kernel(const void* __restrict__ z, int M, const float* __restrict__ 
     constexpr int GROUPS = 8 / WPR;       // rows in flight per block
     __shared__ float red[2][GROUPS][2][WPR];
     __shared__ float colacc[3 * C];
+    extern __shared__ __align__(16) float lnb_stage[];        // ASYNC: [8 warps][LNB_ASYNC_STAGES][2 streams][512] floats
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int grp = warp / WPR, wq = warp % WPR;
     const int c0 = wq * 512 + lane * 4;                       // this lane's columns: c0 + 128 j + i
     const int cols_per_head = C / n_heads;
     for (int i = tid; i < 3 * C; i += 256) colacc[i] = 0.f;
+    float* my_stage = lnb_stage + (size_t)warp * (LNB_ASYNC_STAGES * 2 * 512) + lane * 4;
     float accg[16], accb[16], accz[16], accbag[BAGSUM ? 16 : 1];
 #pragma unroll
     for (int i = 0; i < 16; ++i) { accg[i] = 0.f; accb[i] = 0.f; accz[i] = 0.f; }
@@ -240,12 +255,32 @@ ln_gelu_bwd_kernel(const void* __restrict__ z, int M, const float* __restrict__ 
     const int row_begin = blockIdx.x * rows_per_block;
     const int row_end = min(M, row_begin + rows_per_block);
     const int iters = (rows_per_block + GROUPS - 1) / GROUPS;
+    auto stage_row = [&](int it_) {                            // ASYNC: request row `it_` of this warp into its stage (one group per row)
+        const int mm = row_begin + it_ * GROUPS + grp;
+        if (it_ < iters && mm < row_end) {
+            float* dst = my_stage + (it_ % LNB_ASYNC_STAGES) * (2 * 512);
+            const float* sz = reinterpret_cast<const float*>(z) + (size_t)mm * C + c0;
+            const float* sd = reinterpret_cast<const float*>(dh_a) + (size_t)mm * C + c0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                cp_async16(dst + 128 * j, sz + 128 * j);
+                cp_async16(dst + 512 + 128 * j, sd + 128 * j);
+            }
+        }
+        cp_async_commit();
+    };
+    if (ASYNC) {
+#pragma unroll
+        for (int f = 0; f < LNB_ASYNC_STAGES - 1; ++f) stage_row(f);
+    }
     for (int it = 0; it < iters; ++it) {
         const int m = row_begin + it * GROUPS + grp;
         const bool ok = m < row_end;
         const int mr = ok ? m : 0;                             // clamp; contributions of padded rows are zeroed below
         const size_t row_off = (size_t)mr * C + c0;
-        {   // pull the rows this warp will need two iterations from now into L2 (the kernel is latency-bound otherwise:
+        if (ASYNC) {
+            stage_row(it + LNB_ASYNC_STAGES - 1);               // the row after this one is in flight while this one is evaluated
+        } else {   // pull the rows this warp will need two iterations from now into L2 (the kernel is latency-bound otherwise:
             // 128 registers per thread leave 16 warps per SM to cover the HBM round trip)
             const int mp = m + 2 * GROUPS;
             if (mp < row_end) {
@@ -261,10 +296,20 @@ ln_gelu_bwd_kernel(const void* __restrict__ z, int M, const float* __restrict__ 
         float x[16], dx[16];                                    // xhat, then dy*gamma
         {
             float4 zv[4], dv[4];
+            if (ASYNC) {
+                cp_async_wait<LNB_ASYNC_STAGES - 1>();          // this row's group has landed (the newest one may still be in flight)
+                const float* src = my_stage + (it % LNB_ASYNC_STAGES) * (2 * 512);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                zv[j] = ld_act4<INBF16>(z, row_off + 128 * j);
-                dv[j] = ld_act4<INBF16>(dh_a, row_off + 128 * j);
+                for (int j = 0; j < 4; ++j) {
+                    zv[j] = ok ? *reinterpret_cast<const float4*>(src + 128 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    dv[j] = ok ? *reinterpret_cast<const float4*>(src + 512 + 128 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    zv[j] = ld_act4<INBF16>(z, row_off + 128 * j);
+                    dv[j] = ld_act4<INBF16>(dh_a, row_off + 128 * j);
+                }
             }
             if (HAS_B == 1) {
 #pragma unroll
@@ -714,13 +759,35 @@ int mdl_ln_gelu_fwd(const void* z, long long M, int C, const float* gamma, const
 
 }  // extern "C"
 
+// MDL_LN_BWD_ASYNC=0 selects the register-held loads for A/B measurements
+static const bool g_ln_bwd_async = [] { const char* e = getenv("MDL_LN_BWD_ASYNC"); return !(e && e[0] == '0'); }();
+
 template <int C, bool INBF16>
 static void launch_ln_bwd(int has_b, int npool, int grid, cudaStream_t st, const void* z, int M, const float* gamma, const float* beta,
                           const float* mean, const float* rstd, const void* dh_a, const void* dh_b, const int* dh_b_rows,
                           PoolTerm t0, PoolTerm t1, int n_heads,
                           float drop_p, unsigned long long seed, unsigned stream_id, __nv_bfloat16* dz, long long ps, int npl,
                           float* dgamma, float* dbeta, float* dbias, const int* row2bag, float* bag_dz) {
-#define MDL_LN_BWD(HB, NP, BS) ln_gelu_bwd_kernel<C, HB, NP, BS, INBF16><<<grid, 256, 0, st>>>(z, M, gamma, beta, mean, rstd, dh_a, dh_b, dh_b_rows, t0, t1, n_heads, drop_p, seed, stream_id, dz, ps, npl, dgamma, dbeta, dbias, row2bag, bag_dz)
+    // fp32 activations without a dense second gradient take the cp.async-staged variant (64 KB of dynamic shared memory)
+    constexpr int kStageBytes = 8 * LNB_ASYNC_STAGES * 2 * 512 * 4;
+#define MDL_LN_BWD(HB, NP, BS)                                                                                                          \
+    do {                                                                                                                                \
+        if (!INBF16 && (HB) != 1 && g_ln_bwd_async) {                                                                                   \
+            auto kern = ln_gelu_bwd_kernel<C, HB, NP, BS, INBF16, !INBF16 && (HB) != 1>;                                                \
+            static PerDeviceOnce attr_set;                                                                                              \
+            unsigned long long dev_bit;                                                                                                 \
+            if (attr_set.needed(dev_bit)) {                                                                                             \
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes);                                   \
+                attr_set.mark(dev_bit);                                                                                                 \
+            }                                                                                                                           \
+            kern<<<grid, 256, kStageBytes, st>>>(z, M, gamma, beta, mean, rstd, dh_a, dh_b, dh_b_rows, t0, t1, n_heads, drop_p, seed,   \
+                                                 stream_id, dz, ps, npl, dgamma, dbeta, dbias, row2bag, bag_dz);                        \
+        } else {                                                                                                                        \
+            ln_gelu_bwd_kernel<C, HB, NP, BS, INBF16, false><<<grid, 256, 0, st>>>(z, M, gamma, beta, mean, rstd, dh_a, dh_b, dh_b_rows, \
+                                                                                  t0, t1, n_heads, drop_p, seed, stream_id, dz, ps,    \
+                                                                                  npl, dgamma, dbeta, dbias, row2bag, bag_dz);          \
+        }                                                                                                                               \
+    } while (0)
     if constexpr (C == 512) {
         if (bag_dz != nullptr) { MDL_LN_BWD(0, 0, true); return; }   // only the first layer (no second gradient, no pooling term)
     }

@@ -132,6 +132,7 @@ infonce_grads_kernel(Rows q, Rows k, const float* __restrict__ qn, const float* 
     const float self_n = is_q ? qn[a] : kn[a];
     for (int t = threadIdx.x; t < m; t += blockDim.x)
         gs[t] = (is_q ? __ldg(G + (long long)a * m + t) : __ldg(G + (long long)t * m + a)) * __ldg(other_n + t);
+    if (threadIdx.x < 8) gs[m + threadIdx.x] = 0.f;           // padding behind the coefficients (see the launch)
     __syncthreads();
     float dot = 0.f;
     float acc[INFONCE_MAX_U];
@@ -202,7 +203,8 @@ static int infonce_bwd_impl(Rows q, Rows k, int m, int D, float temperature, con
     if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
     infonce_dlogits_kernel<<<blocks, 256, 0, st>>>(L, lse_r, lse_c, w_r, w_c, m, inv_tau, G, go, wr_const, wc_const);
     MDL_CHECK_LAUNCH();
-    infonce_grads_kernel<<<2 * m, 128, m * sizeof(float), st>>>(q, k, qn, kn, G, m, D, dq, dk, accumulate);
+    // + 8 floats: the unrolled dot-product loop may load a few coefficients past m (speculatively, never used)
+    infonce_grads_kernel<<<2 * m, 128, (m + 8) * sizeof(float), st>>>(q, k, qn, kn, G, m, D, dq, dk, accumulate);
     MDL_CHECK_LAUNCH();
     return 0;
 }

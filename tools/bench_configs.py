@@ -73,28 +73,41 @@ def config3(precision, steps, warmup, skip=True, bs=32, tag="BASELINE configs[2]
 
 
 def config5(precision, n_slides, n_tokens):
-    dev = torch.device("cuda")
+    """BASELINE configs[4].  Under torchrun every rank is a replica that extracts its stride of the slides (no collective on
+    the data path); the job's throughput is n_slides over the slowest rank's time."""
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
     model = MADELEINE(cfg(["HE"], precision), stain_encoding=False)
     model.load_state_dict(make_state_dict(0))
     model.to(dev).eval()
     g = torch.Generator().manual_seed(1)
     base = torch.randn(n_tokens + 64, 512, generator=g)
     bags = [base[(i % 64):(i % 64) + n_tokens] for i in range(n_slides)]   # distinct views, no 8 GB of host RAM
-    extract_slide_embeddings(model, bags[:96], dev)                        # warm-up: three batches, both staging slots
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    emb, idx = extract_slide_embeddings(model, bags, dev)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+
+    def timed(inputs):
+        extract_slide_embeddings(model, inputs[:96], dev)                  # warm-up: three batches, both staging slots
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        emb, idx = extract_slide_embeddings(model, inputs, dev, rank=rank, world=world)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return float(dt), emb
+
+    dt, emb = timed(bags)
     # the same slides delivered in pinned memory (DataLoader(pin_memory=True)): no host-side staging copy
     pbase = base.pin_memory()
     pbags = [pbase[(i % 64):(i % 64) + n_tokens] for i in range(n_slides)]
-    extract_slide_embeddings(model, pbags[:96], dev)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    emb_p, _ = extract_slide_embeddings(model, pbags, dev)
-    torch.cuda.synchronize()
-    dt_pinned = time.perf_counter() - t0
+    dt_pinned, emb_p = timed(pbags)
     assert abs(float(abs(emb_p).sum()) - float(abs(emb).sum())) < 1e-3 * float(abs(emb).sum())
     # device-resident forward only (no H2D), same packing
     x = torch.randn(32 * n_tokens, 512, device=dev)
@@ -109,12 +122,18 @@ def config5(precision, n_slides, n_tokens):
             model.encode_packed(x, cu)
         e1.record()
         torch.cuda.synchronize()
-    dev_ms = e0.elapsed_time(e1) / 10
-    print(json.dumps({"config": f"BASELINE configs[4]: inference, {n_slides} slides x {n_tokens} x 512, extraction driver (host->device->host)",
-                      "precision": precision, "e2e_slides_per_s": n_slides / dt, "e2e_seconds": dt,
-                      "e2e_slides_per_s_pinned_inputs": n_slides / dt_pinned,
-                      "device_resident_slides_per_s": 32 / (dev_ms * 1e-3), "h2d_bytes_per_slide": n_tokens * 512 * 4,
-                      "embedding_checksum": float(abs(emb).sum())}))
+    dev_ms = torch.tensor([e0.elapsed_time(e1) / 10], device=dev)
+    if world > 1:
+        dist.all_reduce(dev_ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps({"config": f"BASELINE configs[4]: inference, {n_slides} slides x {n_tokens} x 512, extraction driver (host->device->host)",
+                          "n_gpus": world, "replicas": "rank-strided slides, no data-path collective", "precision": precision,
+                          "e2e_slides_per_s": n_slides / dt, "e2e_seconds": dt,
+                          "e2e_slides_per_s_pinned_inputs": n_slides / dt_pinned,
+                          "device_resident_slides_per_s": world * 32 / (float(dev_ms) * 1e-3), "h2d_bytes_per_slide": n_tokens * 512 * 4,
+                          "embedding_checksum_rank0": float(abs(emb).sum())}))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def resident_loader(precision, steps, bs=65, n_cases=130, token_window="batch"):

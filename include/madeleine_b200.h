@@ -271,6 +271,10 @@ enum mdl_prof_tag {
 int mdl_profile_enable(int on);
 int mdl_profile_read(int* tags, float* ms, int max);
 
+/* Programmatic dependent launch of the hot-path kernels (csrc/common.cuh::launch_k): on by default, MADELEINE_B200_PDL=0 or
+ * mdl_set_pdl(0) restores plain stream-ordered launches (same results; used for A/B timing).  Returns the previous setting. */
+int mdl_set_pdl(int on);
+
 /* ---- small exchanges over NVLink peer memory (case-sharded runs) -------------------------------------- */
 /* One-kernel all-reduce (sum) / all-gather of small fp32 messages over symmetric peer buffers, replacing NCCL where the
  * message is latency-bound: the slide-embedding all-gather before the contrastive loss and the all-reduce of the 2 MB of

@@ -85,13 +85,14 @@ SIGNATURES = {
     "mdl_executor_launches": [c_i],
     "mdl_profile_enable": [c_i],
     "mdl_profile_read": [c_p, c_p, c_i],
+    "mdl_set_pdl": [c_i],
 }
 _RESTYPES = {"mdl_got_workspace_bytes": c_ll, "mdl_pool_workspace_bytes": c_ll, "mdl_encoder_fwd_arena_bytes": c_ll,
              "mdl_encoder_bwd_arena_bytes": c_ll, "mdl_executor_launches": c_ll, "mdl_infonce_rows_workspace_floats": c_ll}
 # functions that return a value rather than a status code
 _VALUE_FUNCS = {"mdl_version", "mdl_built_arch", "mdl_got_workspace_bytes", "mdl_got_max_tokens", "mdl_pool_tsplit",
                 "mdl_pool_workspace_bytes", "mdl_adamw_max_tensors", "mdl_encoder_abi", "mdl_encoder_fwd_arena_bytes",
-                "mdl_encoder_bwd_arena_bytes", "mdl_executor_launches", "mdl_profile_enable", "mdl_profile_read",
+                "mdl_encoder_bwd_arena_bytes", "mdl_executor_launches", "mdl_profile_enable", "mdl_profile_read", "mdl_set_pdl",
                 "mdl_infonce_rows_workspace_floats"}
 
 

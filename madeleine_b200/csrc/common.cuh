@@ -37,6 +37,38 @@ const char* get_last_error();
 
 #define MDL_CHECK_LAUNCH() MDL_CHECK_CUDA(cudaGetLastError())
 
+// ---------------------------------------------------------------------------------------------------
+// programmatic dependent launch
+// ---------------------------------------------------------------------------------------------------
+// Every kernel of the hot path starts with pdl_sync() and is launched through launch_k().  With the launch attribute set
+// (MADELEINE_B200_PDL, default on) a kernel's blocks may become resident while the previous kernel of the stream is still
+// draining: block scheduling, the launch latency and everything in front of pdl_sync() (barrier initialisation, TMEM allocation,
+// tensor-map prefetch in the GEMMs) overlap the predecessor's tail; griddepcontrol.wait then blocks until the predecessor
+// grid has completed and its writes are visible, so no kernel touches memory earlier than it would in plain stream order.
+// launch_dependents follows the wait immediately: at most two kernels of a stream are in flight, and because every kernel
+// of the chain waits before it signals, "my predecessor completed" implies "everything before it completed".  Kernels launched
+// without the attribute (torch's, NCCL's, the <<< >>> launches that remain) keep full stream semantics on both sides.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_wait(); pdl_trigger(); }
+
+bool pdl_enabled();        // misc.cu: MADELEINE_B200_PDL != "0", read once; mdl_set_pdl() overrides
+
+template <typename... P, typename... A>
+inline cudaError_t launch_k(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...);
+}
+
 // Function attributes (opt-in dynamic shared memory) belong to a device, not to the process: a host that drives several
 // GPUs from one process (nn.DataParallel replicas, one thread per GPU) must set them on each.  One bit per device ordinal;
 // setting an attribute twice from racing threads is harmless.

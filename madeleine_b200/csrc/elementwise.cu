@@ -29,6 +29,7 @@ static inline int grid_for(long long work_items, int per_block, int max_blocks_p
 template <bool F16>
 __global__ void split_planes_kernel(const float* __restrict__ x, long long rows, int cols, long long ld,
                                     __nv_bfloat16* __restrict__ planes, long long plane_stride, int nplanes) {
+    pdl_sync();
     const int vec_per_row = cols >> 2;
     const long long total = rows * vec_per_row;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -49,6 +50,7 @@ __global__ void split_planes_kernel(const float* __restrict__ x, long long rows,
 template <bool F16>
 __global__ void gather_split_kernel(const float* __restrict__ src, const int* __restrict__ idx, long long n,
                                     __nv_bfloat16* __restrict__ planes, long long plane_stride, int nplanes) {
+    pdl_sync();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float w = __ldg(src + __ldg(idx + i));
         if (F16) {
@@ -66,11 +68,13 @@ __global__ void gather_split_kernel(const float* __restrict__ src, const int* __
     }
 }
 __global__ void gather_f32_kernel(const float* __restrict__ src, const int* __restrict__ idx, long long n, float* __restrict__ dst) {
+    pdl_sync();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         dst[i] = __ldg(src + __ldg(idx + i));
 }
 // dst[idx[i]] (+)= src[i]; idx is injective so there are no write conflicts.
 __global__ void scatter_f32_kernel(const float* __restrict__ src, const int* __restrict__ idx, long long n, float* __restrict__ dst, int accumulate) {
+    pdl_sync();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int j = __ldg(idx + i);
         dst[j] = accumulate ? dst[j] + src[i] : src[i];
@@ -78,6 +82,7 @@ __global__ void scatter_f32_kernel(const float* __restrict__ src, const int* __r
 }
 
 __global__ void row2bag_kernel(const int* __restrict__ cu, int n_bags, int* __restrict__ row2bag, long long rows) {
+    pdl_sync();
     for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < rows; m += (long long)gridDim.x * blockDim.x) {
         int lo = 0, hi = n_bags;  // find bag with cu[bag] <= m < cu[bag+1]
         while (hi - lo > 1) {
@@ -115,6 +120,7 @@ ln_gelu_fwd_kernel(const void* __restrict__ z, int M, const float* __restrict__ 
                    float eps, float drop_p, unsigned long long seed, unsigned stream_id,
                    __nv_bfloat16* __restrict__ planes, long long plane_stride, int nplanes,
                    float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+    pdl_sync();
     constexpr int V = C / 128;            // float4 per lane per row
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int warps_total = gridDim.x * 8;
@@ -231,6 +237,7 @@ ln_gelu_bwd_kernel(const void* __restrict__ z, int M, const float* __restrict__ 
                    __nv_bfloat16* __restrict__ dz_planes, long long plane_stride, int nplanes,
                    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
                    const int* __restrict__ row2bag, float* __restrict__ bag_dz) {
+    pdl_sync();
     constexpr int WPR = C / 512;          // warps per row
     constexpr int GROUPS = 8 / WPR;       // rows in flight per block
     __shared__ float red[2][GROUPS][2][WPR];
@@ -477,6 +484,7 @@ gate_bwd_kernel(const __half* __restrict__ gate_a, const __half* __restrict__ ga
                 const float* __restrict__ wc, long long M, int n_heads, float drop_p,
                 __nv_bfloat16* __restrict__ dpre, long long plane_stride,
                 float* __restrict__ dba, float* __restrict__ dbb, float* __restrict__ dwc, float* __restrict__ dbc) {
+    pdl_sync();
     __shared__ __align__(16) __nv_bfloat16 stage[2][NPL][2][32][GB_PITCH];     // double-buffered: one barrier per row block
     const int HC = n_heads * 512;
     const int groups = HC / GB_COLS;
@@ -608,6 +616,7 @@ gate_bwd_kernel(const __half* __restrict__ gate_a, const __half* __restrict__ ga
 __global__ void __launch_bounds__(256)
 gather_rows_planes_kernel(const __nv_bfloat16* __restrict__ planes, long long plane_stride_in, int nplanes, int C,
                           const int* __restrict__ rows, long long n_sel, __nv_bfloat16* __restrict__ out, long long plane_stride_out) {
+    pdl_sync();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int vec = C >> 3;                                   // uint4 per row
     for (long long s = (long long)blockIdx.x * 8 + warp; s < n_sel * nplanes; s += (long long)gridDim.x * 8) {
@@ -623,6 +632,7 @@ gather_rows_planes_kernel(const __nv_bfloat16* __restrict__ planes, long long pl
 __global__ void __launch_bounds__(128)
 bag_colsum_planes_kernel(const __nv_bfloat16* __restrict__ planes, long long plane_stride, int nplanes, int C,
                          const int* __restrict__ cu, float* __restrict__ out) {
+    pdl_sync();
     const int bag = blockIdx.y;
     const int c = blockIdx.x * 128 + threadIdx.x;
     if (c >= C) return;
@@ -639,6 +649,7 @@ bag_colsum_planes_kernel(const __nv_bfloat16* __restrict__ planes, long long pla
 // rowbias[r, n] = sum_s emb[code[r], s] * W1[n, d_in + s]   (stain encodings folded into a per-bag bias)
 __global__ void stain_rowbias_kernel(const float* __restrict__ emb, const int* __restrict__ code, const float* __restrict__ w1,
                                      int ldw, int d_in, int se_dim, int n_out, float* __restrict__ rowbias) {
+    pdl_sync();
     const int r = blockIdx.x;
     const float* e = emb + (long long)code[r] * se_dim;
     for (int n = threadIdx.x; n < n_out; n += blockDim.x) {
@@ -652,6 +663,7 @@ __global__ void stain_rowbias_kernel(const float* __restrict__ emb, const int* _
 __global__ void stain_rowbias_bwd_kernel(const float* __restrict__ G, const float* __restrict__ emb, const int* __restrict__ code,
                                          const float* __restrict__ w1, int ldw, int d_in, int se_dim, int n_out, int R,
                                          float* __restrict__ dw1, float* __restrict__ demb) {
+    pdl_sync();
     // grid.x = n_out blocks for dW1 rows, then R blocks for demb rows
     const int bid = blockIdx.x;
     if (bid < n_out) {
@@ -673,6 +685,7 @@ __global__ void stain_rowbias_bwd_kernel(const float* __restrict__ G, const floa
 
 // out[c] (+)= sum_m x[m, c]  for a small fp32 matrix (bias grads of the skinny projections).
 __global__ void colsum_f32_kernel(const float* __restrict__ x, long long M, int C, float* __restrict__ out) {
+    pdl_sync();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     float s = 0.f;
@@ -692,8 +705,8 @@ int mdl_split_planes(const float* x, long long rows, int cols, long long ld, voi
     const long long total = rows * (cols / 4);
     const bool f16 = (nplanes & kPlanesF16) != 0;
     nplanes &= 0xff;
-    if (f16) split_planes_kernel<true><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ld, (__nv_bfloat16*)planes, plane_stride, nplanes);
-    else split_planes_kernel<false><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ld, (__nv_bfloat16*)planes, plane_stride, nplanes);
+    if (f16) launch_k(split_planes_kernel<true>, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, x, rows, cols, ld, (__nv_bfloat16*)planes, plane_stride, nplanes);
+    else launch_k(split_planes_kernel<false>, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, x, rows, cols, ld, (__nv_bfloat16*)planes, plane_stride, nplanes);
     MDL_CHECK_LAUNCH();
     return 0;
 }
@@ -702,29 +715,29 @@ int mdl_gather_split(const float* src, const int* idx, long long n, void* planes
     if (n == 0) return 0;
     const bool f16 = (nplanes & kPlanesF16) != 0;
     nplanes &= 0xff;
-    if (f16) gather_split_kernel<true><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, idx, n, (__nv_bfloat16*)planes, plane_stride, nplanes);
-    else gather_split_kernel<false><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, idx, n, (__nv_bfloat16*)planes, plane_stride, nplanes);
+    if (f16) launch_k(gather_split_kernel<true>, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, src, idx, n, (__nv_bfloat16*)planes, plane_stride, nplanes);
+    else launch_k(gather_split_kernel<false>, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, src, idx, n, (__nv_bfloat16*)planes, plane_stride, nplanes);
     MDL_CHECK_LAUNCH();
     return 0;
 }
 
 int mdl_gather_f32(const float* src, const int* idx, long long n, float* dst, void* stream) {
     if (n == 0) return 0;
-    gather_f32_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, idx, n, dst);
+    launch_k(gather_f32_kernel, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, src, idx, n, dst);
     MDL_CHECK_LAUNCH();
     return 0;
 }
 
 int mdl_scatter_f32(const float* src, const int* idx, long long n, float* dst, int accumulate, void* stream) {
     if (n == 0) return 0;
-    scatter_f32_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, idx, n, dst, accumulate);
+    launch_k(scatter_f32_kernel, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, src, idx, n, dst, accumulate);
     MDL_CHECK_LAUNCH();
     return 0;
 }
 
 int mdl_row2bag(const int* cu_seqlens, int n_bags, int* row2bag, long long rows, void* stream) {
     if (rows == 0) return 0;
-    row2bag_kernel<<<grid_for(rows, 256), 256, 0, (cudaStream_t)stream>>>(cu_seqlens, n_bags, row2bag, rows);
+    launch_k(row2bag_kernel, dim3(grid_for(rows, 256)), dim3(256), 0, (cudaStream_t)stream, cu_seqlens, n_bags, row2bag, rows);
     MDL_CHECK_LAUNCH();
     return 0;
 }
@@ -741,9 +754,9 @@ int mdl_ln_gelu_fwd(const void* z, long long M, int C, const float* gamma, const
     MDL_REQUIRE(!(f16 && z_bf16), "ln_gelu_fwd: fp16 planes are the fp32-grade inference format (z must be fp32)");
 #define MDL_LNF(CC, RPW, grid) \
     do { \
-        if (z_bf16) ln_gelu_fwd_kernel<CC, RPW, true, false><<<grid, 256, 0, st>>>(z, (int)M, gamma, beta, eps, drop_p, seed, stream_id, (__nv_bfloat16*)planes, plane_stride, nplanes, mean, rstd); \
-        else if (f16) ln_gelu_fwd_kernel<CC, RPW, false, true><<<grid, 256, 0, st>>>(z, (int)M, gamma, beta, eps, drop_p, seed, stream_id, (__nv_bfloat16*)planes, plane_stride, nplanes, mean, rstd); \
-        else ln_gelu_fwd_kernel<CC, RPW, false, false><<<grid, 256, 0, st>>>(z, (int)M, gamma, beta, eps, drop_p, seed, stream_id, (__nv_bfloat16*)planes, plane_stride, nplanes, mean, rstd); \
+        if (z_bf16) launch_k(ln_gelu_fwd_kernel<CC, RPW, true, false>, dim3(grid), dim3(256), 0, st, z, (int)M, gamma, beta, eps, drop_p, seed, stream_id, (__nv_bfloat16*)planes, plane_stride, nplanes, mean, rstd); \
+        else if (f16) launch_k(ln_gelu_fwd_kernel<CC, RPW, false, true>, dim3(grid), dim3(256), 0, st, z, (int)M, gamma, beta, eps, drop_p, seed, stream_id, (__nv_bfloat16*)planes, plane_stride, nplanes, mean, rstd); \
+        else launch_k(ln_gelu_fwd_kernel<CC, RPW, false, false>, dim3(grid), dim3(256), 0, st, z, (int)M, gamma, beta, eps, drop_p, seed, stream_id, (__nv_bfloat16*)planes, plane_stride, nplanes, mean, rstd); \
     } while (0)
     if (C == 512) {
         const int grid = grid_for(M, 8 * 2, 6);
@@ -780,10 +793,10 @@ static void launch_ln_bwd(int has_b, int npool, int grid, cudaStream_t st, const
                 cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes);                                   \
                 attr_set.mark(dev_bit);                                                                                                 \
             }                                                                                                                           \
-            kern<<<grid, 256, kStageBytes, st>>>(z, M, gamma, beta, mean, rstd, dh_a, dh_b, dh_b_rows, t0, t1, n_heads, drop_p, seed,   \
+            launch_k(kern, dim3(grid), dim3(256), kStageBytes, st, z, M, gamma, beta, mean, rstd, dh_a, dh_b, dh_b_rows, t0, t1, n_heads, drop_p, seed,   \
                                                  stream_id, dz, ps, npl, dgamma, dbeta, dbias, row2bag, bag_dz);                        \
         } else {                                                                                                                        \
-            ln_gelu_bwd_kernel<C, HB, NP, BS, INBF16, false><<<grid, 256, 0, st>>>(z, M, gamma, beta, mean, rstd, dh_a, dh_b, dh_b_rows, \
+            launch_k(ln_gelu_bwd_kernel<C, HB, NP, BS, INBF16, false>, dim3(grid), dim3(256), 0, st, z, M, gamma, beta, mean, rstd, dh_a, dh_b, dh_b_rows, \
                                                                                   t0, t1, n_heads, drop_p, seed, stream_id, dz, ps,    \
                                                                                   npl, dgamma, dbeta, dbias, row2bag, bag_dz);          \
         }                                                                                                                               \
@@ -857,10 +870,10 @@ int mdl_gate_bwd(const void* gate_a, const void* gate_b, const float* dlogit, co
     if (chunks < 1) chunks = 1;
     const int grid = (int)(chunks * groups);
     if (nplanes > 1)
-        gate_bwd_kernel<2><<<grid, GB_THREADS, 0, (cudaStream_t)stream>>>((const __half*)gate_a, (const __half*)gate_b, dlogit, wc, M, n_heads, drop_p,
+        launch_k(gate_bwd_kernel<2>, dim3(grid), dim3(GB_THREADS), 0, (cudaStream_t)stream, (const __half*)gate_a, (const __half*)gate_b, dlogit, wc, M, n_heads, drop_p,
                                                                   (__nv_bfloat16*)dpre_planes, plane_stride, dba, dbb, dwc, dbc);
     else
-        gate_bwd_kernel<1><<<grid, GB_THREADS, 0, (cudaStream_t)stream>>>((const __half*)gate_a, (const __half*)gate_b, dlogit, wc, M, n_heads, drop_p,
+        launch_k(gate_bwd_kernel<1>, dim3(grid), dim3(GB_THREADS), 0, (cudaStream_t)stream, (const __half*)gate_a, (const __half*)gate_b, dlogit, wc, M, n_heads, drop_p,
                                                                   (__nv_bfloat16*)dpre_planes, plane_stride, dba, dbb, dwc, dbc);
     MDL_CHECK_LAUNCH();
     return 0;
@@ -871,7 +884,7 @@ int mdl_gather_rows_planes(const void* planes, long long plane_stride_in, int np
     nplanes &= 0xff;      // a byte copy: the plane format flag does not matter
     MDL_REQUIRE(C % 8 == 0, "gather_rows_planes: C must be a multiple of 8 (got %d)", C);
     if (n_sel == 0) return 0;
-    gather_rows_planes_kernel<<<grid_for(n_sel * nplanes, 8, 8), 256, 0, (cudaStream_t)stream>>>(
+    launch_k(gather_rows_planes_kernel, dim3(grid_for(n_sel * nplanes, 8, 8)), dim3(256), 0, (cudaStream_t)stream, 
         (const __nv_bfloat16*)planes, plane_stride_in, nplanes, C, rows, n_sel, (__nv_bfloat16*)out, plane_stride_out);
     MDL_CHECK_LAUNCH();
     return 0;
@@ -880,14 +893,14 @@ int mdl_gather_rows_planes(const void* planes, long long plane_stride_in, int np
 int mdl_bag_colsum_planes(const void* planes, long long plane_stride, int nplanes, int C, const int* cu_seqlens, int n_bags, float* out, void* stream) {
     if (n_bags == 0) return 0;
     dim3 grid((C + 127) / 128, n_bags);
-    bag_colsum_planes_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)planes, plane_stride, nplanes, C, cu_seqlens, out);
+    launch_k(bag_colsum_planes_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, (const __nv_bfloat16*)planes, plane_stride, nplanes, C, cu_seqlens, out);
     MDL_CHECK_LAUNCH();
     return 0;
 }
 
 int mdl_stain_rowbias(const float* emb, const int* code, const float* w1, int ldw, int d_in, int se_dim, int n_out, int R, float* rowbias, void* stream) {
     if (R == 0) return 0;
-    stain_rowbias_kernel<<<R, 256, 0, (cudaStream_t)stream>>>(emb, code, w1, ldw, d_in, se_dim, n_out, rowbias);
+    launch_k(stain_rowbias_kernel, dim3(R), dim3(256), 0, (cudaStream_t)stream, emb, code, w1, ldw, d_in, se_dim, n_out, rowbias);
     MDL_CHECK_LAUNCH();
     return 0;
 }
@@ -895,7 +908,7 @@ int mdl_stain_rowbias(const float* emb, const int* code, const float* w1, int ld
 int mdl_stain_rowbias_bwd(const float* G, const float* emb, const int* code, const float* w1, int ldw, int d_in, int se_dim, int n_out, int R,
                           float* dw1, float* demb, void* stream) {
     if (R == 0) return 0;
-    stain_rowbias_bwd_kernel<<<n_out + R, 32, 0, (cudaStream_t)stream>>>(G, emb, code, w1, ldw, d_in, se_dim, n_out, R, dw1, demb);
+    launch_k(stain_rowbias_bwd_kernel, dim3(n_out + R), dim3(32), 0, (cudaStream_t)stream, G, emb, code, w1, ldw, d_in, se_dim, n_out, R, dw1, demb);
     MDL_CHECK_LAUNCH();
     return 0;
 }
@@ -904,7 +917,7 @@ int mdl_colsum_f32(const float* x, long long M, int C, float* out, void* stream)
     if (M == 0) return 0;
     const long long want = (M + 63) / 64, cap = 4LL * kNumSMs / ((C + 127) / 128) + 1;   // ~4 blocks per SM in total
     dim3 grid((C + 127) / 128, (unsigned)(want > cap ? cap : want));
-    colsum_f32_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x, M, C, out);
+    launch_k(colsum_f32_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, x, M, C, out);
     MDL_CHECK_LAUNCH();
     return 0;
 }

@@ -17,6 +17,7 @@ namespace mdl {
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void permute_f32_kernel(const float* __restrict__ src, const int* __restrict__ pos, const int* __restrict__ dst,
                                    long long n, float* __restrict__ out) {
+    pdl_sync();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[dst[i]] = __ldg(src + pos[i]);
 }
@@ -24,12 +25,14 @@ __global__ void permute_f32_kernel(const float* __restrict__ src, const int* __r
 // y += x over n elements (fp32 or bf16 storage): the rare "gradient through the pre-attention features AND token_projector" case
 template <typename T>
 __global__ void add_inplace_kernel(T* __restrict__ y, const T* __restrict__ x, long long n) {
+    pdl_sync();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] = (T)((float)y[i] + (float)x[i]);
 }
 
 // dst[r, c] += src[c, r]   (dst [rows, cols] row-major, src [cols, rows]); first-layer wgrad of widths that are 128- but not 256-aligned
 __global__ void add_transposed_kernel(float* __restrict__ dst, const float* __restrict__ src, int rows, int cols) {
+    pdl_sync();
     __shared__ float tile[32][33];
     const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -48,6 +51,7 @@ __global__ void add_transposed_kernel(float* __restrict__ dst, const float* __re
 // the square roots of this matrix's eigenvalues, so the [n, 512] embedding matrix never leaves the device.
 __global__ void __launch_bounds__(1024)
 gram_f64_kernel(const float* __restrict__ E, long long n, int D, double* __restrict__ G) {
+    pdl_sync();
     const int ti = blockIdx.y, tj = blockIdx.x;
     if (tj < ti) return;
     __shared__ float a[32][33], b[32][33];
@@ -403,8 +407,8 @@ static int run_bwd(const Desc& d, bool dry, size_t* bytes_out) {
             } else if (!dry) {
                 const long long n = M * C;
                 const int blocks = (int)((n + 255) / 256);
-                if (d.act_bf16) add_inplace_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((__nv_bfloat16*)dh3_tok, (const __nv_bfloat16*)d_ref, n);
-                else add_inplace_kernel<float><<<blocks, 256, 0, st>>>((float*)dh3_tok, (const float*)d_ref, n);
+                if (d.act_bf16) launch_k(add_inplace_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, (__nv_bfloat16*)dh3_tok, (const __nv_bfloat16*)d_ref, n);
+                else launch_k(add_inplace_kernel<float>, dim3(blocks), dim3(256), 0, st, (float*)dh3_tok, (const float*)d_ref, n);
                 MDL_CHECK_LAUNCH();
             }
         }
@@ -451,7 +455,7 @@ static int run_bwd(const Desc& d, bool dry, size_t* bytes_out) {
                                                     0, 0, 0, stv));
             if (!dry) {
                 dim3 grid((d.d_in + 31) / 32, (HID + 31) / 32), block(32, 8);
-                add_transposed_kernel<<<grid, block, 0, st>>>(g(MDL_ENC_I_GR_W1), w1t, HID, d.d_in);
+                launch_k(add_transposed_kernel, dim3(grid), dim3(block), 0, st, g(MDL_ENC_I_GR_W1), w1t, HID, d.d_in);
                 MDL_CHECK_LAUNCH();
             }
         }
@@ -517,7 +521,7 @@ int mdl_encoder_bwd(const long long* ip, const double* fp, void* const* pp) {
 
 int mdl_permute_f32(const float* src, const int* pos, const int* dst, long long n, float* out, void* stream) {
     if (n <= 0) return 0;
-    permute_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, pos, dst, n, out);
+    launch_k(permute_f32_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, src, pos, dst, n, out);
     MDL_CHECK_LAUNCH();
     return 0;
 }
@@ -525,7 +529,7 @@ int mdl_permute_f32(const float* src, const int* pos, const int* dst, long long 
 int mdl_gram_f64(const float* E, long long n, int D, double* G, void* stream) {
     MDL_REQUIRE(E && G && n > 0 && D > 0, "gram: empty input");
     dim3 grid((D + 31) / 32, (D + 31) / 32);
-    gram_f64_kernel<<<grid, 1024, 0, (cudaStream_t)stream>>>(E, n, D, G);
+    launch_k(gram_f64_kernel, dim3(grid), dim3(1024), 0, (cudaStream_t)stream, E, n, D, G);
     MDL_CHECK_LAUNCH();
     return 0;
 }

@@ -94,6 +94,7 @@ gemm2_kf_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
+    pdl_wait();      // everything above (barrier init, TMEM allocation, tensor-map prefetch) overlaps the previous kernel's tail
     float* aux = reinterpret_cast<float*>(smem_raw + (smem_base + L::AUX_OFFSET - smem_u32(smem_raw)));
     if constexpr (EPI == EPI_GATED) {
         const int hc = p.n_heads * 512;
@@ -115,8 +116,11 @@ gemm2_kf_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int num_units = p.num_m_tiles * n_groups * p.ksplit;     // m tiles of 256 rows
     const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
     auto decode = [&](int unit, int& m_tile, int& n_group, int& kb0, int& kb1) {
-        const int ks = unit % p.ksplit;
-        const int mn = unit / p.ksplit;
+        // output tile fastest, k-range slowest: the CTAs (pairs) of one round sweep the SAME token range for different output
+        // tiles, so a split-K wgrad fetches every operand row from HBM once and shares it through L2
+        const int mn_count = p.num_m_tiles * n_groups;
+        const int mn = unit % mn_count;
+        const int ks = unit / mn_count;
         n_group = mn % n_groups;
         m_tile = mn / n_groups;
         const int per = (p.k_blocks + p.ksplit - 1) / p.ksplit;
@@ -243,6 +247,9 @@ gemm2_kf_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             }
             unit_parity ^= 1;
         }
+        // A persistent GEMM is one wave from the start: signalling the dependent kernel at the top would park its blocks next to
+        // ours for the whole run (measured: 1 % slower steps).  Signal when this CTA's last tile has been drained instead.
+        if (warp == 2 && lane == 0) pdl_trigger();
     }
 
     tc_fence_before();
@@ -270,7 +277,7 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs&
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int pairs = sms / 2;
     if (units < pairs) pairs = units;
-    kern<<<2 * pairs, GEMM_THREADS, Smem2::TOTAL, stream>>>(ta, tb, args);
+    launch_k(kern, dim3(2 * pairs), dim3(GEMM_THREADS), Smem2::TOTAL, stream, ta, tb, args);
     MDL_CHECK_LAUNCH();
     return 0;
 }

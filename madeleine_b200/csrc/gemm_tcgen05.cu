@@ -58,6 +58,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tmem_alloc(tmem_ptr_addr, TMEM_COLS);
         tmem_relinquish();
     }
+    pdl_wait();      // everything above (barrier init, TMEM allocation, tensor-map prefetch) overlaps the previous kernel's tail
     float* aux = reinterpret_cast<float*>(smem_raw + (smem_base + L::AUX_OFFSET - smem_u32(smem_raw)));
     if constexpr (EPI == EPI_GATED) {
         const int hc = p.n_heads * 512;   // <= 2048
@@ -76,8 +77,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
     // unit -> (m_tile, n_group, k range). n_group varies fastest so CTAs running concurrently share the A tile in L2.
     auto decode = [&](int unit, int& m_tile, int& n_group, int& kb0, int& kb1) {
-        const int ks = unit % p.ksplit;
-        const int mn = unit / p.ksplit;
+        // output tile fastest, k-range slowest: the CTAs (pairs) of one round sweep the SAME token range for different output
+        // tiles, so a split-K wgrad fetches every operand row from HBM once and shares it through L2
+        const int mn_count = p.num_m_tiles * n_groups;
+        const int mn = unit % mn_count;
+        const int ks = unit / mn_count;
         n_group = mn % n_groups;
         m_tile = mn / n_groups;
         const int per = (iters_total + p.ksplit - 1) / p.ksplit;
@@ -235,6 +239,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
             unit_parity ^= 1;
         }
+        // A persistent GEMM is one wave from the start: signalling the dependent kernel at the top would park its blocks next to
+        // ours for the whole run (measured: 1 % slower steps).  Signal when this CTA's last tile has been drained instead.
+        if (warp == 2 && lane == 0) pdl_trigger();
     }
 
     tc_fence_before();
@@ -302,7 +309,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = units < sms ? units : sms;
-    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, args);
+    launch_k(kern, dim3(grid), dim3(GEMM_THREADS), L::TOTAL, stream, ta, tb, args);
     MDL_CHECK_LAUNCH();
     return 0;
 }
@@ -456,10 +463,24 @@ int mdl_gemm_tn_accum(const void* a_planes, long long a_cols, long long lda, lon
     const int mn_tiles = g.num_m_tiles * g.num_n_tiles;
     const int workers = two_cta ? kNumSMs / 2 : kNumSMs;
     if (ksplit <= 0) {
-        // aim for ~4 work units per worker (CTA or CTA pair), never more splits than k-blocks.  (Fewer, longer units look
-        // better when a wgrad is timed alone — tools/wgrad_ksplit_probe.py — but inside the step ~2 units per worker made the
-        // wgrads 10 % slower, 1.16 -> 1.28 ms: the tail of the last wave matters more than the per-unit epilogue.)
-        ksplit = (4 * workers + mn_tiles - 1) / mn_tiles;
+        const char* legacy = getenv("MDL_WGRAD_KSPLIT_LEGACY");      // A/B switch (read per call: tools/ab_probe.py flips it in-process)
+        if (legacy != nullptr && legacy[0] == '1') ksplit = (4 * workers + mn_tiles - 1) / mn_tiles;
+    }
+    if (ksplit <= 0) {
+        // Units = output tiles x k-ranges are dealt round-robin to the persistent workers (CTAs or CTA pairs), so the kernel
+        // lasts ceil(units / workers) rounds of one k-range each: pick the split with the smallest rounds x (k-blocks per range +
+        // a fixed per-unit cost for pipeline refill and the atomic epilogue), i.e. one whose unit count fills its last round
+        // (round 2: the former "~4 units per worker" gave 320 units = 4.3 rounds for the attention wgrad and 304 = 4.1 for
+        // layer 3 - the fifth round ran nearly empty).
+        const int kOverhead = 4;
+        long long best_cost = -1;
+        const int hi = (16 * workers + mn_tiles - 1) / mn_tiles;
+        for (int cand = 1; cand <= hi && cand <= g.k_blocks; ++cand) {
+            const long long rounds = ((long long)mn_tiles * cand + workers - 1) / workers;
+            const long long per = (g.k_blocks + cand - 1) / cand;
+            const long long cost = rounds * (per + kOverhead);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; ksplit = cand; }
+        }
     }
     if (ksplit > g.k_blocks) ksplit = g.k_blocks;
     if (ksplit < 1) ksplit = 1;

@@ -19,6 +19,7 @@ struct Rows {
 
 __global__ void __launch_bounds__(256)
 infonce_norm_kernel(Rows q, Rows k, int m, int D, float* __restrict__ qn, float* __restrict__ kn) {
+    pdl_sync();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + warp;
     if (row >= 2 * m) return;
@@ -36,6 +37,7 @@ infonce_norm_kernel(Rows q, Rows k, int m, int D, float* __restrict__ qn, float*
 __global__ void __launch_bounds__(256)
 infonce_logits_kernel(Rows q, Rows k, const float* __restrict__ qn, const float* __restrict__ kn,
                       int m, int D, float* __restrict__ L) {
+    pdl_sync();
     extern __shared__ float qs[];  // normalised q_i
     const int i = blockIdx.x;
     const float qi = qn[i];
@@ -56,6 +58,7 @@ infonce_logits_kernel(Rows q, Rows k, const float* __restrict__ qn, const float*
 __global__ void __launch_bounds__(256)
 infonce_lse_kernel(const float* __restrict__ L, int m, float inv_tau, float* __restrict__ lse_r, float* __restrict__ lse_c,
                    float* __restrict__ nll_r, float* __restrict__ nll_c) {
+    pdl_sync();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int w = blockIdx.x * 8 + warp;
     if (w >= 2 * m) return;
@@ -81,6 +84,7 @@ infonce_lse_kernel(const float* __restrict__ L, int m, float inv_tau, float* __r
 __global__ void __launch_bounds__(256)
 infonce_reduce_kernel(const float* __restrict__ nll_r, const float* __restrict__ nll_c, int m, float scale_r, float scale_c, float* __restrict__ loss,
                       float* __restrict__ total) {
+    pdl_sync();
     __shared__ float scratch[33];
     float s = 0.f;
     for (int i = threadIdx.x; i < m; i += blockDim.x) s += scale_r * nll_r[i] + (scale_c != 0.f ? scale_c * nll_c[i] : 0.f);
@@ -96,6 +100,7 @@ __global__ void __launch_bounds__(256)
 infonce_dlogits_kernel(const float* __restrict__ L, const float* __restrict__ lse_r, const float* __restrict__ lse_c,
                        const float* __restrict__ w_r, const float* __restrict__ w_c, int m, float inv_tau, float* __restrict__ G,
                        const float* __restrict__ go, float wr_const, float wc_const) {
+    pdl_sync();
     const long long total = (long long)m * m;
     // go != NULL: every sample's weight is (*go) * w{r,c}_const (mean / symmetric scaling folded in by the host)
     const float g0 = go != nullptr ? __ldg(go) : 0.f;
@@ -121,6 +126,7 @@ constexpr int INFONCE_MAX_U = 8;   // D <= 128 * 8
 __global__ void __launch_bounds__(128)
 infonce_grads_kernel(Rows q, Rows k, const float* __restrict__ qn, const float* __restrict__ kn,
                      const float* __restrict__ G, int m, int D, float* __restrict__ dq, float* __restrict__ dk, int accumulate) {
+    pdl_sync();
     __shared__ float scratch[33];
     extern __shared__ float gs[];  // coefficients G[i,:] * kn[:]  (or G[:,j] * qn[:])
     const int row = blockIdx.x;
@@ -176,16 +182,16 @@ static int infonce_fwd_impl(Rows q, Rows k, int m, int D, float temperature, int
     MDL_REQUIRE(temperature > 0.f, "infonce: temperature must be positive");
     MDL_REQUIRE((size_t)D * sizeof(float) <= 48 * 1024, "infonce: D too large (%d)", D);
     const float inv_tau = 1.f / temperature;
-    infonce_norm_kernel<<<(2 * m + 7) / 8, 256, 0, st>>>(q, k, m, D, qn, kn);
+    launch_k(infonce_norm_kernel, dim3((2 * m + 7) / 8), dim3(256), 0, st, q, k, m, D, qn, kn);
     MDL_CHECK_LAUNCH();
-    infonce_logits_kernel<<<m, 256, D * sizeof(float), st>>>(q, k, qn, kn, m, D, L);
+    launch_k(infonce_logits_kernel, dim3(m), dim3(256), D * sizeof(float), st, q, k, qn, kn, m, D, L);
     MDL_CHECK_LAUNCH();
-    infonce_lse_kernel<<<(2 * m + 7) / 8, 256, 0, st>>>(L, m, inv_tau, lse_r, lse_c, nll_r, nll_c);
+    launch_k(infonce_lse_kernel, dim3((2 * m + 7) / 8), dim3(256), 0, st, L, m, inv_tau, lse_r, lse_c, nll_r, nll_c);
     MDL_CHECK_LAUNCH();
     if (loss != nullptr && reduction != 0) {  // 1 = mean, 2 = sum
         const float base = reduction == 1 ? 1.f / m : 1.f;
         const float sr = symmetric ? 0.5f * base : base, sc = symmetric ? 0.5f * base : 0.f;
-        infonce_reduce_kernel<<<1, 256, 0, st>>>(nll_r, nll_c, m, sr, sc, loss, total);
+        launch_k(infonce_reduce_kernel, dim3(1), dim3(256), 0, st, nll_r, nll_c, m, sr, sc, loss, total);
         MDL_CHECK_LAUNCH();
     }
     return 0;
@@ -201,10 +207,10 @@ static int infonce_bwd_impl(Rows q, Rows k, int m, int D, float temperature, con
     const long long total = (long long)m * m;
     int blocks = (int)((total + 255) / 256);
     if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
-    infonce_dlogits_kernel<<<blocks, 256, 0, st>>>(L, lse_r, lse_c, w_r, w_c, m, inv_tau, G, go, wr_const, wc_const);
+    launch_k(infonce_dlogits_kernel, dim3(blocks), dim3(256), 0, st, L, lse_r, lse_c, w_r, w_c, m, inv_tau, G, go, wr_const, wc_const);
     MDL_CHECK_LAUNCH();
     // + 8 floats: the unrolled dot-product loop may load a few coefficients past m (speculatively, never used)
-    infonce_grads_kernel<<<2 * m, 128, (m + 8) * sizeof(float), st>>>(q, k, qn, kn, G, m, D, dq, dk, accumulate);
+    launch_k(infonce_grads_kernel, dim3(2 * m), dim3(128), (m + 8) * sizeof(float), st, q, k, qn, kn, G, m, D, dq, dk, accumulate);
     MDL_CHECK_LAUNCH();
     return 0;
 }

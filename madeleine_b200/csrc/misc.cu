@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "madeleine_b200.h"
 #include <stdarg.h>
+#include <stdlib.h>
 
 namespace mdl {
 
@@ -14,6 +15,18 @@ void set_last_error(const char* fmt, ...) {
     va_end(ap);
 }
 const char* get_last_error() { return g_err; }
+
+static std::atomic<int> g_pdl{-1};
+bool pdl_enabled() {
+    int v = g_pdl.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("MADELEINE_B200_PDL");
+        v = (e != nullptr && e[0] == '0') ? 0 : 1;
+        g_pdl.store(v, std::memory_order_relaxed);
+    }
+    return v != 0;
+}
+void set_pdl(int on) { g_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
 
 __device__ __forceinline__ float plane_val(const __nv_bfloat16* p, long long off, long long plane_stride, int plane) {
     return __bfloat162float(p[off + (long long)plane * plane_stride]);
@@ -68,6 +81,11 @@ extern "C" {
 const char* mdl_last_error(void) { return get_last_error(); }
 int mdl_version(void) { return 100; }
 int mdl_built_arch(void) { return 100; }
+int mdl_set_pdl(int on) {
+    const int before = pdl_enabled() ? 1 : 0;
+    set_pdl(on);
+    return before;
+}
 
 int mdl_gemm_nt_simt(const void* a_planes, long long lda, long long a_plane_stride, const void* b_planes, long long ldb,
                      long long b_plane_stride, float* out, long long ldc, int M, int N, int K, int nsplit, void* stream) {

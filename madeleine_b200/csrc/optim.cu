@@ -32,6 +32,7 @@ __device__ __forceinline__ void adamw_update(float& p, float g, float& m, float&
 __global__ void __launch_bounds__(256)
 adamw_kernel(const AdamWTable t, float lr, float beta1, float beta2, float eps, float weight_decay,
              float bias_corr1, float bias_corr2_sqrt, float grad_scale) {
+    pdl_sync();
     const float step_size = lr / bias_corr1;
     const float decay = 1.f - lr * weight_decay;
     const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nthreads = (long long)gridDim.x * blockDim.x;
@@ -92,7 +93,7 @@ int mdl_adamw_step(int n_tensors, void* const* host_params, void* const* host_gr
     long long blocks = (o / 4 + 255) / 256;
     if (blocks < 1) blocks = 1;
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-    adamw_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(t, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale);
+    launch_k(adamw_kernel, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, t, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale);
     MDL_CHECK_LAUNCH();
     return 0;
 }

@@ -73,6 +73,7 @@ __device__ __forceinline__ float attn_weight_grad(float l, float w, int act) {  
 __global__ void __launch_bounds__(POOL_THREADS)
 pool_weights_kernel(const float* __restrict__ logits, const int* __restrict__ cu, const int* __restrict__ tok_idx, int H,
                     float* __restrict__ attn_p, int act, int* __restrict__ tickets, int halves) {
+    pdl_sync();
     __shared__ float scratch[33];
     const int r = blockIdx.x;
     if (tickets != nullptr && threadIdx.x < halves) tickets[(r * H + blockIdx.y) * halves + threadIdx.x] = 0;
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 4)
 pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long plane_stride, const float* __restrict__ attn_p,
                 const int* __restrict__ cu, const int* __restrict__ tok_idx, int H, int E, int tsplit,
                 float* __restrict__ out, float* __restrict__ partial, int* __restrict__ tickets) {
+    pdl_sync();
     __shared__ int is_last;
     __shared__ float part[POOL_WARPS][256];
     const int halves = E / 256;
@@ -184,6 +186,7 @@ pool_bwd_dlogit_kernel(const __nv_bfloat16* __restrict__ x, long long plane_stri
                        const float* __restrict__ S, const float* __restrict__ attn_p, const int* __restrict__ cu,
                        const int* __restrict__ tok_idx, int H, int E, int tsplit, float* __restrict__ dlogit, int accumulate,
                        const float* __restrict__ logits, int act) {
+    pdl_sync();
     const int split = blockIdx.x, h = blockIdx.y, r = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t0 = cu[r], n = cu[r + 1] - t0;
@@ -251,6 +254,7 @@ pool_bwd_dlogit_kernel(const __nv_bfloat16* __restrict__ x, long long plane_stri
 // ABMILEmbedder(return_preattn_feats=True) called on its own.
 __global__ void planes_to_ref_order_kernel(const __nv_bfloat16* __restrict__ x, long long plane_stride, int nplanes, int f16,
                                            long long M, int H, int E, float* __restrict__ out) {
+    pdl_sync();
     const long long total = M * H * E;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long m = i / (H * E);
@@ -299,7 +303,7 @@ int mdl_pool_weights(const float* logits, const int* cu_seqlens, const int* tok_
     MDL_REQUIRE(tsplit == 1 || workspace != nullptr, "pool_weights: tsplit > 1 needs the pooling workspace (its tickets are cleared here)");
     if (n_bags == 0) return 0;
     const int halves = head_dim / 256 > 0 ? head_dim / 256 : 1;
-    pool_weights_kernel<<<dim3(n_bags, n_heads), POOL_THREADS, 0, (cudaStream_t)stream>>>(
+    launch_k(pool_weights_kernel, dim3(dim3(n_bags, n_heads)), dim3(POOL_THREADS), 0, (cudaStream_t)stream, 
         logits, cu_seqlens, tok_idx, n_heads, attn_p, activation, pool_tickets(workspace, tsplit, n_bags, n_heads, head_dim), halves);
     MDL_CHECK_LAUNCH();
     return 0;
@@ -323,13 +327,13 @@ int mdl_pool_fwd(const void* x_planes, long long plane_stride, int nplanes, cons
     int* tickets = pool_tickets(workspace, tsplit, n_bags, n_heads, head_dim);
     dim3 grid(halves * tsplit, n_heads, n_bags);
     if (nplanes == 2 && f16)
-        pool_fwd_kernel<2, true><<<grid, POOL_THREADS, 0, st>>>((const __nv_bfloat16*)x_planes, plane_stride, attn_p, cu_seqlens, tok_idx, n_heads, head_dim, tsplit, out, partial, tickets);
+        launch_k(pool_fwd_kernel<2, true>, dim3(grid), dim3(POOL_THREADS), 0, st, (const __nv_bfloat16*)x_planes, plane_stride, attn_p, cu_seqlens, tok_idx, n_heads, head_dim, tsplit, out, partial, tickets);
     else if (nplanes == 2)
-        pool_fwd_kernel<2, false><<<grid, POOL_THREADS, 0, st>>>((const __nv_bfloat16*)x_planes, plane_stride, attn_p, cu_seqlens, tok_idx, n_heads, head_dim, tsplit, out, partial, tickets);
+        launch_k(pool_fwd_kernel<2, false>, dim3(grid), dim3(POOL_THREADS), 0, st, (const __nv_bfloat16*)x_planes, plane_stride, attn_p, cu_seqlens, tok_idx, n_heads, head_dim, tsplit, out, partial, tickets);
     else if (f16)
-        pool_fwd_kernel<1, true><<<grid, POOL_THREADS, 0, st>>>((const __nv_bfloat16*)x_planes, plane_stride, attn_p, cu_seqlens, tok_idx, n_heads, head_dim, tsplit, out, partial, tickets);
+        launch_k(pool_fwd_kernel<1, true>, dim3(grid), dim3(POOL_THREADS), 0, st, (const __nv_bfloat16*)x_planes, plane_stride, attn_p, cu_seqlens, tok_idx, n_heads, head_dim, tsplit, out, partial, tickets);
     else
-        pool_fwd_kernel<1, false><<<grid, POOL_THREADS, 0, st>>>((const __nv_bfloat16*)x_planes, plane_stride, attn_p, cu_seqlens, tok_idx, n_heads, head_dim, tsplit, out, partial, tickets);
+        launch_k(pool_fwd_kernel<1, false>, dim3(grid), dim3(POOL_THREADS), 0, st, (const __nv_bfloat16*)x_planes, plane_stride, attn_p, cu_seqlens, tok_idx, n_heads, head_dim, tsplit, out, partial, tickets);
     MDL_CHECK_LAUNCH();
     return 0;
 }
@@ -354,9 +358,9 @@ int mdl_pool_bwd_dlogit(const void* x_planes, long long plane_stride, int nplane
     if (tsplit <= 0) tsplit = choose_tsplit(n_bags, n_heads, 1, total_tokens);
     dim3 grid(tsplit, n_heads, n_bags);
     if (nplanes == 2)
-        pool_bwd_dlogit_kernel<2><<<grid, POOL_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x_planes, plane_stride, dS, S, attn_p, cu_seqlens, tok_idx, n_heads, head_dim, tsplit, dlogit, accumulate, logits, activation);
+        launch_k(pool_bwd_dlogit_kernel<2>, dim3(grid), dim3(POOL_THREADS), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x_planes, plane_stride, dS, S, attn_p, cu_seqlens, tok_idx, n_heads, head_dim, tsplit, dlogit, accumulate, logits, activation);
     else
-        pool_bwd_dlogit_kernel<1><<<grid, POOL_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x_planes, plane_stride, dS, S, attn_p, cu_seqlens, tok_idx, n_heads, head_dim, tsplit, dlogit, accumulate, logits, activation);
+        launch_k(pool_bwd_dlogit_kernel<1>, dim3(grid), dim3(POOL_THREADS), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x_planes, plane_stride, dS, S, attn_p, cu_seqlens, tok_idx, n_heads, head_dim, tsplit, dlogit, accumulate, logits, activation);
     MDL_CHECK_LAUNCH();
     return 0;
 }
@@ -368,7 +372,7 @@ int mdl_planes_to_ref_order(const void* x_planes, long long plane_stride, int np
     const long long total = M * n_heads * head_dim;
     long long blocks = (total + 255) / 256;
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-    planes_to_ref_order_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x_planes, plane_stride, nplanes, f16, M, n_heads, head_dim, out);
+    launch_k(planes_to_ref_order_kernel, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x_planes, plane_stride, nplanes, f16, M, n_heads, head_dim, out);
     MDL_CHECK_LAUNCH();
     return 0;
 }

@@ -555,3 +555,40 @@ def test_encode_he_input_scale_robustness(scale, offset):
         out = model.encode_he(x, DEV)
     ref = oracle.encode_he(sd, x)
     close(out, ref)
+
+
+def test_programmatic_dependent_launch_same_results():
+    """csrc/common.cuh::launch_k: with the PDL launch attribute a kernel's blocks may become resident while its predecessor
+    drains, but griddepcontrol.wait keeps every memory access in stream order - a training step must give the same forward
+    bits and (up to the split-K reduction order of the wgrad GEMMs) the same gradients as plain launches."""
+    from madeleine_b200._lib import call
+    mods = ["HE", "ER", "PR"]
+    feats = make_feats(3, 6, 3, 300, 512)
+    labels = torch.ones(6, 3)
+    args = Namespace(global_loss="info-nce", symmetric_cl=True, local_loss_weight=1.0)
+
+    def run(pdl):
+        before = call("mdl_set_pdl", pdl)
+        try:
+            model = build(mods, True, 11)
+            for _ in range(3):      # repeated so that a stale read of a buffer the previous step rewrote would show
+                model.zero_grad(set_to_none=True)
+                embs, toks = model({"feats": feats}, DEV, train=True, n_views=1)
+                torch.manual_seed(5)
+                loss, _ = calculate_losses(mods[1:], InfoNCE(temperature=0.001), GOT, None, embs, toks, labels[:, 1:], args)
+                loss.backward()
+            torch.cuda.synchronize()
+            grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+            return {m: e.detach().clone() for m, e in embs.items()}, float(loss.detach()), grads
+        finally:
+            call("mdl_set_pdl", before)
+
+    e1, l1, g1 = run(1)
+    e0, l0, g0 = run(0)
+    for m in e1:
+        assert torch.equal(e1[m], e0[m]), m
+    assert abs(l1 - l0) <= 1e-6 * abs(l0)
+    assert g1.keys() == g0.keys()
+    scale = max(float(g.norm()) for g in g0.values())      # attention_c.bias gradients are sums of softmax dlogits: ~0 by cancellation
+    for k in g1:
+        assert float((g1[k] - g0[k]).norm()) <= 1e-4 * float(g0[k].norm()) + 1e-6 * scale, k

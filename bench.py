@@ -56,6 +56,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self.power_w, self.power_limit_w = [], None
         self._stop = threading.Event()
         self._thread = None
         self._smi = None
@@ -75,6 +76,10 @@ class ClockSampler:
             pynvml.nvmlInit()
             h = pynvml.nvmlDeviceGetHandleByIndex(self._visible_index())
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            try:
+                self.power_limit_w = pynvml.nvmlDeviceGetEnforcedPowerLimit(h) / 1e3
+            except Exception:  # noqa: BLE001
+                pass
 
             def poll():
                 while not self._stop.is_set():
@@ -84,6 +89,7 @@ class ClockSampler:
                         for bit, name in self.REASONS.items():
                             if mask & bit:
                                 self.reasons.add(name)
+                        self.power_w.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1e3)
                     except Exception:  # noqa: BLE001
                         pass
                     time.sleep(0.01)
@@ -100,8 +106,14 @@ class ClockSampler:
         self._stop.set()
         if self._thread is not None:
             self._thread.join(timeout=1.0)
-        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples), "source": "nvml, 10 ms period"}
+        out = {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(self.reasons), "samples": len(self.samples), "source": "nvml, 10 ms period"}
+        if self.power_w:
+            # NVML's board power is a slow average (~1 s): over a 0.1 s timed region it mostly reflects the warm-up steps before it.
+            # Sustained, the step draws 983 W of the 1000 W limit at ~1515 MHz (tools/ab_probe.py --power, profiles/r02_s2_ab_probes.json)
+            out["power_w"] = round(statistics.median(self.power_w), 1)
+            out["power_limit_w"] = self.power_limit_w
+        return out
 
 
 class _SmiSampler:

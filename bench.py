@@ -293,6 +293,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--timeline", action="store_true", help="N > 1: add a per-phase device timeline of the step (max and mean over ranks)")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the ~3 s sustained-state run")
     ap.add_argument("--no-canonical", action="store_true", help="skip the reference's canonical 65 x 5 x 2048 configuration block")
     ap.add_argument("--no-optimizer", action="store_true",
                     help="time forward + backward only; by default every timed step also runs the fused AdamW update, so the "
@@ -590,11 +591,11 @@ def main():
     pool_gbs = pool_bytes / (pool_ms * 1e-3) / 1e9
     # DRAM traffic of the same launch from the committed `ncu --set full` capture (profiles/), fp32-mode workload only
     traffic, traffic_src = None, None
-    ncu_json = os.path.join(REPO, "profiles", "r01_pool_fwd_ncu.json")
+    ncu_json = os.path.join(REPO, "profiles", "r02_pool_fwd_ncu.json")
     if args.precision == "fp32" and os.path.exists(ncu_json):
         cap = json.load(open(ncu_json))
         if cap.get("algorithmic_bytes") == pool_bytes:
-            traffic, traffic_src = cap["traffic_bytes"], "profiles/r01_pool_fwd_ncu.json (dram__bytes_read.sum + dram__bytes_write.sum)"
+            traffic, traffic_src = cap["traffic_bytes"], "profiles/r02_pool_fwd_ncu.json (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)"
     roofline = {"kernel": "pool_fwd_kernel (attention pooling, forward; the softmax weights come from the separate pool_weights_kernel)", "bound": "hbm",
                 "achieved": pool_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": pool_gbs / peaks["hbm_gbs"],
                 "traffic": traffic, "traffic_source": traffic_src, "avg_launch_ms": pool_ms,
@@ -637,6 +638,18 @@ def main():
                             "algorithmic_gflop_per_bag": (flops_fwd + flops_bwd) / bags_local / 1e9,
                             "frac_bf16_issue": step_tf * issued / world / peaks["bf16_tflops_sustained"],
                             "note": "algorithmic FLOPs x bags/s over the sustained bf16 rate; x3 issued in the fp32-grade mode"}
+    # the same device-resident step in the SUSTAINED state (~3 s of continuous stepping): the step runs at the board's power limit
+    # (DESIGN.md §6), so the K steps timed right after the warm-up are a few per cent faster than the steady state
+    if not args.no_sustained:
+        n_sus = max(args.steps, int(3000.0 / ms_step))
+        sus = ClockSampler(local_rank)
+        if rank == 0:
+            sus.start()
+        ms_sus = timed(n_sus, lambda i: feats_dev, read_loss=False)
+        sus_clk = sus.stop() if rank == 0 else None
+        out["sustained"] = {"steps": n_sus, "ms_per_step": ms_sus, "slides_per_s": bags_per_step / (ms_sus * 1e-3),
+                            "sm_mhz": sus_clk and sus_clk.get("sm_mhz"), "power_w": sus_clk and sus_clk.get("power_w"),
+                            "power_limit_w": sus_clk and sus_clk.get("power_limit_w"), "reasons": sus_clk and sus_clk.get("reasons")}
     out["parity"] = parity
     if world > 1:
         out["small_collectives"] = parallel.PeerExchange.status()

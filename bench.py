@@ -572,10 +572,28 @@ def main():
         e2e = {"value": bags_per_step / (ms_e2e * 1e-3), "unit": "slides/s", "ms_per_step": ms_e2e, "bound": bound,
                "h2d_bytes_per_step": feats_host[0].numel() * 4, "d2h_bytes_per_step": 4,
                "h2d_gbs_alone": h2d_gbs, "runs_ms_per_step": e2e_runs,
+               "protocol": "5 warm-up steps, then 3 x K timed steps back to back; median.  Every run pays its own pipeline fill (the first "
+                           "batch's 131 MB copy is not overlapped: 2.4 ms / K per step) and runs in the sustained power state",
                "note": "pinned host features staged one batch ahead on a copy stream; every step's loss is read back inside the "
                        "timed region, two steps deferred so the host stays ahead of the device (tools/e2e_probe.py); "
                        "h2d_gbs_alone = this box's pinned H2D rate for one batch with the GPU otherwise idle (N > 1: all ranks copying "
                        "at the same time)"}
+
+    # ---- the same device-resident step in the SUSTAINED state (~3 s of continuous stepping): the step runs at the board's power
+    # limit, so the K steps timed right after the warm-up are a few per cent faster than the steady state.
+    # (All ranks: timed() is a collective.) ----
+    sustained = None
+    if not args.no_sustained:
+        n_sus = max(args.steps, int(3000.0 / ms_step))
+        sus = ClockSampler(local_rank)
+        if rank == 0:
+            sus.start()
+        ms_sus = timed(n_sus, lambda i: feats_dev, read_loss=False)
+        sus_clk = sus.stop() if rank == 0 else None
+        if rank == 0:
+            sustained = {"steps": n_sus, "ms_per_step": ms_sus, "slides_per_s": bags_per_step / (ms_sus * 1e-3),
+                         "sm_mhz": sus_clk.get("sm_mhz"), "power_w": sus_clk.get("power_w"),
+                         "power_limit_w": sus_clk.get("power_limit_w"), "reasons": sus_clk.get("reasons")}
 
     if rank != 0:
         if world > 1:
@@ -638,18 +656,7 @@ def main():
                             "algorithmic_gflop_per_bag": (flops_fwd + flops_bwd) / bags_local / 1e9,
                             "frac_bf16_issue": step_tf * issued / world / peaks["bf16_tflops_sustained"],
                             "note": "algorithmic FLOPs x bags/s over the sustained bf16 rate; x3 issued in the fp32-grade mode"}
-    # the same device-resident step in the SUSTAINED state (~3 s of continuous stepping): the step runs at the board's power limit
-    # (DESIGN.md §6), so the K steps timed right after the warm-up are a few per cent faster than the steady state
-    if not args.no_sustained:
-        n_sus = max(args.steps, int(3000.0 / ms_step))
-        sus = ClockSampler(local_rank)
-        if rank == 0:
-            sus.start()
-        ms_sus = timed(n_sus, lambda i: feats_dev, read_loss=False)
-        sus_clk = sus.stop() if rank == 0 else None
-        out["sustained"] = {"steps": n_sus, "ms_per_step": ms_sus, "slides_per_s": bags_per_step / (ms_sus * 1e-3),
-                            "sm_mhz": sus_clk and sus_clk.get("sm_mhz"), "power_w": sus_clk and sus_clk.get("power_w"),
-                            "power_limit_w": sus_clk and sus_clk.get("power_limit_w"), "reasons": sus_clk and sus_clk.get("reasons")}
+    out["sustained"] = sustained
     out["parity"] = parity
     if world > 1:
         out["small_collectives"] = parallel.PeerExchange.status()

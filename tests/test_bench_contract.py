@@ -38,3 +38,14 @@ def test_cuda_arm_fails_loudly_without_a_gpu():
     out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--steps", "1", "--warmup", "1"],
                          capture_output=True, text=True, timeout=300, cwd=REPO)
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+def test_no_collective_after_the_non_zero_ranks_left():
+    """bench.py's ranks > 0 return once the measurements are done; anything after that point runs on rank 0 alone and must not
+    contain a collective (a sustained-state run placed there hung a 2-GPU bench until its timeout)."""
+    src = open(os.path.join(REPO, "bench.py")).read()
+    marker = "    if rank != 0:\n        if world > 1:\n            dist.destroy_process_group()\n        return\n"
+    assert src.count(marker) == 1
+    tail = src.split(marker)[1]
+    for needle in ("timed(", "dist.barrier", "all_reduce", "all_gather", "run_e2e(", "step(feats"):
+        assert needle not in tail, needle

@@ -410,6 +410,13 @@ def main():
         return out
 
     parity = sharded_parity() if world > 1 else None
+    if world > 1:
+        # The parity check keeps every GPU busy for a while (the ranks > 0 spin in NCCL's barrier while rank 0 evaluates the global
+        # batch), and the step runs at the board's power limit: without a pause the K timed steps of an N > 1 run would start in
+        # the throttled state while an N = 1 run starts from an idle GPU.  Same protocol for every N: idle, W warm-up, K timed.
+        torch.cuda.synchronize()
+        time.sleep(2.0)
+        dist.barrier()
 
     def timed(n_steps, feats_fn, read_loss, ctx=None):
         if world > 1:

@@ -44,7 +44,7 @@ class _PackedStager:
         self.dev = [torch.empty(self.cap, self.D, dtype=torch.float32, device=self.device) for _ in range(2)]
         self.slot_free = [None, None]
         n_cu = max(len(b) for b in batches) + 1
-        self.cu_host = [torch.empty(n_cu, dtype=torch.int32).pin_memory() for _ in range(2)]
+        self.cu_host = [torch.empty(n_cu, dtype=torch.int32, pin_memory=True) for _ in range(2)]
         self.cu_dev = [torch.empty(n_cu, dtype=torch.int32, device=self.device) for _ in range(2)]
         self.cu_done = [None, None]
         self.host = None                                     # pinned staging, allocated on first pageable bag
@@ -53,7 +53,18 @@ class _PackedStager:
 
     def _stage_pageable(self, rows, dst):
         if self.host is None:
-            self.host = [torch.empty(self.cap, self.D, dtype=torch.float32).pin_memory() for _ in range(3)]
+            # page-locked directly (torch's caching host allocator keeps the blocks across calls); `.pin_memory()` on a fresh
+            # pageable tensor would allocate it twice and copy 3 x cap x D floats of garbage inside the caller's timed region
+            # ... first-touched from the GPU's NUMA node (hostmem.bind_to_gpu), the caller's affinity restored afterwards
+            import os
+            from . import hostmem
+            saved = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+            hostmem.bind_to_gpu(self.device.index if self.device.index is not None else torch.cuda.current_device())
+            try:
+                self.host = [hostmem.pinned_empty((self.cap, self.D)) for _ in range(3)]
+            finally:
+                if saved is not None:
+                    os.sched_setaffinity(0, saved)
         h = self.k_host % 3
         self.k_host += 1
         if self.host_done[h] is not None:

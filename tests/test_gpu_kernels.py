@@ -311,9 +311,9 @@ def test_planes_to_ref_order():
 
 
 # ---------------------------------------------------------------------------------------------- skinny / stain
-@pytest.mark.parametrize("R", [1, 32, 77, 325, 1500])
-def test_skinny_linear(R):
-    C, O = 2048, 512
+@pytest.mark.parametrize("R,C,O", [(1, 2048, 512), (32, 2048, 512), (77, 2048, 512), (325, 2048, 512), (1500, 2048, 512),
+                                   (5, 512, 512), (40, 2048, 200), (9, 512, 24), (33, 2048, 8)])
+def test_skinny_linear(R, C, O):
     X = torch.randn(R, C, device=DEV, requires_grad=True)
     W = (torch.randn(O, C, device=DEV) / math.sqrt(C)).requires_grad_(True)
     b = torch.randn(O, device=DEV, requires_grad=True)

@@ -184,6 +184,8 @@ __device__ __forceinline__ float bf16_hi_of(uint32_t packed) { return __uint_as_
 // exponential that underflows should flush to zero.
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// one MUFU, |relative error| <= 2^-11: only where the operands are bf16 anyway (the 1-pass modes)
+__device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // GELU(x) = x Phi(x) and its derivative Phi(x) + x phi(x) from ONE exponential: erfc(|x|/sqrt2) by Abramowitz-Stegun
 // 7.1.26 (|abs err| <= 1.5e-7, far inside the 1e-4 parity budget) uses exp(-x^2/2), which is also the Gaussian pdf.

@@ -99,7 +99,9 @@ gemm2_kf_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     if constexpr (EPI == EPI_GATED) {
         const int hc = p.n_heads * 512;
         for (int i = threadIdx.x; i < hc; i += GEMM_THREADS) {
-            aux[i] = -2.885390081777927f * __ldg(p.ba + i); aux[2048 + i] = -1.4426950408889634f * __ldg(p.bb + i); aux[4096 + i] = __ldg(p.wc + i);   // pre-scaled: see EPI_GATED
+            if constexpr (ONE_PASS) { aux[i] = __ldg(p.ba + i); aux[2048 + i] = 0.5f * __ldg(p.bb + i); }      // FAST_GATES
+            else { aux[i] = -2.885390081777927f * __ldg(p.ba + i); aux[2048 + i] = -1.4426950408889634f * __ldg(p.bb + i); }   // pre-scaled: see EPI_GATED
+            aux[4096 + i] = __ldg(p.wc + i);
         }
     }
     tc_fence_before();
@@ -238,7 +240,7 @@ gemm2_kf_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 mbar_wait(tmem_full_bar(acc), acc_phase);
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-                epilogue_tile<BLOCK_N, EPI>(p, aux, t_row, m_tile * 256 + rank * 128, quad, half, warp - 2, lane, n_tile, n_group, inner,
+                epilogue_tile<BLOCK_N, EPI, ONE_PASS && EPI == EPI_GATED>(p, aux, t_row, m_tile * 256 + rank * 128, quad, half, warp - 2, lane, n_tile, n_group, inner,
                                             kb1 > kb0, gated_partial, unit_parity);
                 tc_fence_before();
                 __syncwarp();

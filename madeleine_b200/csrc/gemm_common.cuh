@@ -67,7 +67,10 @@ __host__ __device__ __forceinline__ size_t gate_tile_offset(long long m, int j, 
 
 // Drain one [128 x BLOCK_N] accumulator tile (this CTA's TMEM lanes) for epilogue warp `warp_epi` (0..7):
 // quadrant = warp_epi & 3 ... see callers; `row_base` is the global output row of TMEM lane 0 of this CTA.
-template <int BLOCK_N, int EPI>
+// FAST_GATES (EPI_GATED, 1-pass modes only): tanh and sigmoid from ONE tanh.approx each (sigmoid(y) = 0.5 tanh(y / 2) + 0.5; 2^-11, below the
+// bf16 operands' own 2^-9) instead of ex2 + rcp each: the bf16-mode gated GEMM is bound by its epilogue's MUFU work, not by
+// its MMAs.  aux then holds ba and bb / 2 unscaled (see the kernels' prologues).
+template <int BLOCK_N, int EPI, bool FAST_GATES = false>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, float* aux, uint32_t t_row, int row_base, int quad, int half,
                                               int warp_epi, int lane, int n_tile, int n_group, int inner, bool have_k,
                                               float& gated_partial, int unit_parity) {
@@ -181,10 +184,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, float* aux, uin
                 float av[4], bv[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float ea = ex2_approx(fmaf(__uint_as_float(xa[4 * i4 + i]), C2, fba[i]));
-                    const float eb = ex2_approx(fmaf(__uint_as_float(xb[4 * i4 + i]), C1, fbb[i]));
-                    av[i] = fmaf(2.f, rcp_approx(1.f + ea), -1.f) * ma[i];
-                    bv[i] = rcp_approx(1.f + eb) * mb[i];
+                    if constexpr (FAST_GATES) {
+                        av[i] = tanh_approx(fmaf(__uint_as_float(xa[4 * i4 + i]), p.acc_scale, fba[i])) * ma[i];
+                        bv[i] = fmaf(0.5f, tanh_approx(fmaf(__uint_as_float(xb[4 * i4 + i]), 0.5f * p.acc_scale, fbb[i])), 0.5f) * mb[i];
+                    } else {
+                        const float ea = ex2_approx(fmaf(__uint_as_float(xa[4 * i4 + i]), C2, fba[i]));
+                        const float eb = ex2_approx(fmaf(__uint_as_float(xb[4 * i4 + i]), C1, fbb[i]));
+                        av[i] = fmaf(2.f, rcp_approx(1.f + ea), -1.f) * ma[i];
+                        bv[i] = rcp_approx(1.f + eb) * mb[i];
+                    }
                     gated_partial = fmaf(av[i] * bv[i], fwc[i], gated_partial);
                 }
                 if (p.gate_a != nullptr) {

@@ -152,7 +152,8 @@ def test_gemm_gated(M, nsplit):
         ref_a.append(a)
         ref_b.append(b)
     ref_l = torch.stack(ref_l, dim=1)
-    torch.testing.assert_close(logits.double(), ref_l, rtol=1e-4, atol=2e-4)
+    # the 1-pass (bf16) mode evaluates each gate with one tanh.approx (2^-11): its operands carry 2^-9 anyway
+    torch.testing.assert_close(logits.double(), ref_l, rtol=1e-4, atol=2e-4 if nsplit == 3 else 3e-3)
     torch.testing.assert_close(ga.double(), torch.cat(ref_a, 1), rtol=2e-3, atol=1e-3)
     torch.testing.assert_close(gb.double(), torch.cat(ref_b, 1), rtol=2e-3, atol=1e-3)
     # gates optional

@@ -178,9 +178,19 @@ class ABMILEmbedder(nn.Module):
             slide, logits, tokens, ref = ops.EncodeFn.apply(holder, x, *params)
         return {"slide": slide, "logits": logits, "tokens": tokens, "ref_feats": ref}
 
+    _cu_cache = {}
+
     @staticmethod
     def uniform_cu(n_bags, n_tokens, device):
-        return torch.arange(0, (n_bags + 1) * n_tokens, n_tokens, dtype=torch.int32, device=device)
+        """cu_seqlens of a dense [n_bags, n_tokens] batch; read-only, so the last few shapes are kept (no arange launch per step)."""
+        key = (int(n_bags), int(n_tokens), str(device))
+        cu = ABMILEmbedder._cu_cache.get(key)
+        if cu is None:
+            if len(ABMILEmbedder._cu_cache) >= 16:
+                ABMILEmbedder._cu_cache.clear()
+            cu = torch.arange(0, (n_bags + 1) * n_tokens, n_tokens, dtype=torch.int32, device=device)
+            ABMILEmbedder._cu_cache[key] = cu
+        return cu
 
     @staticmethod
     def half_views(n_bags, n_tokens, device):

@@ -247,6 +247,10 @@ ln_gelu_bwd_kernel(const void* __restrict__ z, int M, const float* __restrict__ 
     const int grp = warp / WPR, wq = warp % WPR;
     const int c0 = wq * 512 + lane * 4;                       // this lane's columns: c0 + 128 j + i
     const int cols_per_head = C / n_heads;
+    // a warp's 512-column slab lies inside ONE head whenever a head is a whole number of slabs (always for the 2048-wide layer with
+    // 4 heads): the attention weight of (row, head) is then one load per row, not a runtime division and a load per 128 columns
+    const bool one_head = cols_per_head % 512 == 0;
+    const int head_of_warp = one_head ? (wq * 512) / cols_per_head : 0;
     for (int i = tid; i < 3 * C; i += 256) colacc[i] = 0.f;
     float* my_stage = lnb_stage + (size_t)warp * (LNB_ASYNC_STAGES * 2 * 512) + lane * 4;
     float accg[16], accb[16], accz[16], accbag[BAGSUM ? 16 : 1];
@@ -337,9 +341,10 @@ ln_gelu_bwd_kernel(const void* __restrict__ z, int M, const float* __restrict__ 
             }
             if (NPOOL >= 1) {
                 const float* dS = pt0.dS + (size_t)__ldg(pt0.row2seg + mr) * C + c0;
+                const float pw_row = one_head ? __ldg(pt0.p + (size_t)mr * n_heads + head_of_warp) : 0.f;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float pw = __ldg(pt0.p + (size_t)mr * n_heads + (c0 + 128 * j) / cols_per_head);
+                    const float pw = one_head ? pw_row : __ldg(pt0.p + (size_t)mr * n_heads + (c0 + 128 * j) / cols_per_head);
                     const float4 t = __ldg(reinterpret_cast<const float4*>(dS + 128 * j));
                     dv[j].x = fmaf(pw, t.x, dv[j].x); dv[j].y = fmaf(pw, t.y, dv[j].y);
                     dv[j].z = fmaf(pw, t.z, dv[j].z); dv[j].w = fmaf(pw, t.w, dv[j].w);
@@ -347,9 +352,10 @@ ln_gelu_bwd_kernel(const void* __restrict__ z, int M, const float* __restrict__ 
             }
             if (NPOOL >= 2) {
                 const float* dS = pt1.dS + (size_t)__ldg(pt1.row2seg + mr) * C + c0;
+                const float pw_row = one_head ? __ldg(pt1.p + (size_t)mr * n_heads + head_of_warp) : 0.f;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float pw = __ldg(pt1.p + (size_t)mr * n_heads + (c0 + 128 * j) / cols_per_head);
+                    const float pw = one_head ? pw_row : __ldg(pt1.p + (size_t)mr * n_heads + (c0 + 128 * j) / cols_per_head);
                     const float4 t = __ldg(reinterpret_cast<const float4*>(dS + 128 * j));
                     dv[j].x = fmaf(pw, t.x, dv[j].x); dv[j].y = fmaf(pw, t.y, dv[j].y);
                     dv[j].z = fmaf(pw, t.z, dv[j].z); dv[j].w = fmaf(pw, t.w, dv[j].w);

@@ -285,6 +285,51 @@ def canonical_block(precision, dev, steps):
     return res
 
 
+def ragged_block(precision, dev, steps):
+    """BASELINE configs[1] as written (N = 1 only): 16 cases x 2 stains with N_i ~ randint(200, 4001) per bag (generator seed 1234,
+    SURVEY.md §8d), packed back to back ([sum N_i, 512] + cu_seqlens, no padding) through ``forward_packed`` — token embeddings
+    included, as forward(train=True) computes them — + symmetric InfoNCE (tau = 0.001) + backward + fused AdamW, train mode."""
+    from madeleine.models.Model import MADELEINE
+    from madeleine.utils.loss import InfoNCE
+    from madeleine_b200.optim import FusedAdamW
+    from weights import make_state_dict
+    model = MADELEINE(model_cfg(precision), stain_encoding=False)
+    model.load_state_dict(make_state_dict(0, n_mod=2), strict=True)
+    model.to(dev).train()
+    opt = FusedAdamW(model.parameters(), lr=1e-4)
+    g = torch.Generator().manual_seed(1234)
+    lens = torch.randint(200, 4001, (CASES_PER_GPU * N_STAINS,), generator=g)
+    cu = torch.zeros(lens.numel() + 1, dtype=torch.int32)
+    cu[1:] = lens.cumsum(0)
+    total = int(cu[-1])
+    x = torch.randn(total, D_IN, device=dev)
+    cu_dev = cu.to(dev)
+    loss_fn = InfoNCE(temperature=TAU)
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        slide, _tokens = model.forward_packed(x, cu_dev, want_tokens=True)      # bags 2c / 2c + 1 = HE / IHC slide of case c
+        loss = loss_fn(query=slide[0::2], positive_key=slide[1::2], symmetric=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"workload": "16 cases x 2 stains, N_i ~ randint(200, 4001) (seed 1234), bag-packed, fwd+bwd+AdamW, train mode",
+            "bags": int(lens.numel()), "tokens": total, "min_len": int(lens.min()), "max_len": int(lens.max()), "ms_per_step": ms,
+            "slides_per_s": lens.numel() / (ms * 1e-3), "tokens_per_s": total / (ms * 1e-3),
+            "padded_tokens_if_batched_dense": int(lens.max()) * int(lens.numel()), "loss": float(loss.detach())}
+
+
 # ------------------------------------------------------------------------------------------------ our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -298,7 +343,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--timeline", action="store_true", help="N > 1: add a per-phase device timeline of the step (max and mean over ranks)")
     ap.add_argument("--no-sustained", action="store_true", help="skip the ~3 s sustained-state run")
-    ap.add_argument("--no-canonical", action="store_true", help="skip the reference's canonical 65 x 5 x 2048 configuration block")
+    ap.add_argument("--no-canonical", action="store_true", help="skip the two extra N = 1 blocks: configs[1] with ragged bags and the reference's canonical 65 x 5 x 2048 configuration")
     ap.add_argument("--no-optimizer", action="store_true",
                     help="time forward + backward only; by default every timed step also runs the fused AdamW update, so the "
                          "kernel-layout copies of the weights are re-packed every step as in real training (nothing is cached "
@@ -678,6 +723,7 @@ def main():
     if world == 1 and not args.no_canonical:
         del feats_dev, feats_host
         torch.cuda.empty_cache()
+        out["ragged"] = ragged_block(args.precision, dev, args.steps)
         out["canonical"] = canonical_block(args.precision, dev, 5)
     if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_baseline_quick()

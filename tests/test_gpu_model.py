@@ -592,3 +592,69 @@ def test_programmatic_dependent_launch_same_results():
     scale = max(float(g.norm()) for g in g0.values())      # attention_c.bias gradients are sums of softmax dlogits: ~0 by cancellation
     for k in g1:
         assert float((g1[k] - g0[k]).norm()) <= 1e-4 * float(g0[k].norm()) + 1e-6 * scale, k
+
+
+def test_calculate_losses_availability_edge_cases_against_oracle():
+    """trainer.py:24-26: a stain takes part only when MORE than one case of the batch has it; with no such stain the reference
+    returns (-1, False).  Masks: IHC1 present in one case (skipped), IHC2 in two cases (a 2 x 2 InfoNCE and 2-token GOT problems),
+    IHC3 in all four; then a batch where nothing qualifies."""
+    import oracle
+    mods = ["HE", "ER", "PR", "KI67"]
+    sd = make_state_dict(21, n_mod=4, stain_encoding=True)
+    model = MADELEINE(cfg(mods), stain_encoding=True)
+    model.load_state_dict(sd, strict=True)
+    model.to(DEV).eval()
+    labels = torch.tensor([[1., 1., 0., 1.], [1., 0., 1., 1.], [1., 0., 1., 1.], [1., 0., 0., 1.]])
+    feats = make_feats(4, 4, 4, 64, 512) * labels[:, :, None, None]
+    args = Namespace(global_loss="info-nce", symmetric_cl=True, local_loss_weight=1.0)
+
+    embs, toks = model({"feats": feats}, DEV, train=True, n_views=1)
+    torch.manual_seed(3)
+    loss, flag = calculate_losses(mods[1:], InfoNCE(temperature=0.1), GOT, None, embs, toks, labels[:, 1:], args)
+    loss.backward()
+    sd_o = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    embs_o, toks_o = oracle.madeleine_forward_train(sd_o, feats, mods, stain_encoding=True)
+    torch.manual_seed(3)
+    loss_o, flag_o = oracle.calculate_losses(mods[1:], embs_o, toks_o, labels[:, 1:], temperature=0.1, symmetric=True, use_local=True)
+    loss_o.backward()
+    assert flag is True and flag_o is True
+    close(loss, loss_o.detach(), rtol=1e-3, atol=1e-3)
+    for name in ("projector.weight", "wsi_embedders.pre_attn.8.weight", "embedding.weight"):
+        g, go = dict(model.named_parameters())[name].grad.cpu().double(), sd_o[name].grad.double()
+        assert float((g - go).norm() / go.norm()) < 5e-2, name
+
+    # nothing qualifies: every stain present in at most one case
+    lonely = torch.tensor([[1., 1., 0., 0.], [1., 0., 1., 0.], [1., 0., 0., 1.], [1., 0., 0., 0.]])
+    embs, toks = model({"feats": feats * lonely[:, :, None, None]}, DEV, train=True, n_views=1)
+    loss, flag = calculate_losses(mods[1:], InfoNCE(temperature=0.1), GOT, None, embs, toks, lonely[:, 1:], args)
+    assert loss == -1 and flag is False
+    assert oracle.calculate_losses(mods[1:], embs_o, toks_o, lonely[:, 1:], use_local=True) == (-1, False)
+
+
+def test_gradient_accumulation_over_two_backward_calls():
+    """Two forward / backward passes without zero_grad() in between: .grad is the sum of the two passes' gradients (the flat
+    gradient buffer of a pass must not alias the one the parameters' .grad already point into)."""
+    mods = ["HE", "ER"]
+    model = build(mods, False, 13)
+    loss_fn = InfoNCE(temperature=0.1)
+    xs = [make_feats(s, 4, 2, 150, 512) for s in (1, 2)]
+
+    def one(x):
+        embs, _ = model({"feats": x}, DEV, train=True, n_views=1)
+        return loss_fn(query=embs["HE"][:, 0, :, 0], positive_key=embs["ER"][:, 0, :], symmetric=True)
+
+    singles = []
+    for x in xs:
+        model.zero_grad(set_to_none=True)
+        one(x).backward()
+        singles.append({n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None})
+    model.zero_grad(set_to_none=True)
+    one(xs[0]).backward()
+    one(xs[1]).backward()
+    scale = max(float(g.norm()) for g in singles[0].values())
+    for n, p in model.named_parameters():
+        if p.grad is None:
+            assert n not in singles[0]
+            continue
+        want = singles[0][n] + singles[1][n]
+        assert float((p.grad - want).norm()) <= 1e-4 * float(want.norm()) + 1e-6 * scale, n

@@ -207,3 +207,31 @@ def test_oracle_got_large_problems_against_reference(golden):
         torch.testing.assert_close(loss.detach(), g["loss"], rtol=1e-4, atol=1e-5)
         for got, ref in ((vr.grad, g["dv"]), (qr.grad, g["dq"])):
             assert float((got - ref).norm() / ref.norm()) < 1e-3
+
+
+def test_oracle_at_baseline_size_against_the_real_reference(golden):
+    """BASELINE configs[1] at its full size (32 ragged bags, 68 063 tokens, tau = 0.001): the oracle the GPU tests use as yardstick
+    there (tests/parity_utils.py, here in fp32 on the CPU) against the real reference's slide embeddings, loss and gradient norms
+    (tests/golden/baseline_sizes.pt, make_golden_baseline_sizes.py).  tau = 0.001 amplifies rounding differences of the embeddings a
+    thousandfold in the logits, hence the wider loss / gradient tolerances than for the small fixtures."""
+    import parity_utils as pu
+    g = golden("baseline_sizes")
+    gen = torch.Generator().manual_seed(1234)
+    lens = torch.randint(200, 4001, (32,), generator=gen).tolist()
+    assert lens == g["lens"]
+    cu = [0]
+    for n in lens:
+        cu.append(cu[-1] + n)
+    x = torch.randn(cu[-1], 512, generator=gen)
+    assert float(x.double().abs().sum()) == pytest.approx(g["x_checksum"], rel=1e-12)
+    sd = pu.to_oracle_sd(make_state_dict(0, n_mod=2), torch.device("cpu"), torch.float32)
+    loss, emb = pu.oracle_packed_infonce_step(sd, x, cu, g["tau"])
+    close(emb, g["slide"], rtol=1e-4, atol=1e-5)
+    assert float(loss) == pytest.approx(float(g["loss"]), rel=1e-4)
+    total = sum(float(d["norm"]) ** 2 for d in g["grads"].values()) ** 0.5
+    for name, d in g["grads"].items():
+        ref = float(d["norm"])
+        if ref < 1e-6 * total:      # attention_c.bias: exactly 0 under a softmax over the tokens, ~1e-7 of rounding noise in any fp32 evaluation
+            assert float(sd[name].grad.double().norm()) < 1e-6 * total, name
+            continue
+        assert float(sd[name].grad.double().norm()) == pytest.approx(ref, rel=1e-3), name

@@ -22,11 +22,14 @@ sys.path.insert(1, HERE)
 
 import torch  # noqa: E402
 
+torch.Tensor.cuda = lambda self, *a, **k: self  # GOT hard-codes .cuda() (quirk Q7)
+
 import madeleine  # noqa: E402
 
 assert madeleine.__file__.startswith("/root/reference"), madeleine.__file__
 from madeleine.models.Model import MADELEINE  # noqa: E402
-from madeleine.utils.loss import InfoNCE  # noqa: E402
+from madeleine.utils.loss import InfoNCE, GOT  # noqa: E402
+from madeleine.utils.trainer import calculate_losses  # noqa: E402
 from weights import make_state_dict  # noqa: E402
 
 torch.set_num_threads(os.cpu_count() or 8)
@@ -74,5 +77,53 @@ def main():
     print(f"wrote {path} ({os.path.getsize(path) / 1024:.1f} KiB); loss {float(loss):.6f}; {out['meta']['seconds']:.1f} s")
 
 
+def digest(model):
+    grads = {}
+    for name, p in model.named_parameters():
+        if p.grad is None:
+            continue
+        flat = p.grad.detach().flatten()
+        gen = torch.Generator().manual_seed(flat.numel())
+        idx = torch.randint(0, flat.numel(), (64,), generator=gen)
+        grads[name] = {"norm": flat.double().norm(), "idx": idx, "samples": flat[idx].clone()}
+    return grads
+
+
+def config3(T=512):
+    """BASELINE configs[2] (batch 32, 5 stains, stain encodings, ACROBAT availability rates, InfoNCE tau = 0.001 + GOT) through the
+    reference's own forward(train=True) + calculate_losses + backward.  The reference materialises every activation of the whole
+    batch for autograd (~120 KB per token in fp32: 39 GB at the configuration's 2048 tokens per bag, more than this container can
+    give), so the fixture uses 512 tokens per bag: 81 920 tokens, every code path of the full configuration."""
+    mods = ["HE", "HER2", "PGR", "KI67", "ER"]
+    cfg = Namespace(MODALITIES=mods, wsi_encoder="abmil", patch_embedding_dim=512, wsi_encoder_hidden_dim=512, activation="softmax",
+                    n_heads=4)
+    model = MADELEINE(cfg, stain_encoding=True)
+    model.load_state_dict(make_state_dict(3, n_mod=5, stain_encoding=True), strict=True)
+    model.eval()
+    bs = 32
+    g = torch.Generator().manual_seed(0)
+    labels = (torch.rand(bs, 5, generator=g) < torch.tensor([1.0, 0.46, 0.73, 0.73, 0.73])).float()
+    labels[:, 0] = 1
+    feats = torch.randn(bs, 5, T, 512, generator=g) * labels[:, :, None, None]
+    args = Namespace(global_loss="info-nce", symmetric_cl=True, local_loss_weight=1.0)
+    t0 = time.time()
+    embs, toks = model({"feats": feats}, "cpu", train=True, n_views=1)
+    torch.manual_seed(11)
+    loss, flag = calculate_losses(mods[1:], InfoNCE(temperature=TAU), GOT, None, embs, toks, labels[:, 1:], args)
+    model.zero_grad()
+    loss.backward()
+    out = {"meta": {"torch": torch.__version__, "device": "cpu", "dtype": "float32", "reference": "mahmoodlab/MADELEINE@419287dc",
+                    "seconds": time.time() - t0},
+           "T": T, "bs": bs, "tau": TAU, "loss_seed": 11, "labels": labels, "x_checksum": float(feats.double().abs().sum()),
+           "embs": {m: embs[m].detach().clone() for m in mods}, "tok_sum": {m: float(toks[m].detach().double().sum()) for m in mods},
+           "tok_head": {m: toks[m].detach()[:, :2].clone() for m in mods}, "loss": loss.detach().clone(), "flag": flag, "grads": digest(model)}
+    path = os.path.join(HERE, "baseline_config3_t512.pt")
+    torch.save(out, path)
+    print(f"wrote {path} ({os.path.getsize(path) / 1024:.1f} KiB); loss {float(loss.detach()):.6f}; {out['meta']['seconds']:.1f} s")
+
+
 if __name__ == "__main__":
-    main()
+    if "--config3" in sys.argv:
+        config3()
+    else:
+        main()

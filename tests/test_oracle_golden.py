@@ -235,3 +235,33 @@ def test_oracle_at_baseline_size_against_the_real_reference(golden):
             assert float(sd[name].grad.double().norm()) < 1e-6 * total, name
             continue
         assert float(sd[name].grad.double().norm()) == pytest.approx(ref, rel=1e-3), name
+
+
+def test_oracle_config3_shape_against_the_real_reference(golden):
+    """BASELINE configs[2] shape (32 cases x 5 stains, stain encodings, ACROBAT availability rates, InfoNCE tau = 0.001 + GOT) at 512
+    tokens per bag — the largest size the reference's monolithic autograd tape allows in the build container — against the real
+    reference's forward(train=True) + calculate_losses + backward (tests/golden/baseline_config3_t512.pt)."""
+    g = golden("baseline_config3_t512")
+    mods = ["HE", "HER2", "PGR", "KI67", "ER"]
+    gen = torch.Generator().manual_seed(0)
+    labels = (torch.rand(g["bs"], 5, generator=gen) < torch.tensor([1.0, 0.46, 0.73, 0.73, 0.73])).float()
+    labels[:, 0] = 1
+    assert torch.equal(labels, g["labels"])
+    feats = torch.randn(g["bs"], 5, g["T"], 512, generator=gen) * labels[:, :, None, None]
+    assert float(feats.double().abs().sum()) == pytest.approx(g["x_checksum"], rel=1e-12)
+    sd = {k: v.clone().requires_grad_(True) for k, v in make_state_dict(3, n_mod=5, stain_encoding=True).items()}
+    embs, toks = oracle.madeleine_forward_train(sd, feats, mods, stain_encoding=True)
+    torch.manual_seed(g["loss_seed"])
+    loss, flag = oracle.calculate_losses(mods[1:], embs, toks, labels[:, 1:], temperature=g["tau"], symmetric=True, use_local=True)
+    loss.backward()
+    assert flag == g["flag"]
+    for m in mods:
+        close(embs[m].detach(), g["embs"][m], rtol=1e-4, atol=1e-5)
+        close(toks[m].detach()[:, :2], g["tok_head"][m], rtol=1e-4, atol=1e-5)
+    assert float(loss.detach()) == pytest.approx(float(g["loss"]), rel=1e-4)
+    total = sum(float(d["norm"]) ** 2 for d in g["grads"].values()) ** 0.5
+    for name, d in g["grads"].items():
+        ref = float(d["norm"])
+        if ref < 1e-6 * total:
+            continue
+        assert float(sd[name].grad.double().norm()) == pytest.approx(ref, rel=2e-2), name

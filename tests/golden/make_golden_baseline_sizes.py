@@ -30,7 +30,7 @@ assert madeleine.__file__.startswith("/root/reference"), madeleine.__file__
 from madeleine.models.Model import MADELEINE  # noqa: E402
 from madeleine.utils.loss import InfoNCE, GOT  # noqa: E402
 from madeleine.utils.trainer import calculate_losses  # noqa: E402
-from weights import make_state_dict  # noqa: E402
+from weights import make_state_dict, make_feats  # noqa: E402
 
 torch.set_num_threads(os.cpu_count() or 8)
 torch.backends.cuda.matmul.allow_tf32 = False
@@ -122,8 +122,35 @@ def config3(T=512):
     print(f"wrote {path} ({os.path.getsize(path) / 1024:.1f} KiB); loss {float(loss.detach()):.6f}; {out['meta']['seconds']:.1f} s")
 
 
+def inference():
+    """BASELINE configs[4] shape: slides of 4000 x 512 through the reference's inference entry points, H&E model without stain
+    encodings.  `encode_he` (Model.py:95-106, what bin/extract_slide_embeddings.py calls) for six slides, and
+    `forward(train=False, return_attention=True)` (Model.py:205-216) for two of them: the slide embedding plus the raw attention
+    logits [1, 4000, 1, 4] whose ranking is the "attention indices" of the north star."""
+    cfg = Namespace(MODALITIES=["HE"], wsi_encoder="abmil", patch_embedding_dim=512, wsi_encoder_hidden_dim=512, activation="softmax", n_heads=4)
+    model = MADELEINE(cfg, stain_encoding=False)
+    model.load_state_dict(make_state_dict(0), strict=True)
+    model.eval()
+    out = {"meta": {"torch": torch.__version__, "device": "cpu", "dtype": "float32", "reference": "mahmoodlab/MADELEINE@419287dc"},
+           "seed_w": 0, "n_tokens": 4000, "seeds": list(range(100, 106)), "encode_he": [], "attention": {}}
+    with torch.no_grad():
+        for seed in out["seeds"]:
+            x = make_feats(seed, 1, 4000, 512)
+            out["encode_he"].append(model.encode_he(x, "cpu").clone())
+        for seed in out["seeds"][:2]:
+            x = make_feats(seed, 1, 1, 4000, 512)
+            emb, raw = model({"feats": x}, "cpu", train=False, return_attention=True)
+            out["attention"][seed] = {"emb": emb.clone(), "raw": raw.clone()}
+    out["encode_he"] = torch.cat(out["encode_he"])
+    path = os.path.join(HERE, "baseline_inference.pt")
+    torch.save(out, path)
+    print(f"wrote {path} ({os.path.getsize(path) / 1024:.1f} KiB)")
+
+
 if __name__ == "__main__":
     if "--config3" in sys.argv:
         config3()
+    elif "--inference" in sys.argv:
+        inference()
     else:
         main()

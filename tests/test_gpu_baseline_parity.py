@@ -25,7 +25,7 @@ pytestmark = pytest.mark.gpu
 from madeleine.models.Model import MADELEINE  # noqa: E402
 from madeleine.utils.loss import InfoNCE, GOT  # noqa: E402
 from madeleine.utils.trainer import calculate_losses  # noqa: E402
-from weights import make_state_dict  # noqa: E402
+from weights import make_state_dict, make_feats  # noqa: E402
 
 DEV = torch.device("cuda")
 RTOL, ATOL = 1e-3, 1e-4                  # north star: slide embeddings and loss
@@ -306,3 +306,35 @@ def test_attention_rank_statistics_at_baseline_sizes(T):
     assert ours["identical_rank_fraction"] >= 0.995, ours
     assert train_fmt["max_abs_logit_error"] <= 1e-5 and train_fmt["identical_rank_fraction"] >= 0.975, train_fmt
     assert train_fmt["top8_identical"]
+
+
+# ------------------------------------------------------------------------------------------------------------------ (v)
+def test_inference_at_4000_tokens_against_the_real_reference(golden):
+    """BASELINE configs[4] shape against the REAL reference (tests/golden/baseline_inference.pt): the extraction driver on six
+    4000-patch slides vs the reference's `encode_he`, and `forward(train=False, return_attention=True)` vs the reference's slide
+    embedding and raw attention logits — "attention indices": the whole argsort per head against the reference's own fp32 ranking
+    (two fp32-grade evaluations of the same logits; they can only differ where the reference's logits nearly tie)."""
+    import parity_utils as pu
+    from madeleine_b200.utils.inference import extract_slide_embeddings
+    g = golden("baseline_inference")
+    model = _model(["HE"], make_state_dict(g["seed_w"]), False)
+    bags = [make_feats(seed, g["n_tokens"], 512) for seed in g["seeds"]]
+    emb, order = extract_slide_embeddings(model, bags, DEV)
+    assert order == list(range(len(bags)))
+    torch.testing.assert_close(torch.from_numpy(emb), g["encode_he"], rtol=RTOL, atol=ATOL)
+    stats = {}
+    for seed, att in g["attention"].items():
+        x = make_feats(seed, 1, 1, g["n_tokens"], 512)
+        with torch.no_grad():
+            e, raw = model({"feats": x}, DEV, train=False, return_attention=True)
+        assert raw.shape == att["raw"].shape and e.shape == att["emb"].shape
+        torch.testing.assert_close(e.cpu(), att["emb"], rtol=RTOL, atol=ATOL)
+        torch.testing.assert_close(raw.cpu(), att["raw"], rtol=RTOL, atol=ATOL)
+        st = pu.rank_statistics(raw.cpu(), att["raw"])
+        stats[seed] = st
+        assert st["top8_identical"]
+        assert st["identical_rank_fraction"] > 0.99
+        assert st["max_reference_logit_gap_at_mismatch"] < 1e-5          # only near-ties of the reference's own logits flip
+    _report("inference_4000_tokens_vs_real_reference",
+            {"encode_he_max_abs_err": float((torch.from_numpy(emb).double() - g["encode_he"].double()).abs().max()),
+             "attention_rank_vs_reference_fp32": {str(k): v for k, v in stats.items()}, "reference": g["meta"]})

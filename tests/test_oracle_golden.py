@@ -265,3 +265,17 @@ def test_oracle_config3_shape_against_the_real_reference(golden):
         if ref < 1e-6 * total:
             continue
         assert float(sd[name].grad.double().norm()) == pytest.approx(ref, rel=2e-2), name
+
+
+def test_oracle_inference_at_4000_tokens_against_the_real_reference(golden):
+    """BASELINE configs[4] shape (tests/golden/baseline_inference.pt): `encode_he` of six 4000-patch slides and the raw attention
+    logits of two of them from the real reference."""
+    g = golden("baseline_inference")
+    sd = make_state_dict(g["seed_w"])
+    for k, seed in enumerate(g["seeds"]):
+        x = make_feats(seed, 1, g["n_tokens"], 512)
+        close(oracle.encode_he(sd, x), g["encode_he"][k:k + 1])
+    for seed, att in g["attention"].items():
+        x = make_feats(seed, 1, 1, g["n_tokens"], 512)
+        _, _, raw = oracle.abmil_embedder(sd, x[:, 0])
+        close(raw.reshape(att["raw"].shape), att["raw"], rtol=1e-4, atol=2e-5)

@@ -147,8 +147,43 @@ def inference():
     print(f"wrote {path} ({os.path.getsize(path) / 1024:.1f} KiB)")
 
 
+def config4_global_batch():
+    """BASELINE configs[3]: batch = 64 cases (x 2 stains x 2000 patches = 256 000 tokens), the batch that 8 ranks x 8 cases shard,
+    evaluated by the reference as ONE global batch: `forward(train=True)`'s encoder + projector per case (the reference's own
+    modules; a monolithic call would need ~31 GB of autograd tape), `InfoNCE` (tau = 0.001, symmetric) over the 64 HE / IHC pairs
+    through `calculate_losses`, and backward in two stages (loss -> slide embeddings, then case by case into the parameters: the
+    same gradients as one tape, by the chain rule)."""
+    mods = ["HE", "IHC"]
+    cfg = Namespace(MODALITIES=mods, wsi_encoder="abmil", patch_embedding_dim=512, wsi_encoder_hidden_dim=512, activation="softmax", n_heads=4)
+    model = MADELEINE(cfg, stain_encoding=False)
+    model.load_state_dict(make_state_dict(0, n_mod=2), strict=True)
+    model.eval()
+    bs, T = 64, 2000
+    feats = make_feats(64, bs, 2, T, 512)
+    args = Namespace(global_loss="info-nce", symmetric_cl=True, local_loss_weight=1.0)
+    t0 = time.time()
+    with torch.no_grad():
+        parts = [model({"feats": feats[c:c + 1]}, "cpu", train=True, n_views=1)[0] for c in range(bs)]
+    embs = {m: torch.cat([p[m] for p in parts]).requires_grad_(True) for m in mods}      # HE [64, 1, 512, 1], IHC [64, 1, 512]
+    loss, flag = calculate_losses(mods[1:], InfoNCE(temperature=TAU), None, None, embs, None, torch.ones(bs, 1), args)
+    loss.backward()
+    model.zero_grad()
+    for c in range(bs):
+        e, _ = model({"feats": feats[c:c + 1]}, "cpu", train=True, n_views=1)
+        torch.autograd.backward([e[m] for m in mods], [embs[m].grad[c:c + 1] for m in mods])
+    out = {"meta": {"torch": torch.__version__, "device": "cpu", "dtype": "float32", "reference": "mahmoodlab/MADELEINE@419287dc",
+                    "seconds": time.time() - t0},
+           "bs": bs, "T": T, "seed_x": 64, "tau": TAU, "x_checksum": float(feats.double().abs().sum()),
+           "embs": {m: embs[m].detach().clone() for m in mods}, "loss": loss.detach().clone(), "flag": flag, "grads": digest(model)}
+    path = os.path.join(HERE, "baseline_config4_global.pt")
+    torch.save(out, path)
+    print(f"wrote {path} ({os.path.getsize(path) / 1024:.1f} KiB); loss {float(loss.detach()):.6f}; {out['meta']['seconds']:.1f} s")
+
+
 if __name__ == "__main__":
-    if "--config3" in sys.argv:
+    if "--config4" in sys.argv:
+        config4_global_batch()
+    elif "--config3" in sys.argv:
         config3()
     elif "--inference" in sys.argv:
         inference()

@@ -338,3 +338,43 @@ def test_inference_at_4000_tokens_against_the_real_reference(golden):
     _report("inference_4000_tokens_vs_real_reference",
             {"encode_he_max_abs_err": float((torch.from_numpy(emb).double() - g["encode_he"].double()).abs().max()),
              "attention_rank_vs_reference_fp32": {str(k): v for k, v in stats.items()}, "reference": g["meta"]})
+
+
+# ----------------------------------------------------------------------------------------------------------------- (vi)
+def test_configs3_global_batch_of_64_cases_against_the_real_reference(golden):
+    """BASELINE configs[3]: the batch of 64 cases x 2 stains x 2000 patches that 8 ranks x 8 cases shard, evaluated here in ONE
+    process and compared with the REAL reference's numbers for the same global batch (tests/golden/baseline_config4_global.pt).
+    `bench.py --gpus N` checks on its line that the sharded step equals this single-process evaluation (loss identical, gradients
+    ~2e-4), which closes the chain sharded == single == reference."""
+    g = golden("baseline_config4_global")
+    mods = ["HE", "IHC"]
+    feats = make_feats(g["seed_x"], g["bs"], 2, g["T"], 512)
+    assert float(feats.double().abs().sum()) == pytest.approx(g["x_checksum"], rel=1e-12)
+    model = _model(mods, make_state_dict(0, n_mod=2), False)
+    args = Namespace(global_loss="info-nce", symmetric_cl=True, local_loss_weight=1.0)
+    embs, toks = model({"feats": feats.to(DEV)}, device=DEV, n_views=1)
+    loss, flag = calculate_losses(mods[1:], InfoNCE(temperature=g["tau"]), None, None, embs, toks, torch.ones(g["bs"], 1), args)
+    assert flag == g["flag"]
+    loss.backward()
+    worst, worst_name = 0.0, ""
+    total = sum(float(d["norm"]) ** 2 for d in g["grads"].values()) ** 0.5
+    for name, p in model.named_parameters():
+        d = g["grads"].get(name)
+        if d is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
+            continue
+        if float(d["norm"]) < 1e-6 * total:
+            continue
+        rel = abs(float(p.grad.double().norm()) - float(d["norm"])) / float(d["norm"])
+        if rel > worst:
+            worst, worst_name = rel, name
+    rep = {"cases": g["bs"], "tokens": g["bs"] * 2 * g["T"], "loss_ours": float(loss.detach()), "loss_reference": float(g["loss"]),
+           "loss_rel": abs(float(loss.detach()) - float(g["loss"])) / abs(float(g["loss"])),
+           "emb_violation": {m: _max_violation(embs[m].cpu(), g["embs"][m]) for m in mods},
+           "grad_norm_rel_err_max": worst, "worst_param": worst_name, "reference": g["meta"]}
+    _report("configs3_global_batch_vs_real_reference", rep)
+    for m in mods:
+        assert embs[m].shape == g["embs"][m].shape
+        torch.testing.assert_close(embs[m].detach().cpu(), g["embs"][m], rtol=RTOL, atol=ATOL)
+    assert rep["loss_rel"] < 1e-3
+    assert worst < 3e-2, (worst_name, worst)

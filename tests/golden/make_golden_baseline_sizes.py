@@ -180,8 +180,34 @@ def config4_global_batch():
     print(f"wrote {path} ({os.path.getsize(path) / 1024:.1f} KiB); loss {float(loss.detach()):.6f}; {out['meta']['seconds']:.1f} s")
 
 
+def got_shipped_batch():
+    """GOT (loss.py:278-301) at the reference's shipped batch size and at the boundary of the shared-memory kernel: 65 and 96 cases
+    with the stain (problems of 65 / 96 tokens, quirk Q3), token embeddings [m, m + 16, 128].  Loss, gradient norms, the full gradient
+    of the first two cases and 512 sampled entries."""
+    out = {"meta": {"torch": torch.__version__, "device": "cpu", "dtype": "float32", "reference": "mahmoodlab/MADELEINE@419287dc"}, "cases": []}
+    for m in (65, 96):
+        v = make_feats(700 + m, m, m + 16, 128).requires_grad_(True)
+        q = (v.detach() + 0.5 * make_feats(800 + m, m, m + 16, 128)).requires_grad_(True)
+        torch.manual_seed(2000 + m)
+        loss = GOT(v, q, subsample=256)
+        loss.backward()
+        case = {"m": m, "torch_seed": 2000 + m, "seed_v": 700 + m, "seed_q": 800 + m, "loss": loss.detach().clone()}
+        for nm, t in (("dv", v.grad), ("dq", q.grad)):
+            flat = t.flatten()
+            idx = torch.randint(0, flat.numel(), (512,), generator=torch.Generator().manual_seed(m))
+            case[nm] = {"norm": flat.double().norm(), "idx": idx, "samples": flat[idx].clone(), "first2": t[:2].clone(),
+                        "beyond_m_abs_max": float(t[:, m:].abs().max())}
+        out["cases"].append(case)
+        print(f"m = {m}: loss {float(loss.detach()):.6f}")
+    path = os.path.join(HERE, "got_shipped_batch.pt")
+    torch.save(out, path)
+    print(f"wrote {path} ({os.path.getsize(path) / 1024:.1f} KiB)")
+
+
 if __name__ == "__main__":
-    if "--config4" in sys.argv:
+    if "--got65" in sys.argv:
+        got_shipped_batch()
+    elif "--config4" in sys.argv:
         config4_global_batch()
     elif "--config3" in sys.argv:
         config3()

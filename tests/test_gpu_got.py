@@ -136,3 +136,24 @@ def test_got_subsample_256_of_a_large_batch():
     torch.manual_seed(3)
     full = GOT(v.to(DEV), q.to(DEV), subsample=256)            # all 260 problems of 256 tokens in one call
     assert bool(torch.isfinite(full))
+
+
+def test_got_at_the_shipped_batch_size_against_the_real_reference(golden):
+    """65 cases with the stain (the reference's shipped batch of 65: problems of 65 tokens) and 96 (the largest problem of the
+    shared-memory kernel) against the REAL reference (tests/golden/got_shipped_batch.pt): loss, gradient norms, the full gradient of
+    two cases and 512 sampled entries."""
+    from weights import make_feats
+    for c in golden("got_shipped_batch")["cases"]:
+        m = c["m"]
+        v0 = make_feats(c["seed_v"], m, m + 16, 128)
+        q0 = v0 + 0.5 * make_feats(c["seed_q"], m, m + 16, 128)
+        v, q = v0.to(DEV).requires_grad_(True), q0.to(DEV).requires_grad_(True)
+        torch.manual_seed(c["torch_seed"])
+        loss = GOT(v, q, subsample=256)
+        loss.backward()
+        torch.testing.assert_close(loss.detach().cpu(), c["loss"], rtol=1e-3, atol=1e-4)
+        for t, d in ((v.grad.cpu(), c["dv"]), (q.grad.cpu(), c["dq"])):
+            assert float(t.double().norm()) == pytest.approx(float(d["norm"]), rel=2e-2)
+            torch.testing.assert_close(t[:2], d["first2"], rtol=2e-2, atol=2e-3 * float(d["first2"].abs().max()))
+            torch.testing.assert_close(t.flatten()[d["idx"]], d["samples"], rtol=2e-2, atol=2e-3 * float(d["samples"].abs().max()))
+            assert float(t[:, m:].abs().max()) == 0.0

@@ -279,3 +279,20 @@ def test_oracle_inference_at_4000_tokens_against_the_real_reference(golden):
         x = make_feats(seed, 1, 1, g["n_tokens"], 512)
         _, _, raw = oracle.abmil_embedder(sd, x[:, 0])
         close(raw.reshape(att["raw"].shape), att["raw"], rtol=1e-4, atol=2e-5)
+
+
+def test_oracle_got_at_the_shipped_batch_size_against_the_real_reference(golden):
+    """GOT on 65 cases (the reference's shipped batch: problems of 65 tokens) and on 96 (the largest problem of the shared-memory
+    kernel), tests/golden/got_shipped_batch.pt."""
+    for c in golden("got_shipped_batch")["cases"]:
+        m = c["m"]
+        v = make_feats(c["seed_v"], m, m + 16, 128).requires_grad_(True)
+        q = (v.detach() + 0.5 * make_feats(c["seed_q"], m, m + 16, 128)).requires_grad_(True)
+        torch.manual_seed(c["torch_seed"])
+        loss = oracle.got(v, q, subsample=256)
+        loss.backward()
+        close(loss.detach(), c["loss"], rtol=1e-4, atol=1e-5)
+        for t, d in ((v.grad, c["dv"]), (q.grad, c["dq"])):
+            assert float(t.double().norm()) == pytest.approx(float(d["norm"]), rel=1e-3)
+            close(t[:2], d["first2"], rtol=1e-2, atol=1e-3 * float(d["first2"].abs().max()))
+            assert float(t[:, m:].abs().max()) == d["beyond_m_abs_max"] == 0.0

@@ -126,7 +126,7 @@ def encode_packed(sd, feats: torch.Tensor, cu_seqlens: Sequence[int]) -> torch.T
 
 
 def madeleine_forward_train(sd, feats: torch.Tensor, modalities: List[str], stain_encoding: bool = False,
-                            n_views: int = 1):
+                            n_views: int = 1, activation: str = "softmax"):
     """MADELEINE.forward(train=True) (Model.py:110-159), including quirk Q1 (row r gets stain code r // bs)."""
     bs, n_mod, T, D = feats.shape
     x = feats.reshape(bs * n_mod, T, D)
@@ -134,7 +134,7 @@ def madeleine_forward_train(sd, feats: torch.Tensor, modalities: List[str], stai
         ind = torch.tensor([i for i in range(n_mod) for _ in range(bs)], dtype=torch.long, device=feats.device)
         enc = sd["embedding.weight"][ind]                       # [bs*n_mod, 32]
         x = torch.cat([x, enc.unsqueeze(1).expand(-1, T, -1)], dim=-1)
-    slide, tok, _ = abmil_embedder(sd, x, n_views=n_views)
+    slide, tok, _ = abmil_embedder(sd, x, n_views=n_views, activation=activation)      # config.activation (Model.py:63-70)
     tok = tok.reshape(bs, n_mod, T, -1)
     tok = _lin(tok, sd["token_projector.weight"], sd["token_projector.bias"])
     E, H = slide.shape[-2], slide.shape[-1]

@@ -204,8 +204,39 @@ def got_shipped_batch():
     print(f"wrote {path} ({os.path.getsize(path) / 1024:.1f} KiB)")
 
 
+def n_views3_backward():
+    """forward(train=True, n_views=3) (Model.py:419-440: whole view + two random half views, numpy's global RNG) + calculate_losses with
+    the global AND the intra-modality InfoNCE (trainer.py:52-66), backward: 6 cases x 2 stains x 300 patches, tau = 0.1, for the
+    four attention activations.  Embeddings of all three views, loss, gradient digests."""
+    import numpy as np
+    out = {"meta": {"torch": torch.__version__, "numpy": np.__version__, "device": "cpu", "dtype": "float32",
+                    "reference": "mahmoodlab/MADELEINE@419287dc"}, "np_seed": 77, "seed_x": 5, "seed_w": 21, "shape": (6, 2, 300, 512), "tau": 0.1,
+           "activations": {}}
+    mods = ["HE", "IHC"]
+    args = Namespace(global_loss="info-nce", symmetric_cl=True, local_loss_weight=1.0)
+    for activation in ("softmax", "relu", "leaky_relu", "sigmoid"):
+        cfg = Namespace(MODALITIES=mods, wsi_encoder="abmil", patch_embedding_dim=512, wsi_encoder_hidden_dim=512, activation=activation, n_heads=4)
+        model = MADELEINE(cfg, stain_encoding=False)
+        model.load_state_dict(make_state_dict(21, n_mod=2), strict=True)
+        model.eval()
+        feats = make_feats(5, 6, 2, 300, 512)
+        fn = InfoNCE(temperature=0.1)
+        np.random.seed(77)
+        embs, toks = model({"feats": feats}, "cpu", train=True, n_views=3)
+        loss, flag = calculate_losses(mods[1:], fn, None, fn, embs, toks, torch.ones(6, 1), args)
+        model.zero_grad()
+        loss.backward()
+        out["activations"][activation] = {"embs": {m: embs[m].detach().clone() for m in mods}, "loss": loss.detach().clone(), "grads": digest(model)}
+        print(activation, float(loss.detach()))
+    path = os.path.join(HERE, "n_views3_backward.pt")
+    torch.save(out, path)
+    print(f"wrote {path} ({os.path.getsize(path) / 1024:.1f} KiB)")
+
+
 if __name__ == "__main__":
-    if "--got65" in sys.argv:
+    if "--nviews3" in sys.argv:
+        n_views3_backward()
+    elif "--got65" in sys.argv:
         got_shipped_batch()
     elif "--config4" in sys.argv:
         config4_global_batch()

@@ -378,3 +378,39 @@ def test_configs3_global_batch_of_64_cases_against_the_real_reference(golden):
         torch.testing.assert_close(embs[m].detach().cpu(), g["embs"][m], rtol=RTOL, atol=ATOL)
     assert rep["loss_rel"] < 1e-3
     assert worst < 3e-2, (worst_name, worst)
+
+
+# ---------------------------------------------------------------------------------------------------------------- (vii)
+@pytest.mark.parametrize("activation", ["softmax", "relu", "leaky_relu", "sigmoid"])
+def test_n_views3_forward_backward_against_the_real_reference(golden, activation):
+    """forward(train=True, n_views=3) + global and intra-modality InfoNCE + backward against the REAL reference
+    (tests/golden/n_views3_backward.pt; Model.py:419-440, trainer.py:52-66): all three views' embeddings, the loss and every
+    parameter's gradient norm."""
+    g = golden("n_views3_backward")
+    ga = g["activations"][activation]
+    mods = ["HE", "IHC"]
+    model = _model(mods, make_state_dict(g["seed_w"], n_mod=2), False, activation=activation)
+    feats = make_feats(g["seed_x"], *g["shape"]).to(DEV)
+    args = Namespace(global_loss="info-nce", symmetric_cl=True, local_loss_weight=1.0)
+    fn = InfoNCE(temperature=g["tau"])
+    np.random.seed(g["np_seed"])
+    embs, toks = model({"feats": feats}, device=DEV, n_views=3)
+    loss, _ = calculate_losses(mods[1:], fn, None, fn, embs, toks, torch.ones(g["shape"][0], 1), args)
+    loss.backward()
+    worst, worst_name = 0.0, ""
+    total = sum(float(d["norm"]) ** 2 for d in ga["grads"].values()) ** 0.5
+    for name, p in model.named_parameters():
+        d = ga["grads"].get(name)
+        if d is None or float(d["norm"]) < 1e-6 * total:
+            continue
+        rel = abs(float(p.grad.double().norm()) - float(d["norm"])) / float(d["norm"])
+        if rel > worst:
+            worst, worst_name = rel, name
+    _report("n_views3_fwd_bwd_vs_real_reference", {"activation": activation, "loss_ours": float(loss.detach()), "loss_reference": float(ga["loss"]),
+                                                   "grad_norm_rel_err_max": worst, "worst_param": worst_name})
+    for m in mods:
+        assert embs[m].shape == ga["embs"][m].shape
+        scale = 1.0 if activation == "softmax" else max(1.0, float(ga["embs"][m].abs().max()))      # un-normalised sums, see (iii)
+        torch.testing.assert_close(embs[m].detach().cpu(), ga["embs"][m], rtol=RTOL, atol=ATOL * scale)
+    assert float(loss.detach()) == pytest.approx(float(ga["loss"]), rel=1e-3)
+    assert worst < GRAD_RTOL, (worst_name, worst)

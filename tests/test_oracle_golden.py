@@ -296,3 +296,26 @@ def test_oracle_got_at_the_shipped_batch_size_against_the_real_reference(golden)
             assert float(t.double().norm()) == pytest.approx(float(d["norm"]), rel=1e-3)
             close(t[:2], d["first2"], rtol=1e-2, atol=1e-3 * float(d["first2"].abs().max()))
             assert float(t[:, m:].abs().max()) == d["beyond_m_abs_max"] == 0.0
+
+
+@pytest.mark.parametrize("activation", ["softmax", "relu", "leaky_relu", "sigmoid"])
+def test_oracle_n_views3_forward_backward_against_the_real_reference(golden, activation):
+    """forward(train=True, n_views=3) + global and intra-modality InfoNCE + backward (tests/golden/n_views3_backward.pt)."""
+    g = golden("n_views3_backward")
+    ga = g["activations"][activation]
+    mods = ["HE", "IHC"]
+    sd = {k: v.clone().requires_grad_(True) for k, v in make_state_dict(g["seed_w"], n_mod=2).items()}
+    feats = make_feats(g["seed_x"], *g["shape"])
+    np.random.seed(g["np_seed"])
+    embs, toks = oracle.madeleine_forward_train(sd, feats, mods, n_views=3, activation=activation)
+    loss, _ = oracle.calculate_losses(mods[1:], embs, toks, torch.ones(g["shape"][0], 1), temperature=g["tau"], symmetric=True, use_intra=True)
+    loss.backward()
+    for m in mods:
+        scale = max(1.0, float(ga["embs"][m].abs().max()))
+        close(embs[m].detach(), ga["embs"][m], rtol=1e-4, atol=1e-5 * scale)
+    assert float(loss.detach()) == pytest.approx(float(ga["loss"]), rel=1e-5)
+    total = sum(float(d["norm"]) ** 2 for d in ga["grads"].values()) ** 0.5
+    for name, d in ga["grads"].items():
+        if float(d["norm"]) < 1e-6 * total:
+            continue
+        assert float(sd[name].grad.double().norm()) == pytest.approx(float(d["norm"]), rel=1e-3), name

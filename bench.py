@@ -447,8 +447,8 @@ def main():
                     worst, worst_name = err, n
                 o += k
             out = {"what": f"sharded step on {world} ranks vs the same global batch ({world * B} cases) on rank 0 alone, eval mode",
-                   "loss_sharded": float(loss_sh), "loss_single": float(loss_1),
-                   "loss_rel": abs(float(loss_sh) - float(loss_1)) / max(abs(float(loss_1)), 1e-12),
+                   "loss_sharded": float(loss_sh), "loss_single": float(loss_1.detach()),
+                   "loss_rel": abs(float(loss_sh) - float(loss_1.detach())) / max(abs(float(loss_1.detach())), 1e-12),
                    "grad_rel": float((g_sh.double() - g_1.double()).norm()) / total,
                    "grad_rel_worst_param": worst, "worst_param": worst_name}
             parallel.enable_gradient_sync(True)

@@ -493,13 +493,19 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    _lib.start_timing({"mdl_pool_fwd", "mdl_pool_weights", "mdl_pool_bwd_dlogit", "mdl_gemm_nt", "mdl_gemm_gated", "mdl_gemm_tn_accum"})
+    # Inside the timed region only the pooling launches (the metric's named kernel: `roofline`) are bracketed with CUDA events; the
+    # GEMM launches are timed in a second pass of K steps right after it (`roofline_gemm`, `kernel_ms_per_step`): 24 more event
+    # records per step would sit between kernels that otherwise chain through programmatic dependent launch.
+    _lib.start_timing({"mdl_pool_fwd", "mdl_pool_weights", "mdl_pool_bwd_dlogit"})
     _lib.launch_count[0] = 0
     _lib.native_launches(reset=True)
     ms_step = timed(args.steps, lambda i: feats_dev, read_loss=False)
     launches = (_lib.launch_count[0] + _lib.native_launches()) // args.steps
     clocks = sampler.stop() if rank == 0 else None
     kt = _lib.stop_timing()
+    _lib.start_timing({"mdl_gemm_nt", "mdl_gemm_gated", "mdl_gemm_tn_accum"})
+    timed(args.steps, lambda i: feats_dev, read_loss=False)
+    kt.update(_lib.stop_timing())
 
     bags_per_step = B * N_STAINS * world
     value = bags_per_step / (ms_step * 1e-3)
@@ -684,7 +690,8 @@ def main():
     roofline_gemm = {"kernel": "gemm_tcgen05_kernel (all forward/dgrad/wgrad GEMMs of a step)", "bound": "tensor", "achieved": tf,
                      "achieved_bf16_issue": tf * issued, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": tf / peaks["bf16_tflops_sustained"], "frac_bf16_issue": tf * issued / peaks["bf16_tflops_sustained"],
-                     "ms_per_step": gemm_ms, "note": "algorithmic fp32-equivalent FLOPs; the 3-pass split-bf16 mode issues 3x on the tensor pipe"}
+                     "ms_per_step": gemm_ms, "note": "algorithmic fp32-equivalent FLOPs; the 3-pass split-bf16 mode issues 3x on the tensor pipe; timed in a "
+                     "second pass of K steps right after the timed region"}
     pool_bwd_ms = statistics.mean(kt["mdl_pool_bwd_dlogit"]) if kt.get("mdl_pool_bwd_dlogit") else None
     roofline["pool_weights_avg_launch_ms"] = statistics.mean(kt["mdl_pool_weights"]) if kt.get("mdl_pool_weights") else None
 

@@ -72,6 +72,20 @@ def main():
                     "seconds": time.time() - t0},
            "lens": lens, "tau": TAU, "x_checksum": float(x.double().abs().sum()), "slide": slide.detach().clone(), "loss": loss.detach().clone(),
            "grads": grads}
+    # For context (reported next to this repo's bf16 mode, not a parity target): the same evaluation under torch.autocast(bfloat16), the
+    # precision the reference's scripts train in (trainer.py:108 wraps forward AND loss).  The in-batch logits are then a bf16 matmul of
+    # +-1000-sized values (tau = 0.001): the loss and the gradients come out far from the fp32 ones.
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        ac = torch.cat([model.projector(model.wsi_embedders(x[cu[r]:cu[r + 1]].unsqueeze(0)).reshape(1, -1)) for r in range(32)])
+        ac_loss = InfoNCE(temperature=TAU)(query=ac[:16], positive_key=ac[16:], symmetric=True)
+    model.zero_grad()
+    ac_loss.backward()
+    total = sum(float(d["norm"]) ** 2 for d in grads.values()) ** 0.5
+    worst = max(abs(float(p.grad.double().norm()) - float(grads[n]["norm"])) / float(grads[n]["norm"])
+                for n, p in model.named_parameters() if n in grads and float(grads[n]["norm"]) >= 1e-6 * total)
+    out["autocast_bf16_cpu"] = {"slide": ac.detach().float().clone(), "loss": ac_loss.detach().float().clone(),
+                                "emb_max_abs_err_vs_fp32": float((ac.detach().float() - slide.detach()).abs().max()),
+                                "grad_norm_rel_err_max_vs_fp32": worst}
     path = os.path.join(HERE, "baseline_sizes.pt")
     torch.save(out, path)
     print(f"wrote {path} ({os.path.getsize(path) / 1024:.1f} KiB); loss {float(loss):.6f}; {out['meta']['seconds']:.1f} s")

@@ -452,6 +452,13 @@ def test_precision_modes_against_the_real_reference_at_baseline_size(golden, pre
            "emb_max_abs_err": float((slide.detach().float().cpu().double() - g["slide"].double()).abs().max()),
            "emb_violation_of_north_star_budget": _max_violation(slide.detach().float().cpu(), g["slide"]),
            "grad_norm_rel_err_max": norm_err, "grad_samples_rel_err_max": samp_err}
+    ac = g.get("autocast_bf16_cpu")
+    if ac is not None and precision == "bf16":
+        # context: the REFERENCE under torch.autocast(bfloat16) (what its scripts train in) against its own fp32 numbers
+        rep["reference_autocast_bf16_vs_its_fp32"] = {"emb_max_abs_err": ac["emb_max_abs_err_vs_fp32"], "loss": float(ac["loss"]),
+                                                      "loss_rel": abs(float(ac["loss"]) - float(g["loss"])) / abs(float(g["loss"])),
+                                                      "grad_norm_rel_err_max": ac["grad_norm_rel_err_max_vs_fp32"]}
+        assert rep["emb_max_abs_err"] <= ac["emb_max_abs_err_vs_fp32"]      # the bf16 mode is at least as close to fp32 as the reference's autocast
     _report("precision_modes_vs_real_reference_configs1", rep)
     assert rep["emb_violation_of_north_star_budget"] < emb_tol
     assert norm_err < grad_tol
